@@ -1,0 +1,265 @@
+"""ctypes binding of librt_b200.so (the C ABI in include/rt_b200.h) — what a Python caller, the
+tests and bench.py use.  Mirrors the reference's own seams: `Scene` is reference `scene::Scene`
+(src/scene.rs:82-90) after `Scene::new` / `gltf::build_scene`; `Context.render()` is
+`generate_image(&scene)` (src/main.rs:85).  There is no CPU fallback: `Context()` raises when no
+CUDA device is present, and importing never silently substitutes another implementation."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from . import ctypes_types as T
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "librt_b200.so")
+_LIB = None
+
+# every symbol include/rt_b200.h declares (tests check that the library exports each of them)
+SYMBOLS = [
+    "rt_scene_build", "rt_scene_free", "rt_scene_load_text", "rt_scene_load_gltf", "rt_scene_get_info",
+    "rt_scene_get_bvh", "rt_scene_get_triangle", "rt_scene_get_shape", "rt_scene_get_material", "rt_save_ppm",
+    "rt_device_count", "rt_create", "rt_destroy", "rt_last_error", "rt_upload_scene", "rt_trace_rays",
+    "rt_trace_primary", "rt_light_pdf", "rt_render_accum", "rt_accum_device_ptr", "rt_get_accum", "rt_set_accum",
+    "rt_postprocess", "rt_render", "rt_sync", "rt_stream", "rt_get_counters", "rt_reset_counters", "rt_debug_rng",
+]
+
+
+class RtError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"rt_b200 error {code}: {msg}")
+        self.code = code
+
+
+def build(force=False):
+    """Compiles librt_b200.so + the CLI in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    args = ["make", "-C", os.path.join(_HERE, "csrc"), "-s", "-j8"]
+    if force:
+        args.append("-B")
+    subprocess.check_call(args)
+    return _LIB_PATH
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(_LIB_PATH):
+            raise ImportError(f"{_LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no fallback implementation)")
+        L = C.CDLL(_LIB_PATH)
+        vp, u32, u64, i32, dbl = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_double
+        L.rt_scene_build.argtypes = [C.POINTER(T.RawScene), C.POINTER(vp)]
+        L.rt_scene_free.argtypes = [vp]
+        L.rt_scene_free.restype = None
+        L.rt_scene_load_text.argtypes = [C.c_char_p, C.POINTER(vp)]
+        L.rt_scene_load_gltf.argtypes = [C.c_char_p, u32, u32, u32, C.POINTER(vp)]
+        L.rt_scene_get_info.argtypes = [vp, C.POINTER(T.SceneInfo)]
+        L.rt_scene_get_bvh.argtypes = [vp, i32] + [vp] * 6
+        L.rt_scene_get_triangle.argtypes = [vp, i32, u64, vp, C.POINTER(u32)]
+        L.rt_scene_get_shape.argtypes = [vp, i32, u64, C.POINTER(T.Shape), vp]
+        L.rt_scene_get_material.argtypes = [vp, u32, C.POINTER(T.Material)]
+        L.rt_save_ppm.argtypes = [C.c_char_p, u32, u32, vp]
+        L.rt_device_count.argtypes = [C.POINTER(i32)]
+        L.rt_create.argtypes = [i32, C.POINTER(vp)]
+        L.rt_destroy.argtypes = [vp]
+        L.rt_destroy.restype = None
+        L.rt_last_error.argtypes = [vp]
+        L.rt_last_error.restype = C.c_char_p
+        L.rt_upload_scene.argtypes = [vp, vp]
+        L.rt_trace_rays.argtypes = [vp, i32, u64, vp, vp, vp]
+        L.rt_trace_primary.argtypes = [vp, i32, dbl, dbl, vp, vp]
+        L.rt_light_pdf.argtypes = [vp, i32, u64, vp, vp, vp]
+        L.rt_render_accum.argtypes = [vp, C.POINTER(T.RenderParams)]
+        L.rt_accum_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
+        L.rt_get_accum.argtypes = [vp, vp]
+        L.rt_set_accum.argtypes = [vp, vp]
+        L.rt_postprocess.argtypes = [vp, u32, vp]
+        L.rt_render.argtypes = [vp, u64, i32, i32, vp]
+        L.rt_sync.argtypes = [vp]
+        L.rt_stream.argtypes = [vp, C.POINTER(vp)]
+        L.rt_get_counters.argtypes = [vp, C.POINTER(T.Counters)]
+        L.rt_reset_counters.argtypes = [vp]
+        L.rt_debug_rng.argtypes = [vp, u64, u32, u32, u64, vp, vp]
+        _LIB = L
+    return _LIB
+
+
+def _check(code, ctx=None):
+    if code != 0:
+        raise RtError(code, (lib().rt_last_error(ctx) or b"").decode("utf-8", "replace"))
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a.reshape(shape) if shape is not None else a
+
+
+def device_count():
+    n = C.c_int()
+    lib().rt_device_count(C.byref(n))
+    return n.value
+
+
+class Scene:
+    """Host scene: world-space primitives + the six SAH hierarchies (built on construction)."""
+
+    def __init__(self, handle):
+        self._h = handle
+        info = T.SceneInfo()
+        _check(lib().rt_scene_get_info(self._h, C.byref(info)))
+        self.info = info
+        self.width, self.height, self.samples, self.ray_depth = info.width, info.height, info.samples, info.ray_depth
+
+    @classmethod
+    def from_raw(cls, raw_scene):
+        """Scene::new (src/scene.rs:180) / build_scene on an in-memory description."""
+        raw, keep = raw_scene.as_ctypes()
+        h = C.c_void_p()
+        _check(lib().rt_scene_build(C.byref(raw), C.byref(h)))
+        del keep
+        return cls(h)
+
+    @classmethod
+    def load_text(cls, path):
+        """scene_parser::parse_scene + Scene::new on a text-format file."""
+        h = C.c_void_p()
+        _check(lib().rt_scene_load_text(os.fsencode(path), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def load_gltf(cls, path, width, height, samples):
+        """gltf::parse + gltf::build_scene (src/main.rs:47-66)."""
+        h = C.c_void_p()
+        _check(lib().rt_scene_load_gltf(os.fsencode(path), width, height, samples, C.byref(h)))
+        return cls(h)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().rt_scene_free(self._h)
+            self._h = None
+
+    def bvh(self, which):
+        n, p = int(self.info.bvh_nodes[which]), int(self.info.bvh_prims[which])
+        out = dict(bounds=np.zeros((n, 6)), left=np.zeros(n, np.uint32), right=np.zeros(n, np.uint32),
+                   first=np.zeros(n, np.uint32), count=np.zeros(n, np.uint32), prim_order=np.zeros(p, np.uint32))
+        _check(lib().rt_scene_get_bvh(self._h, which, *[_p(out[k]) for k in ("bounds", "left", "right", "first", "count", "prim_order")]))
+        return out
+
+    def triangle(self, which, i):
+        o = np.zeros(28)
+        m = C.c_uint32()
+        _check(lib().rt_scene_get_triangle(self._h, which, i, _p(o), C.byref(m)))
+        return o, m.value
+
+    def shape(self, which, i):
+        s = T.Shape()
+        bb = np.zeros(6)
+        _check(lib().rt_scene_get_shape(self._h, which, i, C.byref(s), _p(bb)))
+        return s, bb
+
+    def material(self, i):
+        m = T.Material()
+        _check(lib().rt_scene_get_material(self._h, i, C.byref(m)))
+        return m
+
+
+class Context:
+    """One CUDA device.  render() == generate_image (src/main.rs:85-114)."""
+
+    def __init__(self, device=0):
+        h = C.c_void_p()
+        _check(lib().rt_create(device, C.byref(h)))
+        self._h = h
+        self.device = device
+        self.scene = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().rt_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def upload(self, scene):
+        _check(lib().rt_upload_scene(self._h, scene._h), self._h)
+        self.scene = scene
+        return self
+
+    def trace_rays(self, origins, dirs, mode=T.MODE_EXACT):
+        origins, dirs = _f64(origins, (-1, 3)), _f64(dirs, (-1, 3))
+        hits = np.zeros(origins.shape[0], T.HIT_DTYPE)
+        _check(lib().rt_trace_rays(self._h, mode, origins.shape[0], _p(origins), _p(dirs), _p(hits)), self._h)
+        return hits
+
+    def trace_primary(self, jx=0.5, jy=0.5, mode=T.MODE_EXACT, want_rays=False, want_hits=True):
+        n = self.scene.width * self.scene.height
+        hits = np.zeros(n, T.HIT_DTYPE) if want_hits else None
+        rays = np.zeros((n, 6)) if want_rays else None
+        _check(lib().rt_trace_primary(self._h, mode, jx, jy, _p(hits), _p(rays)), self._h)
+        return hits, rays
+
+    def light_pdf(self, pos, dirs, mode=T.MODE_EXACT):
+        pos, dirs = _f64(pos, (-1, 3)), _f64(dirs, (-1, 3))
+        out = np.zeros(pos.shape[0])
+        _check(lib().rt_light_pdf(self._h, mode, pos.shape[0], _p(pos), _p(dirs), _p(out)), self._h)
+        return out
+
+    def render_accum(self, sample_begin, sample_count, seed, mode=T.MODE_FAST, sched=T.SCHED_MEGAKERNEL, clear=False):
+        p = T.RenderParams(sample_begin, sample_count, seed, mode, sched, 1 if clear else 0, 0)
+        _check(lib().rt_render_accum(self._h, C.byref(p)), self._h)
+
+    def accum(self):
+        out = np.zeros((self.scene.height, self.scene.width, 3))
+        _check(lib().rt_get_accum(self._h, _p(out)), self._h)
+        return out
+
+    def set_accum(self, accum):
+        accum = _f64(accum, (self.scene.height, self.scene.width, 3))
+        _check(lib().rt_set_accum(self._h, _p(accum)), self._h)
+
+    def accum_device_ptr(self):
+        p, n = C.c_void_p(), C.c_uint64()
+        _check(lib().rt_accum_device_ptr(self._h, C.byref(p), C.byref(n)), self._h)
+        return p.value, n.value
+
+    def postprocess(self, total_samples):
+        out = np.zeros((self.scene.height, self.scene.width, 3))
+        _check(lib().rt_postprocess(self._h, total_samples, _p(out)), self._h)
+        return out
+
+    def render(self, seed=0xC0FFEE, mode=T.MODE_FAST, sched=T.SCHED_MEGAKERNEL):
+        out = np.zeros((self.scene.height, self.scene.width, 3))
+        _check(lib().rt_render(self._h, seed, mode, sched, _p(out)), self._h)
+        return out
+
+    def sync(self):
+        _check(lib().rt_sync(self._h), self._h)
+
+    def stream(self):
+        s = C.c_void_p()
+        _check(lib().rt_stream(self._h, C.byref(s)), self._h)
+        return s.value or 0
+
+    def counters(self):
+        c = T.Counters()
+        _check(lib().rt_get_counters(self._h, C.byref(c)), self._h)
+        return c.as_dict()
+
+    def reset_counters(self):
+        _check(lib().rt_reset_counters(self._h), self._h)
+
+    def debug_rng(self, seed, pixel, sample, n):
+        u = np.zeros(n, np.uint64)
+        probe = np.zeros(8)
+        _check(lib().rt_debug_rng(self._h, seed, pixel, sample, n, _p(u), _p(probe)), self._h)
+        return u, probe
+
+
+def save_ppm(path, rgb):
+    rgb = _f64(rgb)
+    h, w = rgb.shape[0], rgb.shape[1]
+    _check(lib().rt_save_ppm(os.fsencode(path), w, h, _p(rgb)))

@@ -1,0 +1,547 @@
+// capi.cpp — the C ABI of include/rt_b200.h: scene objects, device context, upload, launches.
+// No C++ exception and no CUDA error crosses the boundary: every entry point returns rt_status.
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/rt_b200.h"
+#include "exact_limits.hpp"
+#include "fast_build.hpp"
+#include "kernels.hpp"
+#include "scene_host.hpp"
+
+using namespace rt;
+
+static thread_local std::string g_last_error;
+
+struct rt_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    std::vector<void *> scene_allocs;
+    DScene dsc{};
+    bool has_scene = false;
+    double *d_accum = nullptr, *d_rgb = nullptr;
+    size_t n_px = 0;
+    DCounters *d_ctr = nullptr;
+    uint64_t launches = 0;
+    uint32_t samples = 0;
+};
+
+namespace {
+
+int set_err(rt_ctx *ctx, int code, const std::string &msg) {
+    g_last_error = msg;
+    if (ctx) ctx->err = msg;
+    return code;
+}
+#define CK(ctx, call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return set_err(ctx, RT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));      \
+    } while (0)
+
+template <class F>
+int guarded(rt_ctx *ctx, int code_on_throw, F &&f) {
+    try {
+        return f();
+    } catch (const std::bad_alloc &) {
+        return set_err(ctx, RT_ERR_LIMIT, "out of host memory");
+    } catch (const std::exception &e) {
+        return set_err(ctx, code_on_throw, e.what());
+    } catch (...) {
+        return set_err(ctx, code_on_throw, "unknown error");
+    }
+}
+
+void free_scene(rt_ctx *ctx) {
+    for (void *p : ctx->scene_allocs) cudaFree(p);
+    ctx->scene_allocs.clear();
+    if (ctx->d_accum) cudaFree(ctx->d_accum);
+    if (ctx->d_rgb) cudaFree(ctx->d_rgb);
+    ctx->d_accum = ctx->d_rgb = nullptr;
+    ctx->has_scene = false;
+}
+
+template <class T>
+cudaError_t upload(rt_ctx *ctx, const std::vector<T> &v, const T **out) {
+    *out = nullptr;
+    if (v.empty()) return cudaSuccess;
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, v.size() * sizeof(T));
+    if (e != cudaSuccess) return e;
+    ctx->scene_allocs.push_back(p);
+    e = cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream);
+    *out = (const T *)p;
+    return e;
+}
+
+std::vector<DNode> flatten_nodes(const std::vector<HostNode> &nodes) {
+    std::vector<DNode> out(nodes.size());
+    for (size_t i = 0; i < nodes.size(); ++i) {
+        const HostNode &n = nodes[i];
+        DNode d{};
+        for (int k = 0; k < 3; ++k) { d.lo[k] = n.box.lo[k]; d.hi[k] = n.box.hi[k]; }
+        if (n.left != RT_NO_CHILD && n.left != i + 1) throw std::runtime_error("BVH is not in pre-order");
+        d.right = n.right;
+        d.first = n.first;
+        d.count = n.count;
+        out[i] = d;
+    }
+    return out;
+}
+std::vector<DShape> flatten_shapes(const std::vector<HostShape> &v) {
+    std::vector<DShape> out(v.size());
+    for (size_t i = 0; i < v.size(); ++i) {
+        const HostShape &s = v[i];
+        DShape d{};
+        d.param[0] = s.param.x; d.param[1] = s.param.y; d.param[2] = s.param.z;
+        d.position[0] = s.position.x; d.position[1] = s.position.y; d.position[2] = s.position.z;
+        d.rot[0] = s.rotation.v.x; d.rot[1] = s.rotation.v.y; d.rot[2] = s.rotation.v.z; d.rot[3] = s.rotation.s;
+        d.type = s.type;
+        d.material = s.material;
+        out[i] = d;
+    }
+    return out;
+}
+void flatten_tris(const std::vector<HostTri> &v, std::vector<DTriI> &ti, std::vector<DTriS> &ts) {
+    ti.resize(v.size());
+    ts.resize(v.size());
+    for (size_t i = 0; i < v.size(); ++i) {
+        const HostTri &t = v[i];
+        DTriI a{};
+        a.a[0] = t.a.x; a.a[1] = t.a.y; a.a[2] = t.a.z;
+        a.ba[0] = t.ba.x; a.ba[1] = t.ba.y; a.ba[2] = t.ba.z;
+        a.ca[0] = t.ca.x; a.ca[1] = t.ca.y; a.ca[2] = t.ca.z;
+        a.material = t.material;
+        ti[i] = a;
+        DTriS s{};
+        s.ng[0] = t.ng.x; s.ng[1] = t.ng.y; s.ng[2] = t.ng.z;
+        s.na[0] = t.na.x; s.na[1] = t.na.y; s.na[2] = t.na.z;
+        s.nb[0] = t.nb.x; s.nb[1] = t.nb.y; s.nb[2] = t.nb.z;
+        s.nc[0] = t.nc.x; s.nc[1] = t.nc.y; s.nc[2] = t.nc.z;
+        s.inv_area = t.inv_area;
+        s.material = t.material;
+        ts[i] = s;
+    }
+}
+
+int need_scene(rt_ctx *ctx) {
+    if (!ctx) return set_err(nullptr, RT_ERR_INVALID_ARG, "null context");
+    if (!ctx->has_scene) return set_err(ctx, RT_ERR_NO_SCENE, "no scene uploaded");
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return set_err(ctx, RT_ERR_CUDA, cudaGetErrorString(e));
+    return RT_OK;
+}
+int check_mode(rt_ctx *ctx, int mode) {
+    if (mode != RT_MODE_EXACT && mode != RT_MODE_FAST) return set_err(ctx, RT_ERR_INVALID_ARG, "unknown mode");
+    return RT_OK;
+}
+
+struct DevBuf {                         // scoped device allocation for the array-in / array-out calls
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+};
+
+}  // namespace
+
+template <class P>
+static void export_bvh(const HostBvh<P> &b, double *bounds, uint32_t *left, uint32_t *right, uint32_t *first,
+                       uint32_t *count, uint32_t *order) {
+    for (size_t i = 0; i < b.nodes.size(); ++i) {
+        const HostNode &n = b.nodes[i];
+        if (bounds) for (int k = 0; k < 3; ++k) { bounds[i * 6 + k] = n.box.lo[k]; bounds[i * 6 + 3 + k] = n.box.hi[k]; }
+        if (left) left[i] = n.left;
+        if (right) right[i] = n.right;
+        if (first) first[i] = n.first;
+        if (count) count[i] = n.count;
+    }
+    if (order) for (size_t i = 0; i < b.prims.size(); ++i) order[i] = b.prims[i].orig;
+}
+// ---- host side -----------------------------------------------------------------------------------
+extern "C" {
+
+int rt_scene_build(const rt_raw_scene *raw, rt_scene **out) {
+    if (!raw || !out) return set_err(nullptr, RT_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    return guarded(nullptr, RT_ERR_INVALID_ARG, [&]() {
+        std::unique_ptr<rt_scene> s(new rt_scene());
+        build_scene(*raw, s->s);
+        *out = s.release();
+        return (int)RT_OK;
+    });
+}
+void rt_scene_free(rt_scene *scene) { delete scene; }
+
+int rt_scene_load_text(const char *path, rt_scene **out) {
+    if (!out) return set_err(nullptr, RT_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    return guarded(nullptr, RT_ERR_PARSE, [&]() {
+        RawSceneStorage st;
+        if (path) {
+            std::ifstream f(path);
+            if (!f) return set_err(nullptr, RT_ERR_IO, std::string("cannot open '") + path + "'");
+            parse_text_scene(f, st);
+        } else {
+            parse_text_scene(std::cin, st);
+        }
+        std::unique_ptr<rt_scene> s(new rt_scene());
+        build_scene(st.raw, s->s);
+        *out = s.release();
+        return (int)RT_OK;
+    });
+}
+int rt_scene_load_gltf(const char *path, uint32_t width, uint32_t height, uint32_t samples, rt_scene **out) {
+    if (!out || !path) return set_err(nullptr, RT_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    return guarded(nullptr, RT_ERR_PARSE, [&]() {
+        RawSceneStorage st;
+        load_gltf_scene(path, width, height, samples, st);
+        std::unique_ptr<rt_scene> s(new rt_scene());
+        build_scene(st.raw, s->s);
+        *out = s.release();
+        return (int)RT_OK;
+    });
+}
+
+int rt_scene_get_info(const rt_scene *scene, rt_scene_info *info) {
+    if (!scene || !info) return set_err(nullptr, RT_ERR_INVALID_ARG, "null argument");
+    const HostScene &s = scene->s;
+    *info = rt_scene_info{};
+    info->width = s.width; info->height = s.height; info->samples = s.samples; info->ray_depth = s.ray_depth;
+    const d3 *src[5] = {&s.bg_color, &s.cam_position, &s.cam_right, &s.cam_up, &s.cam_forward};
+    double *dst[5] = {info->bg_color, info->cam_position, info->cam_right, info->cam_up, info->cam_forward};
+    for (int i = 0; i < 5; ++i) { dst[i][0] = src[i]->x; dst[i][1] = src[i]->y; dst[i][2] = src[i]->z; }
+    info->tan_half_fov_x = s.tan_half_fov_x; info->tan_half_fov_y = s.tan_half_fov_y;
+    info->n_planes = (uint32_t)s.planes.size(); info->n_materials = (uint32_t)s.materials.size();
+    auto put = [&](int which, size_t nodes, size_t prims, uint32_t depth) {
+        info->bvh_nodes[which] = nodes; info->bvh_prims[which] = prims; info->bvh_depth[which] = depth;
+    };
+    put(RT_BVH_BOXES, s.boxes.nodes.size(), s.boxes.prims.size(), s.boxes.depth);
+    put(RT_BVH_ELLIPSOIDS, s.ellipsoids.nodes.size(), s.ellipsoids.prims.size(), s.ellipsoids.depth);
+    put(RT_BVH_TRIANGLES, s.tris.nodes.size(), s.tris.prims.size(), s.tris.depth);
+    put(RT_BVH_LIGHT_BOXES, s.light_boxes.nodes.size(), s.light_boxes.prims.size(), s.light_boxes.depth);
+    put(RT_BVH_LIGHT_ELLIPSOIDS, s.light_ellipsoids.nodes.size(), s.light_ellipsoids.prims.size(), s.light_ellipsoids.depth);
+    put(RT_BVH_LIGHT_TRIANGLES, s.light_tris.nodes.size(), s.light_tris.prims.size(), s.light_tris.depth);
+    return RT_OK;
+}
+
+int rt_scene_get_bvh(const rt_scene *scene, int which, double *bounds, uint32_t *left, uint32_t *right,
+                     uint32_t *first, uint32_t *count, uint32_t *prim_order) {
+    if (!scene) return set_err(nullptr, RT_ERR_INVALID_ARG, "null scene");
+    const HostScene &s = scene->s;
+    switch (which) {
+        case RT_BVH_BOXES: export_bvh(s.boxes, bounds, left, right, first, count, prim_order); break;
+        case RT_BVH_ELLIPSOIDS: export_bvh(s.ellipsoids, bounds, left, right, first, count, prim_order); break;
+        case RT_BVH_TRIANGLES: export_bvh(s.tris, bounds, left, right, first, count, prim_order); break;
+        case RT_BVH_LIGHT_BOXES: export_bvh(s.light_boxes, bounds, left, right, first, count, prim_order); break;
+        case RT_BVH_LIGHT_ELLIPSOIDS: export_bvh(s.light_ellipsoids, bounds, left, right, first, count, prim_order); break;
+        case RT_BVH_LIGHT_TRIANGLES: export_bvh(s.light_tris, bounds, left, right, first, count, prim_order); break;
+        default: return set_err(nullptr, RT_ERR_INVALID_ARG, "unknown hierarchy");
+    }
+    return RT_OK;
+}
+int rt_scene_get_triangle(const rt_scene *scene, int which, uint64_t i, double *o, uint32_t *material) {
+    if (!scene || !o) return set_err(nullptr, RT_ERR_INVALID_ARG, "null argument");
+    const HostBvh<HostTri> *b = which == RT_BVH_TRIANGLES ? &scene->s.tris : (which == RT_BVH_LIGHT_TRIANGLES ? &scene->s.light_tris : nullptr);
+    if (!b || i >= b->prims.size()) return set_err(nullptr, RT_ERR_INVALID_ARG, "triangle index out of range");
+    const HostTri &t = b->prims[i];
+    const d3 vs[7] = {t.a, t.ba, t.ca, t.ng, t.na, t.nb, t.nc};
+    for (int k = 0; k < 7; ++k) { o[k * 3] = vs[k].x; o[k * 3 + 1] = vs[k].y; o[k * 3 + 2] = vs[k].z; }
+    o[21] = t.inv_area;
+    for (int k = 0; k < 3; ++k) { o[22 + k] = t.box.lo[k]; o[25 + k] = t.box.hi[k]; }
+    if (material) *material = t.material;
+    return RT_OK;
+}
+int rt_scene_get_shape(const rt_scene *scene, int which, uint64_t i, rt_shape *out, double *aabb6) {
+    if (!scene || !out) return set_err(nullptr, RT_ERR_INVALID_ARG, "null argument");
+    const HostScene &s = scene->s;
+    const std::vector<HostShape> *v = nullptr;
+    switch (which) {
+        case -1: v = &s.planes; break;
+        case RT_BVH_BOXES: v = &s.boxes.prims; break;
+        case RT_BVH_ELLIPSOIDS: v = &s.ellipsoids.prims; break;
+        case RT_BVH_LIGHT_BOXES: v = &s.light_boxes.prims; break;
+        case RT_BVH_LIGHT_ELLIPSOIDS: v = &s.light_ellipsoids.prims; break;
+        default: return set_err(nullptr, RT_ERR_INVALID_ARG, "unknown shape set");
+    }
+    if (i >= v->size()) return set_err(nullptr, RT_ERR_INVALID_ARG, "shape index out of range");
+    const HostShape &p = (*v)[i];
+    *out = rt_shape{};
+    out->type = p.type; out->material = p.material;
+    out->param[0] = p.param.x; out->param[1] = p.param.y; out->param[2] = p.param.z;
+    out->position[0] = p.position.x; out->position[1] = p.position.y; out->position[2] = p.position.z;
+    out->rotation[0] = p.rotation.v.x; out->rotation[1] = p.rotation.v.y; out->rotation[2] = p.rotation.v.z; out->rotation[3] = p.rotation.s;
+    if (aabb6) for (int k = 0; k < 3; ++k) { aabb6[k] = p.box.lo[k]; aabb6[3 + k] = p.box.hi[k]; }
+    return RT_OK;
+}
+int rt_scene_get_material(const rt_scene *scene, uint32_t i, rt_material *out) {
+    if (!scene || !out || i >= scene->s.materials.size()) return set_err(nullptr, RT_ERR_INVALID_ARG, "bad material index");
+    *out = scene->s.materials[i];
+    return RT_OK;
+}
+int rt_save_ppm(const char *path, uint32_t width, uint32_t height, const double *rgb) {
+    if (!path || !rgb) return set_err(nullptr, RT_ERR_INVALID_ARG, "null argument");
+    return guarded(nullptr, RT_ERR_IO, [&]() { save_ppm(path, width, height, rgb); return (int)RT_OK; });
+}
+
+// ---- device side -----------------------------------------------------------------------------------
+int rt_device_count(int *count) {
+    if (!count) return set_err(nullptr, RT_ERR_INVALID_ARG, "null argument");
+    *count = 0;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) { *count = 0; cudaGetLastError(); return set_err(nullptr, RT_ERR_NO_DEVICE, cudaGetErrorString(e)); }
+    return RT_OK;
+}
+int rt_create(int device_id, rt_ctx **out) {
+    if (!out) return set_err(nullptr, RT_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return set_err(nullptr, RT_ERR_NO_DEVICE, std::string("no CUDA device: the render path has no CPU fallback (") +
+                                                      (e != cudaSuccess ? cudaGetErrorString(e) : "0 devices") + ")");
+    }
+    if (device_id < 0 || device_id >= n) return set_err(nullptr, RT_ERR_INVALID_ARG, "device id out of range");
+    std::unique_ptr<rt_ctx> ctx(new rt_ctx());
+    ctx->device = device_id;
+    CK(nullptr, cudaSetDevice(device_id));
+    CK(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CK(nullptr, cudaMalloc(&ctx->d_ctr, sizeof(DCounters)));
+    CK(nullptr, cudaMemsetAsync(ctx->d_ctr, 0, sizeof(DCounters), ctx->stream));
+    *out = ctx.release();
+    return RT_OK;
+}
+void rt_destroy(rt_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    free_scene(ctx);
+    if (ctx->d_ctr) cudaFree(ctx->d_ctr);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+const char *rt_last_error(const rt_ctx *ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+int rt_upload_scene(rt_ctx *ctx, const rt_scene *scene) {
+    if (!ctx || !scene) return set_err(ctx, RT_ERR_INVALID_ARG, "null argument");
+    const HostScene &s = scene->s;
+    const uint32_t depths[6] = {s.boxes.depth, s.ellipsoids.depth, s.tris.depth, s.light_boxes.depth, s.light_ellipsoids.depth, s.light_tris.depth};
+    for (uint32_t d : depths)
+        if (d > (uint32_t)kExactStackHost)
+            return set_err(ctx, RT_ERR_LIMIT, "BVH depth " + std::to_string(d) + " exceeds the traversal stack (" + std::to_string(kExactStackHost) + ")");
+    return guarded(ctx, RT_ERR_INVALID_ARG, [&]() -> int {
+        CK(ctx, cudaSetDevice(ctx->device));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        free_scene(ctx);
+        DScene d{};
+        struct Pair { const HostBvh<HostShape> *b; DBvh *dst; const DShape **prims; };
+        Pair shapes[4] = {{&s.boxes, &d.boxes, &d.box_prims}, {&s.ellipsoids, &d.ellipsoids, &d.ell_prims},
+                          {&s.light_boxes, &d.lboxes, &d.lbox_prims}, {&s.light_ellipsoids, &d.lellipsoids, &d.lell_prims}};
+        for (Pair &p : shapes) {
+            CK(ctx, upload(ctx, flatten_nodes(p.b->nodes), &p.dst->nodes));
+            CK(ctx, upload(ctx, flatten_shapes(p.b->prims), p.prims));
+            p.dst->n_nodes = (uint32_t)p.b->nodes.size();
+            p.dst->n_prims = (uint32_t)p.b->prims.size();
+        }
+        CK(ctx, upload(ctx, flatten_shapes(s.planes), &d.planes));
+        d.n_planes = (uint32_t)s.planes.size();
+        struct TPair { const HostBvh<HostTri> *b; DBvh *dst; const DTriI **ti; const DTriS **ts; FBvh *f; };
+        TPair tris[2] = {{&s.tris, &d.tris, &d.tri_i, &d.tri_s, &d.ftris}, {&s.light_tris, &d.ltris, &d.ltri_i, &d.ltri_s, &d.fltris}};
+        for (TPair &p : tris) {
+            std::vector<DTriI> ti;
+            std::vector<DTriS> ts;
+            flatten_tris(p.b->prims, ti, ts);
+            CK(ctx, upload(ctx, flatten_nodes(p.b->nodes), &p.dst->nodes));
+            CK(ctx, upload(ctx, ti, p.ti));
+            CK(ctx, upload(ctx, ts, p.ts));
+            p.dst->n_nodes = (uint32_t)p.b->nodes.size();
+            p.dst->n_prims = (uint32_t)p.b->prims.size();
+            FastHierarchy fh;
+            build_fast_hierarchy(*p.b, fh);
+            CK(ctx, upload(ctx, fh.nodes, &p.f->nodes));
+            CK(ctx, upload(ctx, fh.leaves, &p.f->leaves));
+            CK(ctx, upload(ctx, fh.tris, &p.f->tris));
+            p.f->root = fh.root;
+            CK(ctx, cudaStreamSynchronize(ctx->stream));       // staging vectors die at scope end
+        }
+        std::vector<DMaterial> mats(s.materials.size());
+        for (size_t i = 0; i < mats.size(); ++i) {
+            DMaterial m{};
+            for (int k = 0; k < 3; ++k) { m.color[k] = s.materials[i].color[k]; m.emission[k] = s.materials[i].emission[k]; }
+            m.ior = s.materials[i].ior;
+            m.kind = s.materials[i].kind;
+            mats[i] = m;
+        }
+        CK(ctx, upload(ctx, mats, &d.materials));
+        d.n_lights = (uint32_t)(s.light_boxes.prims.size() + s.light_ellipsoids.prims.size() + s.light_tris.prims.size());
+        d.width = s.width; d.height = s.height; d.ray_depth = s.ray_depth;
+        d.cam.position = s.cam_position; d.cam.right = s.cam_right; d.cam.up = s.cam_up; d.cam.forward = s.cam_forward;
+        d.cam.tan_half_fov_x = s.tan_half_fov_x; d.cam.tan_half_fov_y = s.tan_half_fov_y;
+        d.cam.width = (double)s.width; d.cam.height = (double)s.height;
+        d.bg = s.bg_color;
+        ctx->n_px = (size_t)s.width * s.height;
+        CK(ctx, cudaMalloc(&ctx->d_accum, ctx->n_px * 3 * sizeof(double)));
+        CK(ctx, cudaMalloc(&ctx->d_rgb, ctx->n_px * 3 * sizeof(double)));
+        CK(ctx, cudaMemsetAsync(ctx->d_accum, 0, ctx->n_px * 3 * sizeof(double), ctx->stream));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->dsc = d;
+        ctx->samples = s.samples;
+        ctx->has_scene = true;
+        return RT_OK;
+    });
+}
+
+int rt_trace_rays(rt_ctx *ctx, int mode, uint64_t n, const double *origins, const double *dirs, rt_hit *hits) {
+    if (int r = need_scene(ctx)) return r;
+    if (int r = check_mode(ctx, mode)) return r;
+    if (n && (!origins || !dirs || !hits)) return set_err(ctx, RT_ERR_INVALID_ARG, "null argument");
+    if (n == 0) return RT_OK;
+    DevBuf o, d, h;
+    CK(ctx, o.alloc(n * 24));
+    CK(ctx, d.alloc(n * 24));
+    CK(ctx, h.alloc(n * sizeof(rt_hit)));
+    CK(ctx, cudaMemcpyAsync(o.p, origins, n * 24, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(d.p, dirs, n * 24, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, launch_trace_rays(ctx->stream, ctx->dsc, mode, n, (const double *)o.p, (const double *)d.p, h.p, ctx->d_ctr));
+    ++ctx->launches;
+    CK(ctx, cudaMemcpyAsync(hits, h.p, n * sizeof(rt_hit), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+int rt_trace_primary(rt_ctx *ctx, int mode, double jx, double jy, rt_hit *hits, double *rays_out) {
+    if (int r = need_scene(ctx)) return r;
+    if (int r = check_mode(ctx, mode)) return r;
+    DevBuf h, rb;
+    if (hits) CK(ctx, h.alloc(ctx->n_px * sizeof(rt_hit)));
+    if (rays_out) CK(ctx, rb.alloc(ctx->n_px * 48));
+    CK(ctx, launch_trace_primary(ctx->stream, ctx->dsc, mode, jx, jy, h.p, (double *)rb.p, ctx->d_ctr));
+    ++ctx->launches;
+    if (hits) CK(ctx, cudaMemcpyAsync(hits, h.p, ctx->n_px * sizeof(rt_hit), cudaMemcpyDeviceToHost, ctx->stream));
+    if (rays_out) CK(ctx, cudaMemcpyAsync(rays_out, rb.p, ctx->n_px * 48, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+int rt_light_pdf(rt_ctx *ctx, int mode, uint64_t n, const double *pos, const double *dir, double *pdf) {
+    if (int r = need_scene(ctx)) return r;
+    if (int r = check_mode(ctx, mode)) return r;
+    if (n && (!pos || !dir || !pdf)) return set_err(ctx, RT_ERR_INVALID_ARG, "null argument");
+    if (n == 0) return RT_OK;
+    DevBuf p, d, o;
+    CK(ctx, p.alloc(n * 24));
+    CK(ctx, d.alloc(n * 24));
+    CK(ctx, o.alloc(n * 8));
+    CK(ctx, cudaMemcpyAsync(p.p, pos, n * 24, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(d.p, dir, n * 24, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, launch_light_pdf(ctx->stream, ctx->dsc, mode, n, (const double *)p.p, (const double *)d.p, (double *)o.p, ctx->d_ctr));
+    ++ctx->launches;
+    CK(ctx, cudaMemcpyAsync(pdf, o.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+int rt_render_accum(rt_ctx *ctx, const rt_render_params *p) {
+    if (int r = need_scene(ctx)) return r;
+    if (!p) return set_err(ctx, RT_ERR_INVALID_ARG, "null params");
+    if (int r = check_mode(ctx, p->mode)) return r;
+    if (p->sched != RT_SCHED_MEGAKERNEL && p->sched != RT_SCHED_WAVEFRONT) return set_err(ctx, RT_ERR_INVALID_ARG, "unknown scheduler");
+    if ((uint64_t)p->sample_begin + p->sample_count > 0xFFFFFFFFull) return set_err(ctx, RT_ERR_INVALID_ARG, "sample range overflows u32");
+    if (p->clear) CK(ctx, cudaMemsetAsync(ctx->d_accum, 0, ctx->n_px * 3 * sizeof(double), ctx->stream));
+    if (p->sample_count == 0) return RT_OK;
+    if (p->sched == RT_SCHED_WAVEFRONT) return set_err(ctx, RT_ERR_INVALID_ARG, "wavefront scheduler not built into this library yet");
+    CK(ctx, launch_render_mega(ctx->stream, ctx->dsc, p->mode, p->sample_begin, p->sample_count, p->seed, ctx->d_accum, ctx->d_ctr));
+    ++ctx->launches;
+    return RT_OK;
+}
+int rt_accum_device_ptr(rt_ctx *ctx, void **dptr, uint64_t *n_doubles) {
+    if (int r = need_scene(ctx)) return r;
+    if (dptr) *dptr = ctx->d_accum;
+    if (n_doubles) *n_doubles = ctx->n_px * 3;
+    return RT_OK;
+}
+int rt_get_accum(rt_ctx *ctx, double *sum_rgb) {
+    if (int r = need_scene(ctx)) return r;
+    if (!sum_rgb) return set_err(ctx, RT_ERR_INVALID_ARG, "null argument");
+    CK(ctx, cudaMemcpyAsync(sum_rgb, ctx->d_accum, ctx->n_px * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+int rt_set_accum(rt_ctx *ctx, const double *sum_rgb) {
+    if (int r = need_scene(ctx)) return r;
+    if (!sum_rgb) return set_err(ctx, RT_ERR_INVALID_ARG, "null argument");
+    CK(ctx, cudaMemcpyAsync(ctx->d_accum, sum_rgb, ctx->n_px * 24, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+int rt_postprocess(rt_ctx *ctx, uint32_t total_samples, double *rgb_out) {
+    if (int r = need_scene(ctx)) return r;
+    if (!rgb_out) return set_err(ctx, RT_ERR_INVALID_ARG, "null argument");
+    CK(ctx, launch_postprocess(ctx->stream, ctx->n_px * 3, ctx->d_accum, total_samples, ctx->d_rgb));
+    ++ctx->launches;
+    CK(ctx, cudaMemcpyAsync(rgb_out, ctx->d_rgb, ctx->n_px * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+int rt_render(rt_ctx *ctx, uint64_t seed, int mode, int sched, double *rgb_out) {
+    if (int r = need_scene(ctx)) return r;
+    rt_render_params p{};
+    p.sample_begin = 0;
+    p.sample_count = ctx->samples;
+    p.seed = seed; p.mode = mode; p.sched = sched; p.clear = 1;
+    if (int r = rt_render_accum(ctx, &p)) return r;
+    return rt_postprocess(ctx, ctx->samples, rgb_out);
+}
+int rt_debug_rng(rt_ctx *ctx, uint64_t seed, uint32_t pixel, uint32_t sample, uint64_t n, uint64_t *u64_out, double *probe8) {
+    if (!ctx || !u64_out || !probe8) return set_err(ctx, RT_ERR_INVALID_ARG, "null argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    DevBuf u, pr;
+    CK(ctx, u.alloc(n * 8));
+    CK(ctx, pr.alloc(64));
+    CK(ctx, launch_rng_probe(ctx->stream, seed, pixel, sample, n, (unsigned long long *)u.p, (double *)pr.p));
+    ++ctx->launches;
+    CK(ctx, cudaMemcpyAsync(u64_out, u.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(probe8, pr.p, 64, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+int rt_sync(rt_ctx *ctx) {
+    if (!ctx) return set_err(nullptr, RT_ERR_INVALID_ARG, "null context");
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+int rt_stream(rt_ctx *ctx, void **stream) {
+    if (!ctx || !stream) return set_err(ctx, RT_ERR_INVALID_ARG, "null argument");
+    *stream = (void *)ctx->stream;
+    return RT_OK;
+}
+int rt_get_counters(rt_ctx *ctx, rt_counters *out) {
+    if (!ctx || !out) return set_err(ctx, RT_ERR_INVALID_ARG, "null argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    DCounters c{};
+    CK(ctx, cudaMemcpyAsync(&c, ctx->d_ctr, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    out->segments = c.segments; out->light_pdf_rays = c.light_pdf_rays; out->paths = c.paths;
+    out->aabb_tests = c.aabb_tests; out->prim_tests = c.prim_tests;
+    out->light_aabb_tests = c.light_aabb_tests; out->light_prim_tests = c.light_prim_tests;
+    out->kernel_launches = ctx->launches;
+    return RT_OK;
+}
+int rt_reset_counters(rt_ctx *ctx) {
+    if (!ctx) return set_err(nullptr, RT_ERR_INVALID_ARG, "null context");
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaMemsetAsync(ctx->d_ctr, 0, sizeof(DCounters), ctx->stream));
+    ctx->launches = 0;
+    return RT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,18 @@
+// fast_build.hpp — host: derives the fp32 culling hierarchy of FAST mode from a built BVH.
+#pragma once
+#include <vector>
+
+#include "device_scene.cuh"
+#include "scene_host.hpp"
+
+namespace rt {
+
+struct FastHierarchy {
+    std::vector<FNode> nodes;
+    std::vector<uint2> leaves;
+    std::vector<FTri> tris;
+    int32_t root = INT32_MIN;
+};
+void build_fast_hierarchy(const HostBvh<HostTri> &bvh, FastHierarchy &out);
+
+}  // namespace rt

@@ -1,0 +1,69 @@
+// main.cpp — the reference's command line (reference src/main.rs:30-83, run.sh):
+//   cpu-raytracing-rt custom <out.ppm> < scene.txt
+//   cpu-raytracing-rt glTF <in.gltf> <W> <H> <spp> <out.ppm>
+// Scene loading and the BVH build run on the host; generate_image (src/main.rs:85) runs on the GPU.
+// Extra, optional environment knobs (not in the reference): RT_SEED, RT_MODE=exact|fast, RT_DEVICE.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/rt_b200.h"
+
+static int die(const char *what, rt_ctx *ctx) {
+    std::fprintf(stderr, "%s: %s\n", what, rt_last_error(ctx));
+    return 101;     // a Rust panic exits with 101
+}
+
+int main(int argc, char **argv) {
+    if (argc < 2) { std::puts("You must specify the input format"); return 0; }
+    const std::string format = argv[1];
+    if (format != "custom" && format != "glTF") { std::puts("Input format must be 'custom' or 'glTF'"); return 0; }
+    const int out_idx = format == "custom" ? 2 : 6;
+    if (argc <= out_idx) { std::puts("You must specify the output file"); return 0; }
+    const char *output = argv[out_idx];
+
+    std::puts("Started scene parsing");
+    rt_scene *scene = nullptr;
+    if (format == "glTF") {
+        char *e1 = nullptr, *e2 = nullptr, *e3 = nullptr;
+        const unsigned long w = std::strtoul(argv[3], &e1, 10), h = std::strtoul(argv[4], &e2, 10), spp = std::strtoul(argv[5], &e3, 10);
+        if (*e1 || *e2 || *e3) { std::fprintf(stderr, "width, height and samples must be base-10 integers\n"); return 101; }
+        if (rt_scene_load_gltf(argv[2], (uint32_t)w, (uint32_t)h, (uint32_t)spp, &scene)) return die("glTF", nullptr);
+    } else {
+        if (rt_scene_load_text(nullptr, &scene)) return die("scene", nullptr);
+    }
+    rt_scene_info info;
+    rt_scene_get_info(scene, &info);
+
+    const char *dev = std::getenv("RT_DEVICE");
+    rt_ctx *ctx = nullptr;
+    if (rt_create(dev ? std::atoi(dev) : 0, &ctx)) return die("device", nullptr);
+    if (rt_upload_scene(ctx, scene)) return die("upload", ctx);
+    std::puts("Started raytracing");
+    const char *seed_s = std::getenv("RT_SEED"), *mode_s = std::getenv("RT_MODE");
+    const uint64_t seed = seed_s ? std::strtoull(seed_s, nullptr, 0) : 0xC0FFEEull;
+    const int mode = (mode_s && !std::strcmp(mode_s, "exact")) ? RT_MODE_EXACT : RT_MODE_FAST;
+    std::vector<double> rgb((size_t)info.width * info.height * 3);
+    // progress lines of the reference (src/main.rs:105-110) at 5% granularity of the SAMPLE range
+    rt_render_params p{};
+    p.seed = seed; p.mode = mode; p.sched = RT_SCHED_MEGAKERNEL; p.clear = 1;
+    uint32_t done = 0;
+    for (int step = 1; step <= 20; ++step) {
+        const uint32_t upto = (uint32_t)((uint64_t)info.samples * step / 20);
+        if (upto > done) {
+            p.sample_begin = done; p.sample_count = upto - done;
+            if (rt_render_accum(ctx, &p)) return die("render", ctx);
+            if (rt_sync(ctx)) return die("render", ctx);
+            p.clear = 0;
+            done = upto;
+        }
+        std::printf("%d%%\n", step * 5);
+    }
+    if (rt_postprocess(ctx, info.samples, rgb.data())) return die("postprocess", ctx);
+    if (rt_save_ppm(output, info.width, info.height, rgb.data())) return die("Cannot create output file", nullptr);
+    rt_destroy(ctx);
+    rt_scene_free(scene);
+    return 0;
+}

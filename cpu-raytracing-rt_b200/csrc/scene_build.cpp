@@ -1,0 +1,373 @@
+// scene_build.cpp — host: primitive baking and the bit-exact SAH hierarchy build.
+//
+// The reference builds each BVH single-threaded by physically sorting ~290-byte primitive
+// structs four times per node (reference src/bvh.rs:75-113, :120-135).  This builder produces
+// the SAME node array and primitive order from 16-byte (key, index) items: per node three stable
+// key sorts + one re-sort, a suffix-box sweep, and task-parallel subtrees that are stitched back
+// into the reference's pre-order numbering.
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <limits>
+#include <stdexcept>
+#include <thread>
+
+#include "scene_host.hpp"
+
+namespace rt {
+namespace {
+
+constexpr double kInf = std::numeric_limits<double>::infinity();
+
+inline Box6 empty_box() {           // AABB::empty, src/aabb.rs:16-21
+    return Box6{{kInf, kInf, kInf}, {-kInf, -kInf, -kInf}};
+}
+inline void grow(Box6 &b, const Box6 &o) {      // extend_aabb, src/aabb.rs:28-31
+    for (int k = 0; k < 3; ++k) {
+        b.lo[k] = rmin(b.lo[k], o.lo[k]);
+        b.hi[k] = rmax(b.hi[k], o.hi[k]);
+    }
+}
+inline void grow(Box6 &b, d3 p) {               // extend, src/aabb.rs:23-26
+    const double v[3] = {p.x, p.y, p.z};
+    for (int k = 0; k < 3; ++k) {
+        b.lo[k] = rmin(b.lo[k], v[k]);
+        b.hi[k] = rmax(b.hi[k], v[k]);
+    }
+}
+inline double half_area(const Box6 &b) {        // aabb_score, src/bvh.rs:115-118
+    const double sx = b.hi[0] - b.lo[0], sy = b.hi[1] - b.lo[1], sz = b.hi[2] - b.lo[2];
+    return sx * sy + sx * sz + sy * sz;
+}
+inline int64_t order_key(double v) {            // f64::total_cmp as an integer key (src/bvh.rs:139)
+    int64_t b;
+    std::memcpy(&b, &v, 8);
+    return b ^ (int64_t)(((uint64_t)(b >> 63)) >> 1);
+}
+
+struct Item {
+    int64_t key;
+    uint32_t idx;
+};
+
+// Stable sort of `ord[0..n)` by the midpoint of `axis`.  Small ranges: insertion sort; large
+// ranges: LSD radix over the key bytes that actually differ; otherwise std::stable_sort.
+struct Sorter {
+    std::vector<Item> a, b;
+    void sort(const Box6 *boxes, uint32_t *ord, size_t n, int axis) {
+        a.resize(n);
+        int64_t all_or = 0, all_and = -1;
+        for (size_t i = 0; i < n; ++i) {
+            const Box6 &bx = boxes[ord[i]];
+            const int64_t k = order_key((bx.lo[axis] + bx.hi[axis]) / 2.0);     // src/bvh.rs:138
+            a[i] = Item{k, ord[i]};
+            all_or |= k;
+            all_and &= k;
+        }
+        if (n <= 32) {
+            for (size_t i = 1; i < n; ++i) {
+                Item v = a[i];
+                size_t j = i;
+                while (j > 0 && v.key < a[j - 1].key) { a[j] = a[j - 1]; --j; }
+                a[j] = v;
+            }
+        } else if (n >= 4096) {
+            radix(n, (uint64_t)(all_or ^ all_and));
+        } else {
+            std::stable_sort(a.begin(), a.end(), [](const Item &x, const Item &y) { return x.key < y.key; });
+        }
+        for (size_t i = 0; i < n; ++i) ord[i] = a[i].idx;
+    }
+    void radix(size_t n, uint64_t differing) {
+        b.resize(n);
+        Item *src = a.data(), *dst = b.data();
+        for (int pass = 0; pass < 8; ++pass) {
+            if (((differing >> (pass * 8)) & 0xFF) == 0) continue;      // byte identical in all keys
+            size_t hist[256] = {0};
+            const int sh = pass * 8;
+            // signed order: flip the top bit of the most significant byte
+            const uint64_t flip = pass == 7 ? 0x80u : 0u;
+            for (size_t i = 0; i < n; ++i) ++hist[(((uint64_t)src[i].key >> sh) & 0xFF) ^ flip];
+            size_t sum = 0;
+            for (int d = 0; d < 256; ++d) { size_t c = hist[d]; hist[d] = sum; sum += c; }
+            for (size_t i = 0; i < n; ++i) dst[hist[(((uint64_t)src[i].key >> sh) & 0xFF) ^ flip]++] = src[i];
+            std::swap(src, dst);
+        }
+        if (src != a.data()) std::memcpy(a.data(), src, n * sizeof(Item));
+    }
+};
+
+struct BuildShared {
+    const Box6 *boxes;
+    std::atomic<int> spare_threads;
+};
+
+struct Worker {
+    BuildShared &sh;
+    Sorter sorter;
+    std::vector<Box6> suffix;
+    explicit Worker(BuildShared &s) : sh(s) {}
+
+    // Evaluates every split position of the current arrangement (src/bvh.rs:120-135).
+    void sweep(const uint32_t *ord, size_t n, int axis, size_t &best_first, double &best_score, int &best_axis) {
+        suffix.resize(n);
+        Box6 acc = empty_box();
+        for (size_t i = n - 1; i >= 1; --i) {       // AABBSplitsBuilder backward half, :249-253
+            grow(acc, sh.boxes[ord[i]]);
+            suffix[i] = acc;
+        }
+        acc = empty_box();
+        for (size_t i = 0; i + 1 < n; ++i) {
+            grow(acc, sh.boxes[ord[i]]);
+            const size_t left_cnt = i + 1, right_cnt = n - left_cnt;
+            const double score = half_area(acc) * (double)left_cnt + half_area(suffix[i + 1]) * (double)right_cnt;
+            if (score < best_score) { best_first = left_cnt; best_score = score; best_axis = axis; }
+        }
+    }
+
+    // build_nodes, src/bvh.rs:75-113.  Nodes are appended to `out` in pre-order; child indices
+    // are relative to out[0].
+    uint32_t build(uint32_t *ord, size_t n, size_t global_offset, std::vector<HostNode> &out) {
+        Box6 box = empty_box();
+        for (size_t i = 0; i < n; ++i) grow(box, sh.boxes[ord[i]]);
+        auto leaf = [&]() {
+            out.push_back(HostNode{box, RT_NO_CHILD, RT_NO_CHILD, (uint32_t)global_offset, (uint32_t)n});
+            return (uint32_t)(out.size() - 1);
+        };
+        if (n <= 4) return leaf();
+        size_t best_first = n;
+        double best_score = half_area(box) * (double)n;
+        int best_axis = -1;
+        for (int axis = 0; axis < 3; ++axis) {
+            sorter.sort(sh.boxes, ord, n, axis);
+            sweep(ord, n, axis, best_first, best_score, best_axis);
+        }
+        if (best_axis < 0) return leaf();
+        if (best_axis != 2) sorter.sort(sh.boxes, ord, n, best_axis);   // a stable re-sort by Z of a Z-sorted range is the identity
+        const uint32_t me = (uint32_t)out.size();
+        out.push_back(HostNode{box, RT_NO_CHILD, RT_NO_CHILD, 0, 0});
+        const size_t nl = best_first, nr = n - best_first;
+        if (n >= 16384 && sh.spare_threads.fetch_sub(1) > 0) {
+            // right subtree on another thread into its own array, stitched in afterwards
+            std::vector<HostNode> right_nodes;
+            std::thread th([&]() {
+                Worker w(sh);
+                w.build(ord + nl, nr, global_offset + nl, right_nodes);
+            });
+            const uint32_t l = build(ord, nl, global_offset, out);
+            th.join();
+            sh.spare_threads.fetch_add(1);
+            const uint32_t shift = (uint32_t)out.size();
+            out.reserve(out.size() + right_nodes.size());
+            for (HostNode nd : right_nodes) {
+                if (nd.left != RT_NO_CHILD) nd.left += shift;
+                if (nd.right != RT_NO_CHILD) nd.right += shift;
+                out.push_back(nd);
+            }
+            out[me].left = l;
+            out[me].right = shift;
+        } else {
+            if (n >= 16384) sh.spare_threads.fetch_add(1);
+            const uint32_t l = build(ord, nl, global_offset, out);
+            const uint32_t r = build(ord + nl, nr, global_offset + nl, out);
+            out[me].left = l;
+            out[me].right = r;
+        }
+        return me;
+    }
+};
+
+}  // namespace
+
+void build_bvh(const Box6 *boxes, size_t n, std::vector<HostNode> &nodes, std::vector<uint32_t> &order,
+               uint32_t &depth, int max_threads) {
+    if (n >= 0xFFFFFFF0ull) throw std::runtime_error("too many primitives for 32-bit indices");
+    order.resize(n);
+    for (size_t i = 0; i < n; ++i) order[i] = (uint32_t)i;
+    nodes.clear();
+    if (max_threads <= 0) max_threads = (int)std::thread::hardware_concurrency();
+    if (max_threads < 1) max_threads = 1;
+    BuildShared sh{boxes, {max_threads - 1}};
+    Worker w(sh);
+    w.build(order.data(), n, 0, nodes);
+    // depth (root = 1); children always follow their parent in pre-order
+    std::vector<uint32_t> d(nodes.size(), 0);
+    depth = 0;
+    if (!nodes.empty()) d[0] = 1;
+    for (size_t i = 0; i < nodes.size(); ++i) {
+        depth = std::max(depth, d[i]);
+        if (nodes[i].left != RT_NO_CHILD) d[nodes[i].left] = d[i] + 1;
+        if (nodes[i].right != RT_NO_CHILD) d[nodes[i].right] = d[i] + 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+inline d3 ld3(const double *p) { return mk3(p[0], p[1], p[2]); }
+
+void triangle_props(d3 a, d3 b, d3 c, HostTri &t) {     // props, src/primitives/triangle.rs:41-47
+    t.a = a;
+    t.ba = sub(b, a);
+    t.ca = sub(c, a);
+    const d3 sized = cross3(t.ba, t.ca);
+    const double area = sqrt(dot3(sized, sized)) / 2.0;
+    t.ng = unit3(sized);
+    t.inv_area = 1.0 / area;
+}
+
+Box6 rotated_box(const Box6 &b, quat r) {               // rotated_aabb, src/scene.rs:255-268
+    Box6 o = empty_box();
+    for (int ix = 0; ix < 2; ++ix)
+        for (int iy = 0; iy < 2; ++iy)
+            for (int iz = 0; iz < 2; ++iz)
+                grow(o, qrot(r, mk3(ix ? b.hi[0] : b.lo[0], iy ? b.hi[1] : b.lo[1], iz ? b.hi[2] : b.lo[2])));
+    return o;
+}
+
+HostShape bake_shape(const rt_shape &s, uint32_t orig) {    // Primitive::new, src/scene.rs:108-137
+    HostShape o{};
+    o.type = s.type;
+    o.material = s.material;
+    o.param = ld3(s.param);
+    o.position = ld3(s.position);
+    o.rotation = mkq_xyzw(s.rotation[0], s.rotation[1], s.rotation[2], s.rotation[3]);
+    o.orig = orig;
+    o.box = empty_box();
+    if (s.type != RT_SHAPE_PLANE) {
+        Box6 local = empty_box();                           // Box::new, src/primitives/box.rs:12-17
+        grow(local, o.param);
+        grow(local, neg(o.param));
+        o.box = rotated_box(local, o.rotation);
+        const double p[3] = {o.position.x, o.position.y, o.position.z};
+        for (int k = 0; k < 3; ++k) { o.box.lo[k] += p[k]; o.box.hi[k] += p[k]; }
+    }
+    return o;
+}
+
+HostTri bake_triangle(const rt_raw_scene &raw, uint64_t i) {
+    const double *p = raw.tri_pos + i * 9;
+    HostTri t{};
+    triangle_props(ld3(p), ld3(p + 3), ld3(p + 6), t);
+    if (raw.tri_nrm) {
+        const double *n = raw.tri_nrm + i * 9;
+        t.na = ld3(n); t.nb = ld3(n + 3); t.nc = ld3(n + 6);
+    } else {
+        t.na = t.nb = t.nc = t.ng;                          // new_with_geometry_normals, triangle.rs:25-28
+    }
+    t.material = raw.tri_mat ? raw.tri_mat[i] : 0;
+    t.orig = (uint32_t)i;
+    if (raw.tri_mode == RT_TRI_BAKED) {                     // instantiate, gltf/scene_builder.rs:42-55
+        t.box = empty_box();
+        grow(t.box, t.a);
+        grow(t.box, add(t.a, t.ba));
+        grow(t.box, add(t.a, t.ca));
+        return t;
+    }
+    d3 position = mk3(0, 0, 0);                             // TrianglePrimitive::new, src/scene.rs:139-165
+    quat rotation = mkq_xyzw(0, 0, 0, 1);
+    if (raw.tri_xform) {
+        const double *x = raw.tri_xform + i * 7;
+        position = ld3(x);
+        rotation = mkq_xyzw(x[3], x[4], x[5], x[6]);
+    }
+    const d3 wa = add(qrot(rotation, t.a), position);
+    const d3 wb = add(qrot(rotation, add(t.ba, t.a)), position);
+    const d3 wc = add(qrot(rotation, add(t.ca, t.a)), position);
+    HostTri w{};
+    triangle_props(wa, wb, wc, w);
+    w.na = qrot(rotation, t.na);
+    w.nb = qrot(rotation, t.nb);
+    w.nc = qrot(rotation, t.nc);
+    w.material = t.material;
+    w.orig = t.orig;
+    w.box = empty_box();
+    grow(w.box, wa);
+    grow(w.box, wb);
+    grow(w.box, wc);
+    return w;
+}
+
+template <class P>
+void make_bvh(std::vector<P> input, HostBvh<P> &out) {      // BVH::new, src/bvh.rs:12-17
+    std::vector<Box6> boxes(input.size());
+    for (size_t i = 0; i < input.size(); ++i) boxes[i] = input[i].box;
+    std::vector<uint32_t> order;
+    build_bvh(boxes.data(), input.size(), out.nodes, order, out.depth);
+    out.prims.resize(input.size());
+    for (size_t i = 0; i < input.size(); ++i) out.prims[i] = input[order[i]];
+}
+
+inline bool emits(const rt_material &m) {                   // is_light, src/scene.rs:225-227
+    return !(m.emission[0] == 0.0 && m.emission[1] == 0.0 && m.emission[2] == 0.0);
+}
+
+}  // namespace
+
+void build_scene(const rt_raw_scene &raw, HostScene &s) {
+    if (raw.width == 0 || raw.height == 0) throw std::runtime_error("zero image dimensions");
+    if (raw.ray_depth > 255) throw std::runtime_error("ray_depth is a u8 in the reference");
+    if ((raw.n_materials && !raw.materials) || (raw.n_shapes && !raw.shapes) || (raw.n_triangles && !raw.tri_pos))
+        throw std::runtime_error("null array in rt_raw_scene");
+    s = HostScene{};
+    s.width = raw.width; s.height = raw.height; s.samples = raw.samples; s.ray_depth = raw.ray_depth;
+    s.bg_color = ld3(raw.bg_color);
+    s.cam_position = ld3(raw.cam_position); s.cam_right = ld3(raw.cam_right);
+    s.cam_up = ld3(raw.cam_up); s.cam_forward = ld3(raw.cam_forward);
+    const double fw = (double)raw.width, fh = (double)raw.height;      // Camera::new, src/camera.rs:18-46
+    if (raw.fov_kind == RT_FOV_Y) {
+        s.tan_half_fov_y = tan(raw.fov / 2.0);
+        s.tan_half_fov_x = s.tan_half_fov_y / (fh / fw);
+    } else {
+        s.tan_half_fov_x = tan(raw.fov / 2.0);
+        s.tan_half_fov_y = s.tan_half_fov_x / (fw / fh);
+    }
+    s.materials.assign(raw.materials, raw.materials + raw.n_materials);
+    auto check_mat = [&](uint32_t m) { if (m >= raw.n_materials) throw std::runtime_error("material index out of range"); };
+
+    std::vector<HostShape> boxes, ellipsoids;
+    for (uint32_t i = 0; i < raw.n_shapes; ++i) {           // make_scenes, src/scene.rs:194-207
+        const rt_shape &sh = raw.shapes[i];
+        check_mat(sh.material);
+        if (sh.type == RT_SHAPE_BOX) boxes.push_back(bake_shape(sh, (uint32_t)boxes.size()));
+        else if (sh.type == RT_SHAPE_ELLIPSOID) ellipsoids.push_back(bake_shape(sh, (uint32_t)ellipsoids.size()));
+        else if (sh.type == RT_SHAPE_PLANE) s.planes.push_back(bake_shape(sh, (uint32_t)s.planes.size()));
+        else throw std::runtime_error("unknown shape type");
+    }
+    std::vector<HostTri> tris(raw.n_triangles);
+    {
+        const uint64_t n = raw.n_triangles;
+        int nt = (int)std::thread::hardware_concurrency();
+        if (nt < 1 || n < 65536) nt = 1;
+        std::vector<std::thread> ts;
+        for (int t = 0; t < nt; ++t)
+            ts.emplace_back([&, t]() {
+                for (uint64_t i = n * t / nt; i < n * (t + 1) / nt; ++i) tris[i] = bake_triangle(raw, i);
+            });
+        for (auto &t : ts) t.join();
+        if (raw.tri_mat)
+            for (uint64_t i = 0; i < n; ++i) check_mat(raw.tri_mat[i]);
+        else if (n) check_mat(0);
+    }
+    auto pick_lights = [&](const auto &v) {
+        std::remove_cv_t<std::remove_reference_t<decltype(v)>> out;
+        for (const auto &p : v)
+            if (emits(s.materials[p.material])) out.push_back(p);
+        return out;
+    };
+    const bool gltf = raw.tri_mode == RT_TRI_BAKED && raw.n_shapes == 0;
+    // lights first (src/scene.rs:209-213), then the scene sets (:215-220); glTF scenes use
+    // BVH::new_empty for the shape hierarchies (gltf/scene_builder.rs:14-15): no nodes at all.
+    if (!gltf) {
+        make_bvh(pick_lights(boxes), s.light_boxes);
+        make_bvh(pick_lights(ellipsoids), s.light_ellipsoids);
+    }
+    make_bvh(pick_lights(tris), s.light_tris);
+    if (!gltf) {
+        make_bvh(std::move(ellipsoids), s.ellipsoids);
+        make_bvh(std::move(boxes), s.boxes);
+    }
+    make_bvh(std::move(tris), s.tris);
+}
+
+}  // namespace rt

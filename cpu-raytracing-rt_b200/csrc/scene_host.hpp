@@ -1,0 +1,88 @@
+// scene_host.hpp — host-side scene model: what the reference keeps in `Scene`
+// (reference src/scene.rs:82-90) after Scene::new / gltf::build_scene, i.e. world-space
+// primitives in post-build order plus the six hierarchies of src/bvh.rs.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/rt_b200.h"
+#include "rtmath.cuh"
+
+namespace rt {
+
+struct Box6 {                       // src/aabb.rs:5-9
+    double lo[3], hi[3];
+};
+
+struct HostNode {                   // src/bvh.rs:49-54
+    Box6 box;
+    uint32_t left, right;           // RT_NO_CHILD for leaves
+    uint32_t first, count;          // primitive_indices
+};
+
+struct HostTri {                    // src/primitives/triangle.rs:6-17 + src/scene.rs:30-34
+    d3 a, ba, ca, ng;
+    double inv_area;
+    d3 na, nb, nc;
+    uint32_t material;
+    uint32_t orig;                  // position in the list that was fed to BVH::new
+    Box6 box;
+};
+
+struct HostShape {                  // src/scene.rs:21-27 Primitive<Box|Ellipsoid|Plane>
+    int32_t type;
+    uint32_t material;
+    d3 param, position;
+    quat rotation;
+    uint32_t orig;
+    Box6 box;
+};
+
+template <class P>
+struct HostBvh {                    // src/bvh.rs:6-9
+    std::vector<P> prims;
+    std::vector<HostNode> nodes;
+    uint32_t depth = 0;
+};
+
+struct HostScene {
+    uint32_t width = 0, height = 0, samples = 0, ray_depth = 0;
+    d3 bg_color{0, 0, 0};
+    d3 cam_position{0, 0, 0}, cam_right{1, 0, 0}, cam_up{0, 1, 0}, cam_forward{0, 0, 1};
+    double tan_half_fov_x = 1.0, tan_half_fov_y = 1.0;
+    std::vector<rt_material> materials;
+    std::vector<HostShape> planes;
+    HostBvh<HostShape> boxes, ellipsoids, light_boxes, light_ellipsoids;
+    HostBvh<HostTri> tris, light_tris;
+};
+
+// Full-sweep SAH build of src/bvh.rs:12-17, :75-144 over `n` primitive boxes.
+// Outputs the pre-order node array and order[i] = input index of the primitive at slot i.
+// Ties in the midpoint sort keep their current relative order ("BVH tie order").
+void build_bvh(const Box6 *boxes, size_t n, std::vector<HostNode> &nodes, std::vector<uint32_t> &order,
+               uint32_t &depth, int max_threads = 0);
+
+// Scene::new + make_scenes (src/scene.rs:180-223) / build_scene (src/gltf/scene_builder.rs:9-22).
+// Throws std::runtime_error on invalid input.
+void build_scene(const rt_raw_scene &raw, HostScene &out);
+
+// Loaders (throw std::runtime_error where the reference would panic).
+struct RawSceneStorage {            // owns the arrays an rt_raw_scene points to
+    rt_raw_scene raw{};
+    std::vector<rt_material> materials;
+    std::vector<rt_shape> shapes;
+    std::vector<double> tri_pos, tri_nrm, tri_xform;
+    std::vector<uint32_t> tri_mat;
+    void link();
+};
+void parse_text_scene(std::istream &in, RawSceneStorage &out);                     // src/scene_parser.rs
+void load_gltf_scene(const std::string &path, uint32_t w, uint32_t h, uint32_t spp,
+                     RawSceneStorage &out);                                          // src/gltf/*
+void save_ppm(const std::string &path, uint32_t w, uint32_t h, const double *rgb);  // src/ppm.rs
+
+}  // namespace rt
+
+struct rt_scene {
+    rt::HostScene s;
+};

@@ -228,6 +228,12 @@ typedef struct rt_counters {
 RT_API int rt_get_counters(rt_ctx *ctx, rt_counters *out);      /* syncs the stream */
 RT_API int rt_reset_counters(rt_ctx *ctx);
 
+/* Test hook: the first n u64 draws of the device RNG stream (seed, pixel, sample) and one value
+ * of each rand-0.8 distribution used on the path, for parity with the
+ * oracle's stream.  probe8 = 8 doubles. */
+RT_API int rt_debug_rng(rt_ctx *ctx, uint64_t seed, uint32_t pixel, uint32_t sample, uint64_t n,
+                        uint64_t *u64_out, double *probe8);
+
 #ifdef __cplusplus
 }
 #endif

@@ -590,12 +590,19 @@ static Scene *scene_build(const rt_raw_scene &raw) {         // Scene::new + mak
         for (auto &p : v) if (is_light(s->materials[p.material])) out.push_back(p);
         return out;
     };
-    s->lights.boxes = bvh_new(lights_of(boxes));             // scene.rs:209-213 (lights first)
-    s->lights.ellipsoids = bvh_new(lights_of(ellipsoids));
+    // glTF scenes use BVH::new_empty() for the shape hierarchies (gltf/scene_builder.rs:14-15):
+    // no nodes at all, whereas BVH::new(vec![]) pushes one empty leaf (bvh.rs:77-80).
+    const bool gltf = raw.tri_mode == RT_TRI_BAKED && raw.n_shapes == 0;
+    if (!gltf) {
+        s->lights.boxes = bvh_new(lights_of(boxes));         // scene.rs:209-213 (lights first)
+        s->lights.ellipsoids = bvh_new(lights_of(ellipsoids));
+    }
     s->lights.triangles = bvh_new(lights_of(triangles));
     s->primitives.planes = std::move(planes);                // scene.rs:215-220
-    s->primitives.ellipsoids = bvh_new(std::move(ellipsoids));
-    s->primitives.boxes = bvh_new(std::move(boxes));
+    if (!gltf) {
+        s->primitives.ellipsoids = bvh_new(std::move(ellipsoids));
+        s->primitives.boxes = bvh_new(std::move(boxes));
+    }
     s->primitives.triangles = bvh_new(std::move(triangles));
     return s;
 }

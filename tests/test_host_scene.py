@@ -1,0 +1,194 @@
+"""CPU tests of the host side (no GPU): the product's scene loaders and bit-exact SAH build
+against the oracle's restatement of reference src/scene.rs, src/bvh.rs:12-17,:75-144,
+src/scene_parser.rs and src/gltf/scene_builder.rs; PPM bytes against src/ppm.rs; the C ABI."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import rtb200
+import rtb200.ctypes_types as T
+from rtb200.scene_desc import RawScene
+from tests import helpers
+
+
+def test_abi_exports_every_declared_symbol():
+    L = rtb200.lib()
+    hdr = open(os.path.join(os.path.dirname(__file__), "..", "include", "rt_b200.h")).read()
+    declared = set(re.findall(r"RT_API\s+[\w\s\*]+?\b(rt_\w+)\s*\(", hdr))
+    assert declared == set(rtb200.SYMBOLS), declared ^ set(rtb200.SYMBOLS)
+    for name in declared:
+        assert hasattr(L, name), name
+
+
+def test_no_device_is_an_error_not_a_fallback():
+    if rtb200.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(rtb200.RtError) as e:
+        rtb200.Context(0)
+    assert e.value.code == 2 and "no CPU fallback" in str(e.value)
+
+
+def test_text_scene_matches_oracle(orc, tmp_path):
+    from oracle import loaders
+    path = helpers.cornell(tmp_path, 96, 64, 8, 6)
+    prod = rtb200.Scene.load_text(path)
+    raw = loaders.parse_text_scene(open(path).read())
+    oracle = orc.OracleScene(raw)
+    assert (prod.width, prod.height, prod.samples, prod.ray_depth) == (96, 64, 8, 6)
+    assert prod.info.n_planes == 6 and prod.info.bvh_prims[T.BVH_BOXES] == 3 and prod.info.bvh_prims[T.BVH_ELLIPSOIDS] == 3
+    assert prod.info.bvh_prims[T.BVH_LIGHT_BOXES] == 1 and prod.info.bvh_prims[T.BVH_LIGHT_ELLIPSOIDS] == 1
+    assert prod.info.bvh_prims[T.BVH_TRIANGLES] == 2 and prod.info.bvh_prims[T.BVH_LIGHT_TRIANGLES] == 1
+    helpers.assert_scene_equal(prod, oracle)
+    # the same description through rt_scene_build
+    helpers.assert_scene_equal(rtb200.Scene.from_raw(raw), oracle)
+
+
+def test_text_defaults_and_errors(tmp_path):
+    p = helpers.write_text(tmp_path, "DIMENSIONS 3 2\nNEW_PRIMITIVE\nPLANE 0 1 0\nFOO bar\n\n")
+    s = rtb200.Scene.load_text(p)
+    assert (s.samples, s.ray_depth) == (64, 16)                     # src/scene.rs:185-187
+    assert s.info.tan_half_fov_x == np.tan(np.pi / 2.0 / 2.0)       # CAMERA_FOV_X default pi/2
+    for bad in ("NEW_PRIMITIVE\nPLANE 0 1 0\n",                     # DIMENSIONS missing -> unwrap panic
+                "DIMENSIONS 2 2\nCOLOR 1 1 1\n",                    # property before NEW_PRIMITIVE
+                "DIMENSIONS 2 2\nNEW_PRIMITIVE\n",                  # primitive without a shape
+                "DIMENSIONS 2 2\nNEW_PRIMITIVE\nBOX 1 1\n",         # missing value
+                "DIMENSIONS 2 2\nNEW_PRIMITIVE\nBOX 1 1 1\nDIELECTRIC\n",   # ior.unwrap()
+                "DIMENSIONS 2 2\nRAY_DEPTH 300\n"):                 # u8 overflow
+        with pytest.raises(rtb200.RtError) as e:
+            rtb200.Scene.load_text(helpers.write_text(tmp_path, bad, "bad.txt"))
+        assert e.value.code == 5
+    with pytest.raises(rtb200.RtError) as e:
+        rtb200.Scene.load_text(os.path.join(str(tmp_path), "missing.txt"))
+    assert e.value.code == 4
+
+
+def test_gltf_scene_matches_oracle(orc, tmp_path):
+    from oracle import loaders
+    path, n = helpers.heightfield(tmp_path, 40, 80)
+    prod = rtb200.Scene.load_gltf(path, 160, 90, 4)
+    raw = loaders.load_gltf(path, 160, 90, 4)
+    assert raw.n_triangles() == n == prod.info.bvh_prims[T.BVH_TRIANGLES]
+    assert prod.info.bvh_prims[T.BVH_LIGHT_TRIANGLES] == 64 and prod.ray_depth == 8
+    assert prod.info.bvh_nodes[T.BVH_BOXES] == 0                    # BVH::new_empty for glTF scenes
+    helpers.assert_scene_equal(prod, orc.OracleScene(raw))
+    kinds = sorted(prod.material(i).kind for i in range(prod.info.n_materials))
+    assert kinds == [T.MAT_DIFFUSE, T.MAT_DIFFUSE, T.MAT_METALLIC, T.MAT_DIELECTRIC]
+
+
+def test_gltf_node_transforms_u16_indices_and_stride(orc, tmp_path):
+    """TRS propagation through a node tree, matrix nodes, UNSIGNED_SHORT indices, byteStride,
+    non-indexed primitives and the default (metallic) material: src/gltf/scene_builder.rs."""
+    import json
+    from oracle import loaders
+    rng = np.random.default_rng(7)
+    v = rng.uniform(-1, 1, (12, 3)).astype(np.float32)
+    nrm = rng.normal(size=(12, 3)).astype(np.float32)
+    inter = np.concatenate([v, nrm], axis=1)                        # interleaved, stride 24
+    idx = np.array([0, 1, 2, 3, 4, 5, 6, 7, 8, 2, 1, 9], np.uint16)
+    blob = inter.tobytes() + idx.tobytes()
+    open(os.path.join(str(tmp_path), "t.bin"), "wb").write(blob)
+    doc = {
+        "scenes": [{"nodes": [0, 3]}],
+        "nodes": [{"children": [1], "translation": [1, 2, 3], "rotation": [0.1, 0.2, 0.3, 0.9273618495495704], "scale": [2, 3, 4]},
+                  {"mesh": 0, "children": [2], "matrix": [0, 0, 1, 0, 0, 1, 0, 0, -1, 0, 0, 0, 0.5, 0.25, 2, 1]},
+                  {"mesh": 1, "scale": [1, -1, 1]},
+                  {"camera": 0, "translation": [0, 0, 5]}],
+        "cameras": [{"type": "perspective", "perspective": {"yfov": 0.7}}],
+        "meshes": [{"primitives": [{"attributes": {"POSITION": 0, "NORMAL": 1}, "indices": 2, "material": 0}]},
+                   {"primitives": [{"attributes": {"POSITION": 0, "NORMAL": 1}}]}],
+        "materials": [{"emissiveFactor": [1, 0.5, 0.25]}],
+        "buffers": [{"uri": "t.bin", "byteLength": len(blob)}],
+        "bufferViews": [{"buffer": 0, "byteLength": 288, "byteStride": 24}, {"buffer": 0, "byteOffset": 288, "byteLength": 24}],
+        "accessors": [{"bufferView": 0, "componentType": 5126, "count": 12, "type": "VEC3"},
+                      {"bufferView": 0, "byteOffset": 12, "componentType": 5126, "count": 12, "type": "VEC3"},
+                      {"bufferView": 1, "componentType": 5123, "count": 12, "type": "SCALAR"}],
+    }
+    path = os.path.join(str(tmp_path), "t.gltf")
+    json.dump(doc, open(path, "w"))
+    prod = rtb200.Scene.load_gltf(path, 32, 16, 2)
+    raw = loaders.load_gltf(path, 32, 16, 2)
+    assert raw.n_triangles() == 8
+    helpers.assert_scene_equal(prod, orc.OracleScene(raw))
+    assert prod.material(0).kind == T.MAT_METALLIC and tuple(prod.material(0).emission) == (1.0, 0.5, 0.25)
+    assert prod.material(1).kind == T.MAT_METALLIC                  # default material: metallicFactor 1.0
+    assert tuple(prod.info.cam_position) == (0.0, 0.0, 5.0) and tuple(prod.info.cam_forward) == (-0.0, -0.0, -1.0)
+
+
+def test_gltf_errors(tmp_path):
+    import json
+    base = {"scenes": [{"nodes": [0]}], "nodes": [{"camera": 0}],
+            "cameras": [{"type": "perspective", "perspective": {"yfov": 0.7}}]}
+    ok = os.path.join(str(tmp_path), "ok.gltf")
+    json.dump(base, open(ok, "w"))
+    assert rtb200.Scene.load_gltf(ok, 4, 4, 1).info.bvh_prims[T.BVH_TRIANGLES] == 0
+    for mutate in (lambda d: d.update(cameras=[]),                                  # single perspective camera
+                   lambda d: d.update(nodes=[{"camera": 0}, {"camera": 0}], scenes=[{"nodes": [0, 1]}]),
+                   lambda d: d.update(nodes=[{}]),                                  # no camera node
+                   lambda d: d.update(nodes=[{"camera": 0, "mesh": 0}], meshes=[{"primitives": [{"attributes": {"POSITION": 0}}]}])):
+        d = json.loads(json.dumps(base))
+        mutate(d)
+        bad = os.path.join(str(tmp_path), "bad.gltf")
+        json.dump(d, open(bad, "w"))
+        with pytest.raises(rtb200.RtError):
+            rtb200.Scene.load_gltf(bad, 4, 4, 1)
+    open(os.path.join(str(tmp_path), "junk.gltf"), "w").write("{ not json")
+    with pytest.raises(rtb200.RtError) as e:
+        rtb200.Scene.load_gltf(os.path.join(str(tmp_path), "junk.gltf"), 4, 4, 1)
+    assert e.value.code == 5
+
+
+@pytest.mark.parametrize("n,seed", [(0, 1), (1, 2), (4, 3), (5, 4), (33, 5), (1000, 6), (20000, 7)])
+def test_bvh_build_bit_exact_random_soups(orc, n, seed):
+    """Random triangle soups incl. the edge sizes around the leaf rule (<= 4) and the parallel
+    build threshold; node array + primitive order bit-exact against the oracle."""
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(-10, 10, (n, 1, 3))
+    tri = (c + rng.normal(scale=0.3, size=(n, 3, 3))).reshape(n, 9)
+    raw = RawScene(width=4, height=4)
+    raw.materials = [{"kind": T.MAT_DIFFUSE, "color": (0.5, 0.5, 0.5)}, {"kind": T.MAT_DIFFUSE, "emission": (1.0, 1.0, 1.0)}]
+    raw.tri_pos = tri if n else None
+    raw.tri_mat = (rng.uniform(size=n) < 0.1).astype(np.uint32) if n else None
+    helpers.assert_scene_equal(rtb200.Scene.from_raw(raw), orc.OracleScene(raw))
+
+
+def test_bvh_build_with_midpoint_ties(orc):
+    """A regular grid of identical quads: every axis sort is full of equal midpoints, and many
+    splits tie on score.  Stable tie order + first-best split must match the oracle exactly."""
+    xs, zs = np.meshgrid(np.arange(24.0), np.arange(16.0), indexing="ij")
+    a = np.stack([xs, np.zeros_like(xs), zs], -1).reshape(-1, 3)
+    t1 = np.concatenate([a, a + [1, 0, 0], a + [0, 0, 1]], 1)
+    t2 = np.concatenate([a + [1, 0, 0], a + [1, 0, 1], a + [0, 0, 1]], 1)
+    raw = RawScene(width=4, height=4)
+    raw.materials = [{"kind": T.MAT_DIFFUSE}]
+    raw.tri_pos = np.stack([t1, t2], 1).reshape(-1, 9)
+    raw.tri_mat = np.zeros(len(raw.tri_pos), np.uint32)
+    prod, oracle = rtb200.Scene.from_raw(raw), orc.OracleScene(raw)
+    helpers.assert_scene_equal(prod, oracle)
+    assert prod.info.bvh_depth[T.BVH_TRIANGLES] >= 7
+
+
+def test_bvh_build_larger_mesh_parallel_path(orc, tmp_path):
+    """120k triangles: exercises the radix sort and the task-parallel subtree stitching."""
+    from oracle import loaders
+    path, n = helpers.heightfield(tmp_path, 200, 300, lights=True, spheres=False)
+    prod = rtb200.Scene.load_gltf(path, 64, 36, 1)
+    oracle = orc.OracleScene(loaders.load_gltf(path, 64, 36, 1))
+    assert n == 120064
+    helpers.assert_scene_equal(prod, oracle)
+
+
+def test_ppm_bytes(orc, tmp_path):
+    rng = np.random.default_rng(3)
+    img = rng.uniform(-0.2, 1.2, (5, 7, 3))
+    img[0, 0] = [0.5 / 255.0, 1.5 / 255.0, 2.5 / 255.0]             # round-half-away-from-zero cases
+    img[0, 1] = [np.nan, np.inf, -np.inf]
+    out = os.path.join(str(tmp_path), "o.ppm")
+    rtb200.save_ppm(out, img)
+    data = open(out, "rb").read()
+    assert data.startswith(b"P6\n7 5\n255\n")
+    body = np.frombuffer(data[len(b"P6\n7 5\n255\n"):], np.uint8).reshape(5, 7, 3)
+    assert np.array_equal(body, orc.to_bytes(img))
+    assert tuple(body[0, 0]) == (1, 2, 3) and tuple(body[0, 1]) == (0, 255, 0)
