@@ -301,8 +301,11 @@ RT_D SceneHit intersect_exact(const DScene &sc, d3 o, d3 d, Cnt &c) {
         tri_exact(sc.tri_i + h.prim, o, d, t, u, v);
         d3 ng, ns;
         tri_finish(sc.tri_s + h.prim, d, u, v, ng, ns, h.inside);
-        h.ng = unit3(ng);                                 // DONT_ROTATE (:64) still renormalises
-        h.ns = unit3(ns);
+        // DONT_ROTATE (:64) is still APPLIED: the identity rotation rewrites signed zeros and
+        // the normalisation moves the last bits, so both are replayed rather than skipped.
+        const quat ident = mkq_xyzw(0.0, 0.0, 0.0, 1.0);
+        h.ng = unit3(qrot(ident, ng));
+        h.ns = unit3(qrot(ident, ns));
         h.material = __ldg(&sc.tri_i[h.prim].material);
     } else {
         const DShape *sp = h.kind == 0 ? sc.planes + h.prim : (h.kind == 1 ? sc.box_prims + h.prim : sc.ell_prims + h.prim);

@@ -1,0 +1,157 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the C ABI,
+against the CPU oracle on the same inputs.  Integer / index results are bit-exact; EXACT mode
+floating-point results are compared bitwise too (same IEEE operations in the same order); the
+radiance accumulation is compared to 1e-9 relative (throughput form vs the reference's
+recursion order round differently in the last bits)."""
+import os
+
+import numpy as np
+import pytest
+
+import rtb200
+import rtb200.ctypes_types as T
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = rtb200.Context(0)
+    yield c
+    c.close()
+
+
+def _load_pair(orc, tmp_path, kind, **kw):
+    from oracle import loaders
+    if kind == "cornell":
+        path = helpers.cornell(tmp_path, kw.get("w", 96), kw.get("h", 80), kw.get("spp", 4), kw.get("depth", 6))
+        return rtb200.Scene.load_text(path), orc.OracleScene(loaders.parse_text_scene(open(path).read()))
+    path, _ = helpers.heightfield(tmp_path, kw.get("nx", 100), kw.get("nz", 200))
+    w, h, spp = kw.get("w", 320), kw.get("h", 180), kw.get("spp", 2)
+    return rtb200.Scene.load_gltf(path, w, h, spp), orc.OracleScene(loaders.load_gltf(path, w, h, spp))
+
+
+def _assert_hits_bitwise(gpu, cpu):
+    assert helpers.hits_equal(gpu, cpu) == 0
+    hit = cpu["kind"] >= 0
+    assert gpu["t"][hit].tobytes() == cpu["t"][hit].tobytes()
+    assert gpu["geometry_normal"][hit].tobytes() == cpu["geometry_normal"][hit].tobytes()
+    assert gpu["shading_normal"][hit].tobytes() == cpu["shading_normal"][hit].tobytes()
+
+
+def test_missing_scene_is_an_error(ctx):
+    c2 = rtb200.Context(0)
+    with pytest.raises(rtb200.RtError) as e:
+        c2.trace_rays(np.zeros((1, 3)), np.ones((1, 3)))
+    assert e.value.code == 6
+    c2.close()
+
+
+def test_rng_stream_and_distributions(orc, ctx):
+    for seed, px, smp in ((0xC0FFEE, 0, 0), (1, 123456, 77), (2**63 + 5, 2**32 - 1, 2**32 - 1)):
+        u, probe = ctx.debug_rng(seed, px, smp, 64)
+        assert np.array_equal(u, orc.rng_u64(seed, px, smp, 64))
+        assert probe.tobytes() == orc.rng_probe(seed, px, smp).tobytes()
+
+
+@pytest.mark.parametrize("kind", ["cornell", "heightfield"])
+def test_primary_rays_exact(orc, ctx, tmp_path, kind):
+    prod, oracle = _load_pair(orc, tmp_path, kind)
+    ctx.upload(prod)
+    ctx.reset_counters()
+    for jx, jy in ((0.5, 0.5), (0.0, 0.999)):
+        g_hits, g_rays = ctx.trace_primary(jx, jy, T.MODE_EXACT, want_rays=True)
+        c_hits, c_rays, _ = oracle.trace_primary(jx, jy)
+        assert g_rays.tobytes() == c_rays.tobytes()             # camera.rs:48-55 + normalise
+        _assert_hits_bitwise(g_hits, c_hits)
+        assert (c_hits["kind"] >= 0).sum() > 0.3 * len(c_hits)
+    ctx.reset_counters()
+    ctx.trace_primary(0.5, 0.5, T.MODE_EXACT)
+    _, _, cc = oracle.trace_primary(0.5, 0.5)
+    gc = ctx.counters()
+    # identical visit order => identical numbers of AABB::intersects and primitive tests
+    for k in ("segments", "aabb_tests", "prim_tests"):
+        assert gc[k] == cc[k], k
+
+
+@pytest.mark.parametrize("kind", ["cornell", "heightfield"])
+def test_secondary_rays_and_light_pdf_exact(orc, ctx, tmp_path, kind):
+    prod, oracle = _load_pair(orc, tmp_path, kind)
+    ctx.upload(prod)
+    c_hits, c_rays, _ = oracle.trace_primary(0.5, 0.5)
+    hit = c_hits["kind"] >= 0
+    pos = c_rays[hit, :3] + c_rays[hit, 3:] * c_hits["t"][hit, None]
+    rng = np.random.default_rng(11)
+    d = rng.normal(size=pos.shape)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d = np.where((np.sum(d * c_hits["shading_normal"][hit], axis=1) < 0)[:, None], -d, d)
+    o = pos + 1.1368683772161603e-13 * d                        # EPSILON offset, raytrace.rs:32
+    # not normalised on purpose for half of them (refracted dirs are not unit, raytrace.rs:83)
+    d[::2] *= 0.37
+    _assert_hits_bitwise(ctx.trace_rays(o, d, T.MODE_EXACT), oracle.trace_rays(o, d)[0])
+    # degenerate rays: axis-parallel (zero direction components), origin inside boxes
+    axis = np.eye(3)[rng.integers(0, 3, len(o))] * rng.choice([-1.0, 1.0], (len(o), 1))
+    _assert_hits_bitwise(ctx.trace_rays(o, axis, T.MODE_EXACT), oracle.trace_rays(o, axis)[0])
+    # Light::pdf on directions drawn by the oracle's Light::sample (so most of them hit a light)
+    ld = oracle.light_sample(5, pos)
+    mixed = np.concatenate([ld, d / np.linalg.norm(d, axis=1, keepdims=True)])
+    pp = np.concatenate([pos, pos])
+    g = ctx.light_pdf(pp, mixed, T.MODE_EXACT)
+    c, _ = oracle.light_pdf(pp, mixed)
+    assert (c > 0).sum() > 0.2 * len(c)
+    assert g.tobytes() == c.tobytes()
+
+
+@pytest.mark.parametrize("kind", ["cornell", "heightfield"])
+def test_render_accum_exact_matches_oracle(orc, ctx, tmp_path, kind):
+    prod, oracle = _load_pair(orc, tmp_path, kind, w=64, h=48, spp=3)
+    ctx.upload(prod)
+    ctx.reset_counters()
+    seed = 0xC0FFEE
+    ctx.render_accum(0, 3, seed, T.MODE_EXACT, clear=True)
+    g = ctx.accum()
+    gc = ctx.counters()
+    c, cc = oracle.render_accum(0, 3, seed)
+    for k in ("segments", "light_pdf_rays", "paths", "aabb_tests", "prim_tests", "light_aabb_tests", "light_prim_tests"):
+        assert gc[k] == cc[k], (k, gc[k], cc[k])
+    assert c.sum() > 0
+    err = np.abs(g - c) / np.maximum(np.abs(c), 1e-300)
+    err[c == g] = 0.0
+    assert err.max() <= 1e-9, err.max()
+    # sample-range sharding: [0,1) then [1,3) into the same buffer == one call, bitwise
+    ctx.render_accum(0, 1, seed, T.MODE_EXACT, clear=True)
+    ctx.render_accum(1, 2, seed, T.MODE_EXACT)
+    assert ctx.accum().tobytes() == g.tobytes()
+    # accumulate-elsewhere-then-sum (what the multi-GPU reduce does) agrees to rounding
+    ctx.render_accum(1, 2, seed, T.MODE_EXACT, clear=True)
+    part = ctx.accum()
+    ctx.render_accum(0, 1, seed, T.MODE_EXACT, clear=True)
+    np.testing.assert_allclose(ctx.accum() + part, g, rtol=1e-12, atol=0)
+    # postprocess + PPM bytes
+    ctx.set_accum(g)
+    rgb = ctx.postprocess(3)
+    ref = orc.postprocess(g, 3)
+    np.testing.assert_allclose(rgb, ref, rtol=1e-13, atol=1e-15)
+    assert (orc.to_bytes(rgb) != orc.to_bytes(ref)).mean() < 1e-4
+
+
+@pytest.mark.parametrize("kind", ["cornell", "heightfield"])
+def test_fast_mode_equals_exact_mode(orc, ctx, tmp_path, kind):
+    """FAST mode culls in fp32 but confirms in f64: ids, t, normals and light PDFs must be the
+    EXACT ones; the rendered accumulation must be bitwise identical to EXACT mode."""
+    prod, oracle = _load_pair(orc, tmp_path, kind, w=96, h=64, spp=2)
+    ctx.upload(prod)
+    e_hits, rays = ctx.trace_primary(0.5, 0.5, T.MODE_EXACT, want_rays=True)
+    f_hits, _ = ctx.trace_primary(0.5, 0.5, T.MODE_FAST)
+    _assert_hits_bitwise(f_hits, e_hits)
+    hit = e_hits["kind"] >= 0
+    pos = rays[hit, :3] + rays[hit, 3:] * e_hits["t"][hit, None]
+    ld = oracle.light_sample(9, pos)
+    o = pos + 1.1368683772161603e-13 * ld
+    _assert_hits_bitwise(ctx.trace_rays(o, ld, T.MODE_FAST), ctx.trace_rays(o, ld, T.MODE_EXACT))
+    assert ctx.light_pdf(pos, ld, T.MODE_FAST).tobytes() == ctx.light_pdf(pos, ld, T.MODE_EXACT).tobytes()
+    ctx.render_accum(0, 2, 7, T.MODE_EXACT, clear=True)
+    e = ctx.accum()
+    ctx.render_accum(0, 2, 7, T.MODE_FAST, clear=True)
+    assert ctx.accum().tobytes() == e.tobytes()
