@@ -368,10 +368,12 @@ int rt_upload_scene(rt_ctx *ctx, const rt_scene *scene) {
             p.dst->n_prims = (uint32_t)p.b->prims.size();
             FastHierarchy fh;
             build_fast_hierarchy(*p.b, fh);
+            if (fh.depth + 2 > (uint32_t)kFastStackHost)
+                return set_err(ctx, RT_ERR_LIMIT, "fp32 hierarchy depth " + std::to_string(fh.depth) + " exceeds the traversal stack");
             CK(ctx, upload(ctx, fh.nodes, &p.f->nodes));
-            CK(ctx, upload(ctx, fh.leaves, &p.f->leaves));
             CK(ctx, upload(ctx, fh.tris, &p.f->tris));
             p.f->root = fh.root;
+            p.f->depth = fh.depth;
             CK(ctx, cudaStreamSynchronize(ctx->stream));       // staging vectors die at scope end
         }
         std::vector<DMaterial> mats(s.materials.size());

@@ -51,23 +51,27 @@ struct __align__(16) DMaterial {        // Metadata, 64 B (scene.rs:13-18)
 static_assert(sizeof(DMaterial) == 64, "DMaterial must be 64 bytes");
 
 // ---- FAST mode structures -------------------------------------------------------------------
-// Inner node of the fp32 culling hierarchy: the boxes of BOTH children (rounded outward from
-// the f64 boxes and padded by the scene-scale rounding slack), so one 64-byte fetch decides both
-// descents.  child < 0 encodes a leaf: ~child = index into the leaf table.
+// Inner node of the fp32 culling hierarchy, derived on the host from the reference's binary tree:
+// the boxes of BOTH children, rounded OUTWARD from the f64 boxes, so one 64-byte fetch (4 x 16 B)
+// decides both descents.  child >= 0: FNode index; child < 0: leaf, ~child = (first << 3) |
+// (count - 1) with 1 <= count <= 8 (longer reference leaves are split on the host).
 struct __align__(16) FNode {            // 64 B
-    float lo0[3], hi0[3];               // left child box
+    float lo0[3], hi0[3];               // left child box  (order: lo0.xyz hi0.xyz lo1.xyz hi1.xyz)
     float lo1[3], hi1[3];               // right child box
-    int32_t child0, child1;             // >= 0: FNode index; < 0: ~leaf (first | count<<?) see FLeaf
+    int32_t child0, child1;
     uint32_t _pad[2];
 };
 static_assert(sizeof(FNode) == 64, "FNode must be 64 bytes");
 
-struct __align__(16) FTri {             // fp32 pre-test record, 48 B = 3 x 16 B
-    float a[3], ba[3], ca[3];
-    float err;                          // absolute slack covering f64->f32 rounding of this record
-    uint32_t _pad[2];
+// fp32 pre-test record: anchor vertex in f64 (the subtraction origin - a is done in f64, then
+// rounded once), edges in fp32.  48 B = 3 x 16 B.
+struct __align__(16) FTri {
+    double a[3];
+    float ba[3], ca[3];
 };
 static_assert(sizeof(FTri) == 48, "FTri must be 48 bytes");
+
+constexpr int32_t kFastEmpty = INT32_MIN;   // FBvh::root of a hierarchy without primitives
 
 struct DBvh {
     const DNode *nodes;
@@ -75,11 +79,10 @@ struct DBvh {
 };
 
 struct FBvh {
-    const FNode *nodes;                 // nullptr when the hierarchy has <= 1 leaf
-    const uint2 *leaves;                // (first, count) per leaf
+    const FNode *nodes;
     const FTri *tris;
-    int32_t root;                       // >= 0 inner node, < 0 ~leaf, INT32_MIN: empty
-    uint32_t _pad;
+    int32_t root;                       // >= 0 inner node, < 0 leaf code, kFastEmpty: no primitives
+    uint32_t depth;                     // max number of simultaneously deferred children
 };
 
 struct DCamera {                        // camera.rs:6-15

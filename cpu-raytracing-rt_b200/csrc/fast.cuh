@@ -1,9 +1,240 @@
-// fast.cuh — FAST mode geometry queries (fp32 conservative culling + exact f64 confirmation).
+// fast.cuh — FAST mode geometry queries: conservative fp32 culling, exact f64 confirmation.
+//
+// B200 has no RT cores; its fp32 pipes are twice as wide as its f64 pipes and an IEEE f64
+// division costs ~20 instructions.  The reference spends 12 f64 divisions per node visit
+// (reference src/aabb.rs:62-63) and 9 per triangle test (src/primitives/triangle.rs:56-58).
+// FAST mode never divides while culling:
+//   * boxes: fp32 slabs with a precomputed reciprocal direction.  The fp32 boxes are rounded
+//     outward on the host and every rounding error of the slab arithmetic is bounded and added to
+//     the accepted interval, so any ray that touches the f64 box passes the fp32 test;
+//   * triangles: an fp32 Moller-Trumbore pre-test in determinant-scaled form whose rejection
+//     thresholds carry the error bound of each triple product, so it can only reject triangles
+//     the exact test also rejects;
+//   * every surviving candidate runs tri_exact (the reference's own arithmetic) and only its
+//     f64 (t, u, v) are ever used.  Results are therefore the EXACT-mode ones (ids, t, normals,
+//     light PDFs), which tests/test_gpu_parity.py::test_fast_mode_equals_exact_mode asserts bitwise.
+// Differences from EXACT by construction: equal-t ties between two triangles keep the first one
+// in FAST visit order, and rays whose hits lie beyond t ~ 1e9 are out of range of the fp32 slabs.
 #pragma once
 #include "shade.cuh"
 
 namespace rt {
 
-struct FastPolicy : ExactPolicy {};     // placeholder until the fp32 culling hierarchy lands
+constexpr int kFastStack = 64;              // checked against FBvh::depth at upload time
+constexpr float kU = 5.9604645e-8f;         // 2^-24, fp32 unit roundoff
+constexpr float kGamma = 2.0e-6f;           // > 32 u: bound on the relative error of an fp32 triple product
+
+struct FRay {                               // per-ray culling state (12 registers)
+    float idx, idy, idz;                    // 1 / d, |d| clamped away from 0
+    float nx, ny, nz;                       // -(o * id)
+    float px, py, pz;                       // slack covering the rounding of o, id and o * id
+    float dx, dy, dz;                       // d rounded to fp32 (triangle pre-test)
+};
+RT_D float clamp_recip(float d) {
+    const float a = fabsf(d) < 1e-30f ? copysignf(1e-30f, d) : d;
+    return 1.0f / a;
+}
+RT_D FRay make_fray(d3 o, d3 d) {
+    FRay r;
+    r.dx = __double2float_rn(d.x); r.dy = __double2float_rn(d.y); r.dz = __double2float_rn(d.z);
+    r.idx = clamp_recip(r.dx); r.idy = clamp_recip(r.dy); r.idz = clamp_recip(r.dz);
+    r.nx = -(__double2float_rn(o.x) * r.idx); r.ny = -(__double2float_rn(o.y) * r.idy); r.nz = -(__double2float_rn(o.z) * r.idz);
+    // computed slab value = true * (1 + <=3u) + delta, |delta| <= 2.1 u |o / d|  
+    r.px = 3.0f * kU * fabsf(r.nx); r.py = 3.0f * kU * fabsf(r.ny); r.pz = 3.0f * kU * fabsf(r.nz);
+    return r;
+}
+// Conservative slab test of one fp32 box against [0, tmax]: true => the f64 box may be hit.
+RT_D bool slab(const FRay &r, float lx, float ly, float lz, float hx, float hy, float hz, float tmax, float &tn) {
+    const float ax = fmaf(lx, r.idx, r.nx), bx = fmaf(hx, r.idx, r.nx);
+    const float ay = fmaf(ly, r.idy, r.ny), by = fmaf(hy, r.idy, r.ny);
+    const float az = fmaf(lz, r.idz, r.nz), bz = fmaf(hz, r.idz, r.nz);
+    tn = fmaxf(fmaxf(fminf(ax, bx) - r.px, fminf(ay, by) - r.py), fmaxf(fminf(az, bz) - r.pz, 0.0f));
+    const float tf = fminf(fminf(fmaxf(ax, bx) + r.px, fmaxf(ay, by) + r.py), fminf(fmaxf(az, bz) + r.pz, tmax));
+    return tn <= tf * 1.0000006f;           // (1 + 4u) / (1 - 4u) < 1 + 9u
+}
+
+struct FTriRec {
+    d3 a;
+    float bax, bay, baz, cax, cay, caz;
+};
+RT_D FTriRec load_ftri(const FTri *t) {
+    const double2 q0 = __ldg(reinterpret_cast<const double2 *>(t));
+    const float4 q1 = __ldg(reinterpret_cast<const float4 *>(t) + 1);
+    const float4 q2 = __ldg(reinterpret_cast<const float4 *>(t) + 2);
+    FTriRec r;
+    r.a = mk3(q0.x, q0.y, __hiloint2double(__float_as_int(q1.y), __float_as_int(q1.x)));
+    r.bax = q1.z; r.bay = q1.w; r.baz = q2.x;
+    r.cax = q2.y; r.cay = q2.z; r.caz = q2.w;
+    return r;
+}
+// fp32 pre-test: false => the exact test (triangle.rs:65-70) certainly rejects this triangle or
+// its hit lies beyond tmax.  det-scaled Moller-Trumbore: u = U/det, v = V/det, t = T/det.
+RT_D bool tri_maybe(const FTri *tp, const FRay &r, d3 o, float dl1g, float tmax) {
+    const FTriRec t = load_ftri(tp);
+    const float wx = __double2float_rn(o.x - t.a.x), wy = __double2float_rn(o.y - t.a.y), wz = __double2float_rn(o.z - t.a.z);
+    const float ppx = fmaf(r.dy, t.caz, -(r.dz * t.cay)), ppy = fmaf(r.dz, t.cax, -(r.dx * t.caz)), ppz = fmaf(r.dx, t.cay, -(r.dy * t.cax));
+    const float det = fmaf(t.bax, ppx, fmaf(t.bay, ppy, t.baz * ppz));
+    const float U = fmaf(wx, ppx, fmaf(wy, ppy, wz * ppz));
+    const float qx = fmaf(wy, t.baz, -(wz * t.bay)), qy = fmaf(wz, t.bax, -(wx * t.baz)), qz = fmaf(wx, t.bay, -(wy * t.bax));
+    const float V = fmaf(r.dx, qx, fmaf(r.dy, qy, r.dz * qz));
+    const float Tn = fmaf(t.cax, qx, fmaf(t.cay, qy, t.caz * qz));
+    const float w1 = fabsf(wx) + fabsf(wy) + fabsf(wz);
+    const float lb = fabsf(t.bax) + fabsf(t.bay) + fabsf(t.baz), lc = fabsf(t.cax) + fabsf(t.cay) + fabsf(t.caz);
+    const float eu = dl1g * w1 * lc, ev = dl1g * w1 * lb, et = kGamma * w1 * lb * lc, ed = dl1g * lb * lc;
+    const float ad = fabsf(det);
+    if (!(ad > ed)) return true;            // sign of det unknown (or NaN): the exact test decides
+    const float s = det < 0.0f ? -1.0f : 1.0f;
+    const float us = s * U, vs = s * V, ts = s * Tn;
+    if (us < -eu || vs < -ev || us + vs > ad + eu + ev + ed || ts < -et) return false;
+    if (ts > fmaf(tmax, ad + ed, et)) return false;
+    return true;
+}
+RT_D float up_f32(double t) { return __double2float_ru(t); }
+
+// ---- closest hit over the triangle hierarchy ---------------------------------------------------
+struct FBest {
+    bool has;
+    double t, u, v;
+    uint32_t prim;
+};
+RT_D void closest_fast(const FBvh f, const DTriI *tri_i, d3 o, d3 d, float tmax, FBest &best) {
+    if (f.root == kFastEmpty) return;
+    const FRay r = make_fray(o, d);
+    const float dl1g = kGamma * (fabsf(r.dx) + fabsf(r.dy) + fabsf(r.dz));
+    int32_t stk_n[kFastStack];
+    float stk_t[kFastStack];
+    int sp = 0;
+    int32_t cur = f.root;
+    for (;;) {
+        if (cur >= 0) {
+            const float4 *np = reinterpret_cast<const float4 *>(f.nodes + cur);
+            const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
+            const int4 lk = __ldg(reinterpret_cast<const int4 *>(np) + 3);
+            float t0, t1;
+            const bool h0 = slab(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tmax, t0);
+            const bool h1 = slab(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, tmax, t1);
+            if (h0 && h1) {
+                const bool first0 = t0 <= t1;
+                stk_n[sp] = first0 ? lk.y : lk.x;
+                stk_t[sp] = first0 ? t1 : t0;
+                ++sp;
+                cur = first0 ? lk.x : lk.y;
+                continue;
+            }
+            if (h0) { cur = lk.x; continue; }
+            if (h1) { cur = lk.y; continue; }
+        } else {
+            const uint32_t code = (uint32_t)~cur, first = code >> 3, count = (code & 7u) + 1u;
+            for (uint32_t i = first; i < first + count; ++i) {
+                if (!tri_maybe(f.tris + i, r, o, dl1g, tmax)) continue;
+                double t, u, v;
+                if (!tri_exact(tri_i + i, o, d, t, u, v)) continue;
+                if (!best.has || t < best.t) {
+                    best.has = true; best.t = t; best.u = u; best.v = v; best.prim = i;
+                    tmax = fminf(tmax, up_f32(t));
+                }
+            }
+        }
+        for (;;) {                          // pop, skipping children that the new best already culls
+            if (sp == 0) return;
+            --sp;
+            if (stk_t[sp] <= tmax) { cur = stk_n[sp]; break; }
+        }
+    }
+}
+
+// ---- intersections::intersect in FAST mode ------------------------------------------------------
+RT_D SceneHit intersect_fast(const DScene &sc, d3 o, d3 d, Cnt &c) {
+    SceneHit h;
+    h.kind = -1; h.prim = 0; h.material = 0; h.t = 0.0; h.inside = false;
+    h.ng = h.ns = mk3(0.0, 0.0, 0.0);
+    bool has = false;
+    for (uint32_t i = 0; i < sc.n_planes; ++i) {          // the few analytic shapes stay on the exact path
+        double t; d3 n; bool in;
+        if (!shape_closest(load_shape(sc.planes + i), o, d, t, n, in)) continue;
+        if (!has || t < h.t) { has = true; h.t = t; h.kind = 0; h.prim = i; }
+    }
+    if (sc.boxes.n_prims) {
+        const Best b = closest_exact<1>(sc.boxes, sc.box_prims, o, d, c);
+        if (b.has && (!has || b.t < h.t)) { has = true; h.t = b.t; h.kind = 1; h.prim = b.prim; }
+    }
+    if (sc.ellipsoids.n_prims) {
+        const Best e = closest_exact<2>(sc.ellipsoids, sc.ell_prims, o, d, c);
+        if (e.has && (!has || e.t < h.t)) { has = true; h.t = e.t; h.kind = 2; h.prim = e.prim; }
+    }
+    FBest fb;
+    fb.has = false; fb.t = 0.0; fb.u = 0.0; fb.v = 0.0; fb.prim = 0;
+    // a triangle only replaces an earlier category when strictly closer (intersections.rs:79),
+    // so the shapes' best distance bounds the triangle search
+    const float tmax0 = (has && h.t == h.t) ? up_f32(h.t) : __int_as_float(0x7F800000);
+    if (!(has && h.t != h.t)) closest_fast(sc.ftris, sc.tri_i, o, d, tmax0, fb);
+    if (fb.has && (!has || fb.t < h.t)) { has = true; h.t = fb.t; h.kind = 3; h.prim = fb.prim; }
+    if (!has) return h;
+    if (!(h.t * len3(d) <= dinf())) { h.kind = -1; return h; }
+    if (h.kind == 3) {
+        d3 ng, ns;
+        tri_finish(sc.tri_s + h.prim, d, fb.u, fb.v, ng, ns, h.inside);
+        const quat ident = mkq_xyzw(0.0, 0.0, 0.0, 1.0);
+        h.ng = unit3(qrot(ident, ng));
+        h.ns = unit3(qrot(ident, ns));
+        h.material = __ldg(&sc.tri_i[h.prim].material);
+    } else {
+        const DShape *sp = h.kind == 0 ? sc.planes + h.prim : (h.kind == 1 ? sc.box_prims + h.prim : sc.ell_prims + h.prim);
+        finish_shape_hit(sp, o, d, h);
+    }
+    return h;
+}
+
+// ---- Light::pdf in FAST mode ---------------------------------------------------------------------
+// All hits, no pruning, children visited left then right: the reference's DFS order
+// (src/bvh.rs:188-210), so the floating-point SUM is formed in the same order.
+RT_D void light_hits_fast(const FBvh f, const DTriI *tri_i, const DTriS *tri_s, d3 o, d3 d, double &impact) {
+    if (f.root == kFastEmpty) return;
+    const FRay r = make_fray(o, d);
+    const float dl1g = kGamma * (fabsf(r.dx) + fabsf(r.dy) + fabsf(r.dz));
+    const float inf = __int_as_float(0x7F800000);
+    int32_t stk[kFastStack];
+    int sp = 0;
+    stk[sp++] = f.root;
+    while (sp > 0) {
+        const int32_t cur = stk[--sp];
+        if (cur >= 0) {
+            const float4 *np = reinterpret_cast<const float4 *>(f.nodes + cur);
+            const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
+            const int4 lk = __ldg(reinterpret_cast<const int4 *>(np) + 3);
+            float t0, t1;
+            const bool h0 = slab(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, inf, t0);
+            const bool h1 = slab(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, inf, t1);
+            if (h1) stk[sp++] = lk.y;
+            if (h0) stk[sp++] = lk.x;
+        } else {
+            const uint32_t code = (uint32_t)~cur, first = code >> 3, count = (code & 7u) + 1u;
+            for (uint32_t i = first; i < first + count; ++i) {
+                if (!tri_maybe(f.tris + i, r, o, dl1g, inf)) continue;
+                double t, u, v;
+                if (!tri_exact(tri_i + i, o, d, t, u, v)) continue;
+                const double2 *p = reinterpret_cast<const double2 *>(tri_s + i);
+                const double2 q0 = __ldg(p), q1 = __ldg(p + 1);
+                const double inv_area = __ldg(&tri_s[i].inv_area);
+                // |d . (+-n)| is the same for the flipped normal (triangle.rs:73-77)
+                impact += inv_area * (t * t / fabs(dot3(d, mk3(q0.x, q0.y, q1.x))));
+            }
+        }
+    }
+}
+RT_D double light_pdf_fast(const DScene &sc, d3 pos, d3 dir, Cnt &c) {
+    const d3 o = add(pos, scale_l(kEps, dir));
+    double impact = 0.0;
+    ++c.lray;
+    light_hits_exact<1>(sc.lboxes, sc.lbox_prims, nullptr, o, dir, impact, c);
+    light_hits_exact<2>(sc.lellipsoids, sc.lell_prims, nullptr, o, dir, impact, c);
+    light_hits_fast(sc.fltris, sc.ltri_i, sc.ltri_s, o, dir, impact);
+    return impact / (double)sc.n_lights;
+}
+
+struct FastPolicy {
+    RT_D static SceneHit intersect(const DScene &sc, d3 o, d3 d, Cnt &c) { return intersect_fast(sc, o, d, c); }
+    RT_D static double light_pdf(const DScene &sc, d3 pos, d3 dir, Cnt &c) { return light_pdf_fast(sc, pos, dir, c); }
+};
 
 }  // namespace rt

@@ -9,9 +9,9 @@ namespace rt {
 
 struct FastHierarchy {
     std::vector<FNode> nodes;
-    std::vector<uint2> leaves;
     std::vector<FTri> tris;
-    int32_t root = INT32_MIN;
+    int32_t root = kFastEmpty;
+    uint32_t depth = 0;
 };
 void build_fast_hierarchy(const HostBvh<HostTri> &bvh, FastHierarchy &out);
 

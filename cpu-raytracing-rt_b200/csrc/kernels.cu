@@ -8,7 +8,6 @@
 #include "../../include/rt_b200.h"
 #include "fast.cuh"
 #include "kernels.hpp"
-#include "shade.cuh"
 
 namespace rt {
 
@@ -97,8 +96,12 @@ __global__ void __launch_bounds__(128) k_light_pdf(DScene sc, unsigned long long
     flush_counters(c, ctr);
 }
 
-// Megakernel: one thread per pixel walks its sample range; every (pixel, sample) path runs to
-// completion in registers.  Samples are summed in index order, so the sum is deterministic.
+// Megakernel: one persistent thread per pixel walks its sample range.  The loop is FLAT — one
+// iteration = (start the next path if the lane has none) + one bounce — so a lane whose path ended
+// regenerates immediately instead of idling until the longest path of its warp finishes; lanes of
+// a warp are then always busy with a segment (paths end after ~2 segments on average but may take
+// ray_depth).  Samples of a pixel are still summed in index order, so the sum is deterministic and
+// independent of how sample ranges are split across launches or GPUs.
 template <class POLICY>
 __global__ void __launch_bounds__(128) k_render_mega(DScene sc, uint32_t sample_begin, uint32_t sample_count,
                                                      unsigned long long seed, double *__restrict__ accum, DCounters *ctr) {
@@ -107,17 +110,32 @@ __global__ void __launch_bounds__(128) k_render_mega(DScene sc, uint32_t sample_
     if (tile_pixel(sc.width, sc.height, x, y)) {
         const uint32_t p = y * sc.width + x;
         d3 sum = mk3(accum[(size_t)p * 3], accum[(size_t)p * 3 + 1], accum[(size_t)p * 3 + 2]);
-        for (uint32_t s = 0; s < sample_count; ++s) {
-            Rng rng;
-            rng.init(seed, p, sample_begin + s);
-            const double jx = rng.range(0.0, 1.0), jy = rng.range(0.0, 1.0);       // camera.rs:49-50
-            d3 o, d;
-            camera_ray(sc.cam, x, y, jx, jy, o, d);
-            ++c.paths;
-            d3 T = mk3(1.0, 1.0, 1.0), L = mk3(0.0, 0.0, 0.0);
-            for (uint32_t left = sc.ray_depth; left > 0; --left)                    // raytrace.rs:13
-                if (!bounce<POLICY>(sc, o, d, T, L, rng, c)) break;
-            sum = add(sum, L);                                                      // main.rs:102
+        Rng rng;
+        d3 o = mk3(0.0, 0.0, 0.0), d = o, T = o, L = o;
+        uint32_t s = 0, left = 0;
+        bool alive = false;
+        for (;;) {
+            if (!alive) {
+                if (s == sample_count) break;
+                rng.init(seed, p, sample_begin + s);
+                const double jx = rng.range(0.0, 1.0), jy = rng.range(0.0, 1.0);   // camera.rs:49-50
+                camera_ray(sc.cam, x, y, jx, jy, o, d);
+                ++c.paths;
+                T = mk3(1.0, 1.0, 1.0);
+                L = mk3(0.0, 0.0, 0.0);
+                left = sc.ray_depth;                                                // raytrace.rs:9
+                alive = true;
+            }
+            bool more = false;
+            if (left > 0) {                                                         // raytrace.rs:13
+                more = bounce<POLICY>(sc, o, d, T, L, rng, c);
+                --left;
+            }
+            if (!more || left == 0) {
+                sum = add(sum, L);                                                  // main.rs:102
+                alive = false;
+                ++s;
+            }
         }
         accum[(size_t)p * 3] = sum.x; accum[(size_t)p * 3 + 1] = sum.y; accum[(size_t)p * 3 + 2] = sum.z;
     }
