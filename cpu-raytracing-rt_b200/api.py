@@ -19,7 +19,7 @@ _LIB = None
 SYMBOLS = [
     "rt_scene_build", "rt_scene_free", "rt_scene_load_text", "rt_scene_load_gltf", "rt_scene_get_info",
     "rt_scene_get_bvh", "rt_scene_get_triangle", "rt_scene_get_shape", "rt_scene_get_material", "rt_save_ppm",
-    "rt_device_count", "rt_create", "rt_destroy", "rt_last_error", "rt_upload_scene", "rt_trace_rays",
+    "rt_device_count", "rt_create", "rt_destroy", "rt_last_error", "rt_upload_scene", "rt_scene_device_bytes", "rt_trace_rays",
     "rt_trace_primary", "rt_light_pdf", "rt_render_accum", "rt_accum_device_ptr", "rt_get_accum", "rt_set_accum",
     "rt_postprocess", "rt_render", "rt_sync", "rt_stream", "rt_get_counters", "rt_reset_counters", "rt_debug_rng",
 ]
@@ -66,6 +66,7 @@ def lib():
         L.rt_last_error.argtypes = [vp]
         L.rt_last_error.restype = C.c_char_p
         L.rt_upload_scene.argtypes = [vp, vp]
+        L.rt_scene_device_bytes.argtypes = [vp, C.POINTER(u64)]
         L.rt_trace_rays.argtypes = [vp, i32, u64, vp, vp, vp]
         L.rt_trace_primary.argtypes = [vp, i32, dbl, dbl, vp, vp]
         L.rt_light_pdf.argtypes = [vp, i32, u64, vp, vp, vp]
@@ -230,6 +231,20 @@ class Context:
         out = np.zeros((self.scene.height, self.scene.width, 3))
         _check(lib().rt_postprocess(self._h, total_samples, _p(out)), self._h)
         return out
+
+    def postprocess_device(self, total_samples):
+        """tonemap + gamma on the device only (asynchronous; the image stays in HBM)"""
+        _check(lib().rt_postprocess(self._h, total_samples, None), self._h)
+
+    def postprocess_into(self, total_samples, out):
+        assert out.dtype == np.float64 and out.flags["C_CONTIGUOUS"] and out.size == self.scene.width * self.scene.height * 3
+        _check(lib().rt_postprocess(self._h, total_samples, _p(out)), self._h)
+        return out
+
+    def scene_device_bytes(self):
+        n = C.c_uint64()
+        _check(lib().rt_scene_device_bytes(self._h, C.byref(n)), self._h)
+        return n.value
 
     def render(self, seed=0xC0FFEE, mode=T.MODE_FAST, sched=T.SCHED_MEGAKERNEL):
         out = np.zeros((self.scene.height, self.scene.width, 3))

@@ -24,7 +24,8 @@ struct rt_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     std::string err;
-    std::vector<void *> scene_allocs;
+    char *arena = nullptr;              // one device allocation holding every scene record
+    size_t arena_cap = 0, arena_used = 0;
     DScene dsc{};
     bool has_scene = false;
     double *d_accum = nullptr, *d_rgb = nullptr;
@@ -32,6 +33,7 @@ struct rt_ctx {
     DCounters *d_ctr = nullptr;
     uint64_t launches = 0;
     uint32_t samples = 0;
+    size_t scene_bytes = 0;
 };
 
 namespace {
@@ -61,26 +63,32 @@ int guarded(rt_ctx *ctx, int code_on_throw, F &&f) {
     }
 }
 
-void free_scene(rt_ctx *ctx) {
-    for (void *p : ctx->scene_allocs) cudaFree(p);
-    ctx->scene_allocs.clear();
-    if (ctx->d_accum) cudaFree(ctx->d_accum);
-    if (ctx->d_rgb) cudaFree(ctx->d_rgb);
-    ctx->d_accum = ctx->d_rgb = nullptr;
+void free_scene(rt_ctx *ctx, bool keep_arena) {
+    if (!keep_arena) {
+        if (ctx->arena) cudaFree(ctx->arena);
+        ctx->arena = nullptr;
+        ctx->arena_cap = 0;
+        if (ctx->d_accum) cudaFree(ctx->d_accum);
+        if (ctx->d_rgb) cudaFree(ctx->d_rgb);
+        ctx->d_accum = ctx->d_rgb = nullptr;
+        ctx->n_px = 0;
+    }
+    ctx->arena_used = 0;
     ctx->has_scene = false;
 }
+
+inline size_t align_up(size_t n) { return (n + 255) & ~(size_t)255; }
 
 template <class T>
 cudaError_t upload(rt_ctx *ctx, const std::vector<T> &v, const T **out) {
     *out = nullptr;
     if (v.empty()) return cudaSuccess;
-    void *p = nullptr;
-    cudaError_t e = cudaMalloc(&p, v.size() * sizeof(T));
-    if (e != cudaSuccess) return e;
-    ctx->scene_allocs.push_back(p);
-    e = cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream);
+    const size_t bytes = v.size() * sizeof(T);
+    if (ctx->arena_used + align_up(bytes) > ctx->arena_cap) return cudaErrorMemoryAllocation;
+    char *p = ctx->arena + ctx->arena_used;
+    ctx->arena_used += align_up(bytes);
     *out = (const T *)p;
-    return e;
+    return cudaMemcpyAsync(p, v.data(), bytes, cudaMemcpyHostToDevice, ctx->stream);
 }
 
 std::vector<DNode> flatten_nodes(const std::vector<HostNode> &nodes) {
@@ -131,6 +139,60 @@ void flatten_tris(const std::vector<HostTri> &v, std::vector<DTriI> &ti, std::ve
         s.material = t.material;
         ts[i] = s;
     }
+}
+
+// Everything rt_upload_scene copies, flattened once per rt_scene and kept page-locked so that
+// repeated uploads (one per generate_image call) are plain DMA transfers.
+}  // namespace
+struct rt_device_image {
+    struct ShapeSet { std::vector<DNode> nodes; std::vector<DShape> prims; };
+    struct TriSet { std::vector<DNode> nodes; std::vector<DTriI> ti; std::vector<DTriS> ts; FastHierarchy fh; };
+    ShapeSet shapes[4];                 // boxes, ellipsoids, light boxes, light ellipsoids
+    std::vector<DShape> planes;
+    TriSet tris[2];                     // scene, lights
+    std::vector<DMaterial> mats;
+    std::vector<std::pair<void *, size_t>> pinned;
+    size_t total_bytes = 0;
+    template <class T>
+    void pin(std::vector<T> &v) {
+        total_bytes += align_up(v.size() * sizeof(T));
+        if (v.empty()) return;
+        if (cudaHostRegister(v.data(), v.size() * sizeof(T), cudaHostRegisterDefault) == cudaSuccess) pinned.emplace_back(v.data(), v.size() * sizeof(T));
+        else cudaGetLastError();
+    }
+    ~rt_device_image() { for (auto &p : pinned) cudaHostUnregister(p.first); }
+};
+namespace {
+std::shared_ptr<rt_device_image> make_image(const HostScene &s) {
+    auto im = std::make_shared<rt_device_image>();
+    const HostBvh<HostShape> *sh[4] = {&s.boxes, &s.ellipsoids, &s.light_boxes, &s.light_ellipsoids};
+    for (int k = 0; k < 4; ++k) {
+        im->shapes[k].nodes = flatten_nodes(sh[k]->nodes);
+        im->shapes[k].prims = flatten_shapes(sh[k]->prims);
+    }
+    im->planes = flatten_shapes(s.planes);
+    const HostBvh<HostTri> *tr[2] = {&s.tris, &s.light_tris};
+    for (int k = 0; k < 2; ++k) {
+        im->tris[k].nodes = flatten_nodes(tr[k]->nodes);
+        flatten_tris(tr[k]->prims, im->tris[k].ti, im->tris[k].ts);
+        build_fast_hierarchy(*tr[k], im->tris[k].fh);
+    }
+    im->mats.resize(s.materials.size());
+    for (size_t i = 0; i < im->mats.size(); ++i) {
+        DMaterial m{};
+        for (int k = 0; k < 3; ++k) { m.color[k] = s.materials[i].color[k]; m.emission[k] = s.materials[i].emission[k]; }
+        m.ior = s.materials[i].ior;
+        m.kind = s.materials[i].kind;
+        im->mats[i] = m;
+    }
+    int ndev = 0;
+    const bool cuda_ok = cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0;
+    if (!cuda_ok) cudaGetLastError();
+    for (int k = 0; k < 4; ++k) { im->pin(im->shapes[k].nodes); im->pin(im->shapes[k].prims); }
+    im->pin(im->planes);
+    for (int k = 0; k < 2; ++k) { im->pin(im->tris[k].nodes); im->pin(im->tris[k].ti); im->pin(im->tris[k].ts); im->pin(im->tris[k].fh.nodes); im->pin(im->tris[k].fh.tris); }
+    im->pin(im->mats);
+    return im;
 }
 
 int need_scene(rt_ctx *ctx) {
@@ -325,7 +387,7 @@ void rt_destroy(rt_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    free_scene(ctx);
+    free_scene(ctx, false);
     if (ctx->d_ctr) cudaFree(ctx->d_ctr);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -341,66 +403,69 @@ int rt_upload_scene(rt_ctx *ctx, const rt_scene *scene) {
             return set_err(ctx, RT_ERR_LIMIT, "BVH depth " + std::to_string(d) + " exceeds the traversal stack (" + std::to_string(kExactStackHost) + ")");
     return guarded(ctx, RT_ERR_INVALID_ARG, [&]() -> int {
         CK(ctx, cudaSetDevice(ctx->device));
+        if (!scene->image) scene->image = make_image(s);
+        const rt_device_image &im = *scene->image;
+        for (int k = 0; k < 2; ++k)
+            if (im.tris[k].fh.depth + 2 > (uint32_t)kFastStackHost)
+                return set_err(ctx, RT_ERR_LIMIT, "fp32 hierarchy depth " + std::to_string(im.tris[k].fh.depth) + " exceeds the traversal stack");
         CK(ctx, cudaStreamSynchronize(ctx->stream));
-        free_scene(ctx);
+        const size_t n_px = (size_t)s.width * s.height;
+        const bool keep = ctx->arena_cap >= im.total_bytes && ctx->n_px == n_px;
+        free_scene(ctx, keep);
+        if (!keep) {
+            CK(ctx, cudaMalloc(&ctx->arena, im.total_bytes ? im.total_bytes : 256));
+            ctx->arena_cap = im.total_bytes;
+            ctx->n_px = n_px;
+            CK(ctx, cudaMalloc(&ctx->d_accum, n_px * 3 * sizeof(double)));
+            CK(ctx, cudaMalloc(&ctx->d_rgb, n_px * 3 * sizeof(double)));
+        }
         DScene d{};
-        struct Pair { const HostBvh<HostShape> *b; DBvh *dst; const DShape **prims; };
-        Pair shapes[4] = {{&s.boxes, &d.boxes, &d.box_prims}, {&s.ellipsoids, &d.ellipsoids, &d.ell_prims},
-                          {&s.light_boxes, &d.lboxes, &d.lbox_prims}, {&s.light_ellipsoids, &d.lellipsoids, &d.lell_prims}};
-        for (Pair &p : shapes) {
-            CK(ctx, upload(ctx, flatten_nodes(p.b->nodes), &p.dst->nodes));
-            CK(ctx, upload(ctx, flatten_shapes(p.b->prims), p.prims));
-            p.dst->n_nodes = (uint32_t)p.b->nodes.size();
-            p.dst->n_prims = (uint32_t)p.b->prims.size();
+        DBvh *sb[4] = {&d.boxes, &d.ellipsoids, &d.lboxes, &d.lellipsoids};
+        const DShape **sp[4] = {&d.box_prims, &d.ell_prims, &d.lbox_prims, &d.lell_prims};
+        for (int k = 0; k < 4; ++k) {
+            CK(ctx, upload(ctx, im.shapes[k].nodes, &sb[k]->nodes));
+            CK(ctx, upload(ctx, im.shapes[k].prims, sp[k]));
+            sb[k]->n_nodes = (uint32_t)im.shapes[k].nodes.size();
+            sb[k]->n_prims = (uint32_t)im.shapes[k].prims.size();
         }
-        CK(ctx, upload(ctx, flatten_shapes(s.planes), &d.planes));
-        d.n_planes = (uint32_t)s.planes.size();
-        struct TPair { const HostBvh<HostTri> *b; DBvh *dst; const DTriI **ti; const DTriS **ts; FBvh *f; };
-        TPair tris[2] = {{&s.tris, &d.tris, &d.tri_i, &d.tri_s, &d.ftris}, {&s.light_tris, &d.ltris, &d.ltri_i, &d.ltri_s, &d.fltris}};
-        for (TPair &p : tris) {
-            std::vector<DTriI> ti;
-            std::vector<DTriS> ts;
-            flatten_tris(p.b->prims, ti, ts);
-            CK(ctx, upload(ctx, flatten_nodes(p.b->nodes), &p.dst->nodes));
-            CK(ctx, upload(ctx, ti, p.ti));
-            CK(ctx, upload(ctx, ts, p.ts));
-            p.dst->n_nodes = (uint32_t)p.b->nodes.size();
-            p.dst->n_prims = (uint32_t)p.b->prims.size();
-            FastHierarchy fh;
-            build_fast_hierarchy(*p.b, fh);
-            if (fh.depth + 2 > (uint32_t)kFastStackHost)
-                return set_err(ctx, RT_ERR_LIMIT, "fp32 hierarchy depth " + std::to_string(fh.depth) + " exceeds the traversal stack");
-            CK(ctx, upload(ctx, fh.nodes, &p.f->nodes));
-            CK(ctx, upload(ctx, fh.tris, &p.f->tris));
-            p.f->root = fh.root;
-            p.f->depth = fh.depth;
-            CK(ctx, cudaStreamSynchronize(ctx->stream));       // staging vectors die at scope end
+        CK(ctx, upload(ctx, im.planes, &d.planes));
+        d.n_planes = (uint32_t)im.planes.size();
+        DBvh *tb[2] = {&d.tris, &d.ltris};
+        const DTriI **ti[2] = {&d.tri_i, &d.ltri_i};
+        const DTriS **ts[2] = {&d.tri_s, &d.ltri_s};
+        FBvh *fb[2] = {&d.ftris, &d.fltris};
+        for (int k = 0; k < 2; ++k) {
+            CK(ctx, upload(ctx, im.tris[k].nodes, &tb[k]->nodes));
+            CK(ctx, upload(ctx, im.tris[k].ti, ti[k]));
+            CK(ctx, upload(ctx, im.tris[k].ts, ts[k]));
+            tb[k]->n_nodes = (uint32_t)im.tris[k].nodes.size();
+            tb[k]->n_prims = (uint32_t)im.tris[k].ti.size();
+            CK(ctx, upload(ctx, im.tris[k].fh.nodes, &fb[k]->nodes));
+            CK(ctx, upload(ctx, im.tris[k].fh.tris, &fb[k]->tris));
+            fb[k]->root = im.tris[k].fh.root;
+            fb[k]->depth = im.tris[k].fh.depth;
         }
-        std::vector<DMaterial> mats(s.materials.size());
-        for (size_t i = 0; i < mats.size(); ++i) {
-            DMaterial m{};
-            for (int k = 0; k < 3; ++k) { m.color[k] = s.materials[i].color[k]; m.emission[k] = s.materials[i].emission[k]; }
-            m.ior = s.materials[i].ior;
-            m.kind = s.materials[i].kind;
-            mats[i] = m;
-        }
-        CK(ctx, upload(ctx, mats, &d.materials));
+        CK(ctx, upload(ctx, im.mats, &d.materials));
         d.n_lights = (uint32_t)(s.light_boxes.prims.size() + s.light_ellipsoids.prims.size() + s.light_tris.prims.size());
         d.width = s.width; d.height = s.height; d.ray_depth = s.ray_depth;
         d.cam.position = s.cam_position; d.cam.right = s.cam_right; d.cam.up = s.cam_up; d.cam.forward = s.cam_forward;
         d.cam.tan_half_fov_x = s.tan_half_fov_x; d.cam.tan_half_fov_y = s.tan_half_fov_y;
         d.cam.width = (double)s.width; d.cam.height = (double)s.height;
         d.bg = s.bg_color;
-        ctx->n_px = (size_t)s.width * s.height;
-        CK(ctx, cudaMalloc(&ctx->d_accum, ctx->n_px * 3 * sizeof(double)));
-        CK(ctx, cudaMalloc(&ctx->d_rgb, ctx->n_px * 3 * sizeof(double)));
-        CK(ctx, cudaMemsetAsync(ctx->d_accum, 0, ctx->n_px * 3 * sizeof(double), ctx->stream));
+        CK(ctx, cudaMemsetAsync(ctx->d_accum, 0, n_px * 3 * sizeof(double), ctx->stream));
         CK(ctx, cudaStreamSynchronize(ctx->stream));
         ctx->dsc = d;
         ctx->samples = s.samples;
+        ctx->scene_bytes = ctx->arena_used;
         ctx->has_scene = true;
         return RT_OK;
     });
+}
+int rt_scene_device_bytes(rt_ctx *ctx, uint64_t *bytes) {
+    if (int r = need_scene(ctx)) return r;
+    if (!bytes) return set_err(ctx, RT_ERR_INVALID_ARG, "null argument");
+    *bytes = ctx->scene_bytes;
+    return RT_OK;
 }
 
 int rt_trace_rays(rt_ctx *ctx, int mode, uint64_t n, const double *origins, const double *dirs, rt_hit *hits) {
@@ -486,9 +551,9 @@ int rt_set_accum(rt_ctx *ctx, const double *sum_rgb) {
 }
 int rt_postprocess(rt_ctx *ctx, uint32_t total_samples, double *rgb_out) {
     if (int r = need_scene(ctx)) return r;
-    if (!rgb_out) return set_err(ctx, RT_ERR_INVALID_ARG, "null argument");
     CK(ctx, launch_postprocess(ctx->stream, ctx->n_px * 3, ctx->d_accum, total_samples, ctx->d_rgb));
     ++ctx->launches;
+    if (!rgb_out) return RT_OK;         // device-only (asynchronous): the image stays in HBM
     CK(ctx, cudaMemcpyAsync(rgb_out, ctx->d_rgb, ctx->n_px * 24, cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     return RT_OK;

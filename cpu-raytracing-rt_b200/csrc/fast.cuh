@@ -67,9 +67,12 @@ RT_D FTriRec load_ftri(const FTri *t) {
     r.cax = q2.y; r.cay = q2.z; r.caz = q2.w;
     return r;
 }
-// fp32 pre-test: false => the exact test (triangle.rs:65-70) certainly rejects this triangle or
-// its hit lies beyond tmax.  det-scaled Moller-Trumbore: u = U/det, v = V/det, t = T/det.
-RT_D bool tri_maybe(const FTri *tp, const FRay &r, d3 o, float dl1g, float tmax) {
+// fp32 pre-test in determinant-scaled Moller-Trumbore form (u = U/det, v = V/det, t = T/det).
+// Returns 0: the exact test (triangle.rs:65-70) certainly rejects, or the hit lies beyond tmax;
+//         1: undecided (within the error bound of an edge / of det = 0);
+//         2: the exact test certainly accepts.
+// For 1 and 2, [tlo, thi] bounds the distance the exact test would report.
+RT_D int tri_classify(const FTri *tp, const FRay &r, d3 o, float dl1g, float tmax, float &tlo, float &thi) {
     const FTriRec t = load_ftri(tp);
     const float wx = __double2float_rn(o.x - t.a.x), wy = __double2float_rn(o.y - t.a.y), wz = __double2float_rn(o.z - t.a.z);
     const float ppx = fmaf(r.dy, t.caz, -(r.dz * t.cay)), ppy = fmaf(r.dz, t.cax, -(r.dx * t.caz)), ppz = fmaf(r.dx, t.cay, -(r.dy * t.cax));
@@ -82,31 +85,57 @@ RT_D bool tri_maybe(const FTri *tp, const FRay &r, d3 o, float dl1g, float tmax)
     const float lb = fabsf(t.bax) + fabsf(t.bay) + fabsf(t.baz), lc = fabsf(t.cax) + fabsf(t.cay) + fabsf(t.caz);
     const float eu = dl1g * w1 * lc, ev = dl1g * w1 * lb, et = kGamma * w1 * lb * lc, ed = dl1g * lb * lc;
     const float ad = fabsf(det);
-    if (!(ad > ed)) return true;            // sign of det unknown (or NaN): the exact test decides
+    const float inf = __int_as_float(0x7F800000);
+    if (!(ad > ed)) { tlo = 0.0f; thi = inf; return 1; }       // sign of det unknown (or NaN)
     const float s = det < 0.0f ? -1.0f : 1.0f;
     const float us = s * U, vs = s * V, ts = s * Tn;
-    if (us < -eu || vs < -ev || us + vs > ad + eu + ev + ed || ts < -et) return false;
-    if (ts > fmaf(tmax, ad + ed, et)) return false;
-    return true;
+    if (us < -eu || vs < -ev || us + vs > ad + eu + ev + ed || ts < -et) return 0;
+    if (ts > fmaf(tmax, ad + ed, et)) return 0;
+    tlo = fmaxf(0.0f, __fdividef(ts - et, ad + ed) * 0.9999995f);
+    const float den = ad - ed;
+    thi = den > 1e-30f ? __fdividef(ts + et, den) * 1.0000005f : inf;
+    if (!(thi == thi)) thi = inf;
+    // the exact test also rejects |det| < 1e-11 (triangle.rs:51): "certain" needs det well above it
+    const bool certain = us >= eu && vs >= ev && us + vs <= ad - (eu + ev + ed) && ts >= et && den > 1e-9f;
+    return certain ? 2 : 1;
 }
 RT_D float up_f32(double t) { return __double2float_ru(t); }
 
 // ---- closest hit over the triangle hierarchy ---------------------------------------------------
+// The loop below is fp32 only.  Candidates that survive the pre-test are DEFERRED to a short
+// list and confirmed with the reference's f64 arithmetic after the loop, when the whole warp
+// has left it: an exact test is ~400 f64 instructions and would otherwise run with one or two
+// lanes active while the other lanes of the warp wait.  "Certain" fp32 hits still tighten tmax
+// (with the upper bound of their distance), so pruning works as if the hit were confirmed.
+constexpr int kCand = 6;
 struct FBest {
     bool has;
     double t, u, v;
     uint32_t prim;
 };
+RT_D void confirm(const DTriI *tri_i, d3 o, d3 d, uint32_t prim, FBest &best, float &tmax) {
+    double t, u, v;
+    if (!tri_exact(tri_i + prim, o, d, t, u, v)) return;
+    if (!best.has || t < best.t) {
+        best.has = true; best.t = t; best.u = u; best.v = v; best.prim = prim;
+        tmax = fminf(tmax, up_f32(t));
+    }
+}
 RT_D void closest_fast(const FBvh f, const DTriI *tri_i, d3 o, d3 d, float tmax, FBest &best) {
     if (f.root == kFastEmpty) return;
     const FRay r = make_fray(o, d);
     const float dl1g = kGamma * (fabsf(r.dx) + fabsf(r.dy) + fabsf(r.dz));
     int32_t stk_n[kFastStack];
     float stk_t[kFastStack];
-    int sp = 0;
+    uint32_t cand_p[kCand];
+    float cand_t[kCand];
+    int nc = 0, sp = 0;
     int32_t cur = f.root;
-    for (;;) {
-        if (cur >= 0) {
+    // "while-while": all lanes first walk inner nodes until each holds a leaf (or is done), then
+    // all lanes that hold a leaf run the triangle pre-tests together.  kFastEmpty doubles as the
+    // "nothing left" marker (it is negative and never a valid leaf code of a non-empty tree).
+    while (cur != kFastEmpty) {
+        while (cur >= 0) {
             const float4 *np = reinterpret_cast<const float4 *>(f.nodes + cur);
             const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
             const int4 lk = __ldg(reinterpret_cast<const int4 *>(np) + 3);
@@ -119,28 +148,44 @@ RT_D void closest_fast(const FBvh f, const DTriI *tri_i, d3 o, d3 d, float tmax,
                 stk_t[sp] = first0 ? t1 : t0;
                 ++sp;
                 cur = first0 ? lk.x : lk.y;
-                continue;
-            }
-            if (h0) { cur = lk.x; continue; }
-            if (h1) { cur = lk.y; continue; }
-        } else {
-            const uint32_t code = (uint32_t)~cur, first = code >> 3, count = (code & 7u) + 1u;
-            for (uint32_t i = first; i < first + count; ++i) {
-                if (!tri_maybe(f.tris + i, r, o, dl1g, tmax)) continue;
-                double t, u, v;
-                if (!tri_exact(tri_i + i, o, d, t, u, v)) continue;
-                if (!best.has || t < best.t) {
-                    best.has = true; best.t = t; best.u = u; best.v = v; best.prim = i;
-                    tmax = fminf(tmax, up_f32(t));
+            } else if (h0) {
+                cur = lk.x;
+            } else if (h1) {
+                cur = lk.y;
+            } else {
+                cur = kFastEmpty;
+                while (sp > 0) {                    // pop, skipping children the bound now excludes
+                    --sp;
+                    if (stk_t[sp] <= tmax) { cur = stk_n[sp]; break; }
                 }
             }
         }
-        for (;;) {                          // pop, skipping children that the new best already culls
-            if (sp == 0) return;
+        if (cur == kFastEmpty) break;
+        {
+            const uint32_t code = (uint32_t)~cur, first = code >> 3, count = (code & 7u) + 1u;
+            for (uint32_t i = first; i < first + count; ++i) {
+                float tlo, thi;
+                const int cls = tri_classify(f.tris + i, r, o, dl1g, tmax, tlo, thi);
+                if (cls == 0) continue;
+                if (cls == 2) tmax = fminf(tmax, thi);
+                if (nc == kCand) {                  // rare: drop entries the new bound excludes
+                    int k = 0;
+                    for (int j = 0; j < kCand; ++j)
+                        if (cand_t[j] <= tmax) { cand_p[k] = cand_p[j]; cand_t[k] = cand_t[j]; ++k; }
+                    nc = k;
+                }
+                if (nc == kCand) { confirm(tri_i, o, d, i, best, tmax); continue; }   // very rare
+                cand_p[nc] = i; cand_t[nc] = tlo; ++nc;
+            }
+        }
+        cur = kFastEmpty;
+        while (sp > 0) {
             --sp;
             if (stk_t[sp] <= tmax) { cur = stk_n[sp]; break; }
         }
     }
+    for (int j = 0; j < nc; ++j)                    // warp-converged f64 confirmation
+        if (cand_t[j] <= tmax) confirm(tri_i, o, d, cand_p[j], best, tmax);
 }
 
 // ---- intersections::intersect in FAST mode ------------------------------------------------------
@@ -188,13 +233,23 @@ RT_D SceneHit intersect_fast(const DScene &sc, d3 o, d3 d, Cnt &c) {
 // ---- Light::pdf in FAST mode ---------------------------------------------------------------------
 // All hits, no pruning, children visited left then right: the reference's DFS order
 // (src/bvh.rs:188-210), so the floating-point SUM is formed in the same order.
+RT_D void light_confirm(const DTriI *tri_i, const DTriS *tri_s, d3 o, d3 d, uint32_t i, double &impact) {
+    double t, u, v;
+    if (!tri_exact(tri_i + i, o, d, t, u, v)) return;
+    const double2 *p = reinterpret_cast<const double2 *>(tri_s + i);
+    const double2 q0 = __ldg(p), q1 = __ldg(p + 1);
+    const double inv_area = __ldg(&tri_s[i].inv_area);
+    // |d . (+-n)| is the same for the flipped normal (triangle.rs:73-77)
+    impact += inv_area * (t * t / fabs(dot3(d, mk3(q0.x, q0.y, q1.x))));
+}
 RT_D void light_hits_fast(const FBvh f, const DTriI *tri_i, const DTriS *tri_s, d3 o, d3 d, double &impact) {
     if (f.root == kFastEmpty) return;
     const FRay r = make_fray(o, d);
     const float dl1g = kGamma * (fabsf(r.dx) + fabsf(r.dy) + fabsf(r.dz));
     const float inf = __int_as_float(0x7F800000);
     int32_t stk[kFastStack];
-    int sp = 0;
+    uint32_t cand[kCand];
+    int sp = 0, nc = 0;
     stk[sp++] = f.root;
     while (sp > 0) {
         const int32_t cur = stk[--sp];
@@ -210,17 +265,17 @@ RT_D void light_hits_fast(const FBvh f, const DTriI *tri_i, const DTriS *tri_s, 
         } else {
             const uint32_t code = (uint32_t)~cur, first = code >> 3, count = (code & 7u) + 1u;
             for (uint32_t i = first; i < first + count; ++i) {
-                if (!tri_maybe(f.tris + i, r, o, dl1g, inf)) continue;
-                double t, u, v;
-                if (!tri_exact(tri_i + i, o, d, t, u, v)) continue;
-                const double2 *p = reinterpret_cast<const double2 *>(tri_s + i);
-                const double2 q0 = __ldg(p), q1 = __ldg(p + 1);
-                const double inv_area = __ldg(&tri_s[i].inv_area);
-                // |d . (+-n)| is the same for the flipped normal (triangle.rs:73-77)
-                impact += inv_area * (t * t / fabs(dot3(d, mk3(q0.x, q0.y, q1.x))));
+                float tlo, thi;
+                if (tri_classify(f.tris + i, r, o, dl1g, inf, tlo, thi) == 0) continue;
+                if (nc == kCand) {                  // flush in visit order, then keep collecting
+                    for (int j = 0; j < kCand; ++j) light_confirm(tri_i, tri_s, o, d, cand[j], impact);
+                    nc = 0;
+                }
+                cand[nc++] = i;
             }
         }
     }
+    for (int j = 0; j < nc; ++j) light_confirm(tri_i, tri_s, o, d, cand[j], impact);   // same order as visited
 }
 RT_D double light_pdf_fast(const DScene &sc, d3 pos, d3 dir, Cnt &c) {
     const d3 o = add(pos, scale_l(kEps, dir));

@@ -3,6 +3,7 @@
 // primitives in post-build order plus the six hierarchies of src/bvh.rs.
 #pragma once
 #include <cstdint>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -83,6 +84,8 @@ void save_ppm(const std::string &path, uint32_t w, uint32_t h, const double *rgb
 
 }  // namespace rt
 
+struct rt_device_image;                 // flattened, page-locked copy of the scene (capi.cpp)
 struct rt_scene {
     rt::HostScene s;
+    mutable std::shared_ptr<rt_device_image> image;     // built on the first rt_upload_scene
 };

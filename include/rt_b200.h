@@ -154,6 +154,8 @@ RT_API const char *rt_last_error(const rt_ctx *ctx);    /* ctx may be NULL: last
 /* Flatten Scene (src/scene.rs:82-90) + its six BVHs (src/bvh.rs:6-9, :49-54) into device
  * buffers; replaces any previous scene of the context. */
 RT_API int rt_upload_scene(rt_ctx *ctx, const rt_scene *scene);
+/* Bytes of scene records resident in HBM after the last upload (= H2D bytes of one upload). */
+RT_API int rt_scene_device_bytes(rt_ctx *ctx, uint64_t *bytes);
 
 /* Arithmetic modes.  EXACT follows the reference operation for operation in f64 (divisions
  * included) and its DFS visit order: it is the parity anchor.  FAST culls with conservative
@@ -206,7 +208,8 @@ RT_API int rt_accum_device_ptr(rt_ctx *ctx, void **dptr, uint64_t *n_doubles);
 RT_API int rt_get_accum(rt_ctx *ctx, double *sum_rgb);          /* D2H, W*H*3 */
 RT_API int rt_set_accum(rt_ctx *ctx, const double *sum_rgb);    /* H2D, W*H*3 */
 /* correct_gamma(aces_tonemap(sum / total_samples)) (src/main.rs:104, src/postprocessing.rs),
- * on the device; rgb_out = W*H*3 doubles on the host (the reference's Image.bytes). */
+ * on the device; rgb_out = W*H*3 doubles on the host (the reference's Image.bytes), or NULL to
+ * leave the image in HBM (asynchronous). */
 RT_API int rt_postprocess(rt_ctx *ctx, uint32_t total_samples, double *rgb_out);
 /* generate_image (src/main.rs:85-114) in one call: clear, accumulate scene.samples samples,
  * postprocess, copy to host. */
