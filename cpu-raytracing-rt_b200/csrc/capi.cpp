@@ -34,6 +34,12 @@ struct rt_ctx {
     uint64_t launches = 0;
     uint32_t samples = 0;
     size_t scene_bytes = 0;
+    // wavefront scheduler state (allocated on first use, sized by the image)
+    char *wf_arena = nullptr;
+    WfBuf wf{};
+    uint32_t *wf_host_live = nullptr;   // pinned
+    cudaEvent_t wf_event = nullptr;
+    int wf_blocks = 0;
 };
 
 namespace {
@@ -63,8 +69,50 @@ int guarded(rt_ctx *ctx, int code_on_throw, F &&f) {
     }
 }
 
+void free_wavefront(rt_ctx *ctx) {
+    if (ctx->wf_arena) cudaFree(ctx->wf_arena);
+    ctx->wf_arena = nullptr;
+    ctx->wf = WfBuf{};
+}
+cudaError_t ensure_wavefront(rt_ctx *ctx) {
+    const uint32_t n = (uint32_t)ctx->n_px;
+    if (ctx->wf_arena && ctx->wf.n == n) return cudaSuccess;
+    free_wavefront(ctx);
+    const size_t per = (wf_bytes_per_slot() + 15) & ~(size_t)15;
+    const size_t total = per * n + 65536;
+    cudaError_t e = cudaMalloc(&ctx->wf_arena, total);
+    if (e != cudaSuccess) return e;
+    char *p = ctx->wf_arena;
+    auto take = [&](size_t bytes) { char *r = p; p += (bytes + 255) & ~(size_t)255; return r; };
+    WfBuf &b = ctx->wf;
+    b.n = n;
+    double **d3s[5] = {&b.ro, &b.rd, &b.T, &b.L, &b.pv};
+    for (double **q : d3s) *q = (double *)take((size_t)n * 24);
+    double **d1s[3] = {&b.pcos, &b.pimp, &b.sh_t};
+    for (double **q : d1s) *q = (double *)take((size_t)n * 8);
+    uint32_t **u1s[7] = {&b.sh_id, &b.rng_block, &b.rng_s0, &b.rng_s1, &b.sample, &b.flags, &b.ncand};
+    for (uint32_t **q : u1s) *q = (uint32_t *)take((size_t)n * 4);
+    b.cand = (uint32_t *)take((size_t)n * 4 * kWfCand);
+    b.lcand = (uint32_t *)take((size_t)n * 4 * kWfCand);
+    b.cand_t = (float *)take((size_t)n * 4 * kWfCand);
+    b.live[0] = (uint32_t *)take((size_t)n * 4);
+    b.live[1] = (uint32_t *)take((size_t)n * 4);
+    b.n_live = (uint32_t *)take(8);
+    b.cursor = (uint32_t *)take(4);
+    if ((size_t)(p - ctx->wf_arena) > total) return cudaErrorMemoryAllocation;
+    if (!ctx->wf_host_live) {
+        e = cudaHostAlloc((void **)&ctx->wf_host_live, sizeof(uint32_t), cudaHostAllocDefault);
+        if (e != cudaSuccess) return e;
+        e = cudaEventCreateWithFlags(&ctx->wf_event, cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    }
+    ctx->wf_blocks = wf_trace_blocks(ctx->device);
+    return cudaSuccess;
+}
+
 void free_scene(rt_ctx *ctx, bool keep_arena) {
     if (!keep_arena) {
+        free_wavefront(ctx);
         if (ctx->arena) cudaFree(ctx->arena);
         ctx->arena = nullptr;
         ctx->arena_cap = 0;
@@ -389,6 +437,8 @@ void rt_destroy(rt_ctx *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     free_scene(ctx, false);
     if (ctx->d_ctr) cudaFree(ctx->d_ctr);
+    if (ctx->wf_host_live) cudaFreeHost(ctx->wf_host_live);
+    if (ctx->wf_event) cudaEventDestroy(ctx->wf_event);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -524,7 +574,13 @@ int rt_render_accum(rt_ctx *ctx, const rt_render_params *p) {
     if ((uint64_t)p->sample_begin + p->sample_count > 0xFFFFFFFFull) return set_err(ctx, RT_ERR_INVALID_ARG, "sample range overflows u32");
     if (p->clear) CK(ctx, cudaMemsetAsync(ctx->d_accum, 0, ctx->n_px * 3 * sizeof(double), ctx->stream));
     if (p->sample_count == 0) return RT_OK;
-    if (p->sched == RT_SCHED_WAVEFRONT) return set_err(ctx, RT_ERR_INVALID_ARG, "wavefront scheduler not built into this library yet");
+    if (p->sched == RT_SCHED_WAVEFRONT && ctx->dsc.ray_depth > 0) {
+        if (p->mode != RT_MODE_FAST) return set_err(ctx, RT_ERR_INVALID_ARG, "the wavefront scheduler runs FAST mode only (EXACT is the megakernel parity anchor)");
+        CK(ctx, ensure_wavefront(ctx));
+        CK(ctx, launch_render_wavefront(ctx->stream, ctx->dsc, p->sample_begin, p->sample_count, p->seed, ctx->d_accum, ctx->d_ctr,
+                                        ctx->wf, ctx->wf_host_live, ctx->wf_event, ctx->wf_blocks, &ctx->launches));
+        return RT_OK;
+    }
     CK(ctx, launch_render_mega(ctx->stream, ctx->dsc, p->mode, p->sample_begin, p->sample_count, p->seed, ctx->d_accum, ctx->d_ctr));
     ++ctx->launches;
     return RT_OK;

@@ -379,8 +379,8 @@ RT_D void light_hits_exact(const DBvh bvh, const void *prims, const DTriS *tri_s
         }
     }
 }
-RT_D double light_pdf_exact(const DScene &sc, d3 pos, d3 dir, Cnt &c) {
-    const d3 o = add(pos, scale_l(kEps, dir));
+// o = pos + EPSILON * dir (ray_sampler.rs:133) is formed by the caller
+RT_D double light_pdf_exact(const DScene &sc, d3 o, d3 dir, Cnt &c) {
     double impact = 0.0;
     ++c.lray;
     light_hits_exact<1>(sc.lboxes, sc.lbox_prims, nullptr, o, dir, impact, c);

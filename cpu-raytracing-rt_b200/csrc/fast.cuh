@@ -189,30 +189,47 @@ RT_D void closest_fast(const FBvh f, const DTriI *tri_i, d3 o, d3 d, float tmax,
 }
 
 // ---- intersections::intersect in FAST mode ------------------------------------------------------
-RT_D SceneHit intersect_fast(const DScene &sc, d3 o, d3 d, Cnt &c) {
-    SceneHit h;
-    h.kind = -1; h.prim = 0; h.material = 0; h.t = 0.0; h.inside = false;
-    h.ng = h.ns = mk3(0.0, 0.0, 0.0);
-    bool has = false;
-    for (uint32_t i = 0; i < sc.n_planes; ++i) {          // the few analytic shapes stay on the exact path
+// Split in three so the wavefront scheduler can run the pieces in different kernels:
+//   shapes_closest  planes + box / ellipsoid hierarchies on the exact f64 path (a handful of
+//                   analytic primitives, src/intersections.rs:45-52);
+//   closest_fast    the triangle hierarchy, bounded by the shapes' best distance: a triangle only
+//                   replaces an earlier category when strictly closer (src/intersections.rs:79);
+//   finish_hit      the merge, the max_dist check (:56) and the rotated / renormalised normals.
+struct ShapeBest {
+    bool has;
+    double t;
+    int kind;
+    uint32_t prim;
+};
+RT_D ShapeBest shapes_closest(const DScene &sc, d3 o, d3 d, Cnt &c) {
+    ShapeBest sb;
+    sb.has = false; sb.t = 0.0; sb.kind = -1; sb.prim = 0;
+    for (uint32_t i = 0; i < sc.n_planes; ++i) {
         double t; d3 n; bool in;
         if (!shape_closest(load_shape(sc.planes + i), o, d, t, n, in)) continue;
-        if (!has || t < h.t) { has = true; h.t = t; h.kind = 0; h.prim = i; }
+        if (!sb.has || t < sb.t) { sb.has = true; sb.t = t; sb.kind = 0; sb.prim = i; }
     }
     if (sc.boxes.n_prims) {
         const Best b = closest_exact<1>(sc.boxes, sc.box_prims, o, d, c);
-        if (b.has && (!has || b.t < h.t)) { has = true; h.t = b.t; h.kind = 1; h.prim = b.prim; }
+        if (b.has && (!sb.has || b.t < sb.t)) { sb.has = true; sb.t = b.t; sb.kind = 1; sb.prim = b.prim; }
     }
     if (sc.ellipsoids.n_prims) {
         const Best e = closest_exact<2>(sc.ellipsoids, sc.ell_prims, o, d, c);
-        if (e.has && (!has || e.t < h.t)) { has = true; h.t = e.t; h.kind = 2; h.prim = e.prim; }
+        if (e.has && (!sb.has || e.t < sb.t)) { sb.has = true; sb.t = e.t; sb.kind = 2; sb.prim = e.prim; }
     }
-    FBest fb;
-    fb.has = false; fb.t = 0.0; fb.u = 0.0; fb.v = 0.0; fb.prim = 0;
-    // a triangle only replaces an earlier category when strictly closer (intersections.rs:79),
-    // so the shapes' best distance bounds the triangle search
-    const float tmax0 = (has && h.t == h.t) ? up_f32(h.t) : __int_as_float(0x7F800000);
-    if (!(has && h.t != h.t)) closest_fast(sc.ftris, sc.tri_i, o, d, tmax0, fb);
+    return sb;
+}
+// fp32 bound for the triangle search; skip = the shapes' best is NaN and can never be replaced
+RT_D float shapes_tmax(const ShapeBest &sb, bool &skip) {
+    skip = sb.has && sb.t != sb.t;
+    return (sb.has && !skip) ? up_f32(sb.t) : __int_as_float(0x7F800000);
+}
+RT_D SceneHit finish_hit(const DScene &sc, d3 o, d3 d, const ShapeBest &sb, const FBest &fb) {
+    SceneHit h;
+    h.kind = sb.kind; h.prim = sb.prim; h.material = 0; h.t = sb.t; h.inside = false;
+    h.ng = h.ns = mk3(0.0, 0.0, 0.0);
+    bool has = sb.has;
+    if (!has) h.kind = -1;
     if (fb.has && (!has || fb.t < h.t)) { has = true; h.t = fb.t; h.kind = 3; h.prim = fb.prim; }
     if (!has) return h;
     if (!(h.t * len3(d) <= dinf())) { h.kind = -1; return h; }
@@ -228,6 +245,15 @@ RT_D SceneHit intersect_fast(const DScene &sc, d3 o, d3 d, Cnt &c) {
         finish_shape_hit(sp, o, d, h);
     }
     return h;
+}
+RT_D SceneHit intersect_fast(const DScene &sc, d3 o, d3 d, Cnt &c) {
+    const ShapeBest sb = shapes_closest(sc, o, d, c);
+    FBest fb;
+    fb.has = false; fb.t = 0.0; fb.u = 0.0; fb.v = 0.0; fb.prim = 0;
+    bool skip;
+    const float tmax0 = shapes_tmax(sb, skip);
+    if (!skip) closest_fast(sc.ftris, sc.tri_i, o, d, tmax0, fb);
+    return finish_hit(sc, o, d, sb, fb);
 }
 
 // ---- Light::pdf in FAST mode ---------------------------------------------------------------------
@@ -277,19 +303,23 @@ RT_D void light_hits_fast(const FBvh f, const DTriI *tri_i, const DTriS *tri_s, 
     }
     for (int j = 0; j < nc; ++j) light_confirm(tri_i, tri_s, o, d, cand[j], impact);   // same order as visited
 }
-RT_D double light_pdf_fast(const DScene &sc, d3 pos, d3 dir, Cnt &c) {
-    const d3 o = add(pos, scale_l(kEps, dir));
+// analytic lights (boxes, then ellipsoids: intersect_lights order, intersections.rs:88-89)
+RT_D double light_shapes_impact(const DScene &sc, d3 o, d3 dir, Cnt &c) {
     double impact = 0.0;
-    ++c.lray;
     light_hits_exact<1>(sc.lboxes, sc.lbox_prims, nullptr, o, dir, impact, c);
     light_hits_exact<2>(sc.lellipsoids, sc.lell_prims, nullptr, o, dir, impact, c);
+    return impact;
+}
+RT_D double light_pdf_fast(const DScene &sc, d3 o, d3 dir, Cnt &c) {
+    ++c.lray;
+    double impact = light_shapes_impact(sc, o, dir, c);
     light_hits_fast(sc.fltris, sc.ltri_i, sc.ltri_s, o, dir, impact);
     return impact / (double)sc.n_lights;
 }
 
 struct FastPolicy {
     RT_D static SceneHit intersect(const DScene &sc, d3 o, d3 d, Cnt &c) { return intersect_fast(sc, o, d, c); }
-    RT_D static double light_pdf(const DScene &sc, d3 pos, d3 dir, Cnt &c) { return light_pdf_fast(sc, pos, dir, c); }
+    RT_D static double light_pdf_ray(const DScene &sc, d3 o, d3 dir, Cnt &c) { return light_pdf_fast(sc, o, dir, c); }
 };
 
 }  // namespace rt

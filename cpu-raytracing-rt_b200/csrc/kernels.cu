@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(128) k_light_pdf(DScene sc, unsigned long long
     if (i < n) {
         const d3 p = mk3(pos[i * 3], pos[i * 3 + 1], pos[i * 3 + 2]);
         const d3 d = mk3(dir[i * 3], dir[i * 3 + 1], dir[i * 3 + 2]);
-        pdf[i] = sc.n_lights ? POLICY::light_pdf(sc, p, d, c) : 0.0;
+        pdf[i] = sc.n_lights ? POLICY::light_pdf_ray(sc, add(p, scale_l(kEps, d)), d, c) : 0.0;       // ray_sampler.rs:133
     }
     flush_counters(c, ctr);
 }

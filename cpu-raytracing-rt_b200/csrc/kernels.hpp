@@ -16,6 +16,25 @@ cudaError_t launch_light_pdf(cudaStream_t st, const DScene &sc, int mode, uint64
                              double *pdf, DCounters *ctr);
 cudaError_t launch_render_mega(cudaStream_t st, const DScene &sc, int mode, uint32_t sample_begin, uint32_t sample_count,
                                uint64_t seed, double *accum, DCounters *ctr);
+// ---- wavefront scheduler (wavefront.cu) ----------------------------------------------------------
+constexpr int kWfCand = 4;              // deferred candidates kept per ray and per search
+struct WfBuf {                          // per-pixel path slots, structure of arrays; n = width * height
+    uint32_t n;
+    double *ro, *rd, *T, *L, *pv;       // 3 * n: ray origin / direction, throughput, radiance, pending weight
+    double *pcos, *pimp, *sh_t;         // n: Cosine::pdf, light impact of analytic lights, shapes' best t
+    uint32_t *sh_id, *rng_block, *rng_s0, *rng_s1, *sample, *flags, *ncand;    // n
+    uint32_t *cand, *lcand;             // kWfCand * n: triangle candidates (scene / lights)
+    float *cand_t;                      // kWfCand * n: lower bound of each scene candidate's distance
+    uint32_t *live[2];                  // n each: compacted indices of slots with work
+    uint32_t *n_live;                   // [2]
+    uint32_t *cursor;                   // trace kernel's fetch position in the live list
+};
+size_t wf_bytes_per_slot();
+int wf_trace_blocks(int device);
+cudaError_t launch_render_wavefront(cudaStream_t st, const DScene &sc, uint32_t sample_begin, uint32_t sample_count,
+                                    uint64_t seed, double *accum, DCounters *ctr, const WfBuf &b, volatile uint32_t *host_live,
+                                    cudaEvent_t ev, int trace_blocks, uint64_t *launches);
+
 cudaError_t launch_postprocess(cudaStream_t st, uint64_t n, const double *accum, uint32_t samples, double *rgb);
 cudaError_t launch_rng_probe(cudaStream_t st, uint64_t seed, uint32_t pixel, uint32_t sample, uint64_t n,
                              unsigned long long *u64_out, double *probe8);

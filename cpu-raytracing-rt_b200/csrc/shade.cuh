@@ -144,12 +144,19 @@ RT_D double powi(double a, int b) {                         // f64::powi (compil
 
 // One bounce of raytrace_impl (reference src/raytrace.rs:12-60) in throughput form: the
 // reference returns e0 + w0*(e1 + w1*(...)) up its recursion; the loop carries T = w0*w1*... and
-// adds T*e_k.  Returns false when the path ends.  POLICY supplies intersect / light_pdf.
-template <class POLICY>
-RT_D bool bounce(const DScene &sc, d3 &o, d3 &d, d3 &T, d3 &L, Rng &rng, Cnt &c) {
-    ++c.seg;
-    const SceneHit h = POLICY::intersect(sc, o, d, c);
-    if (h.kind < 0) { L = add(L, mul3(T, sc.bg)); return false; }          // :14
+// adds T*e_k.  The bounce is split so that both schedulers run the SAME arithmetic:
+//   shade_hit      emission + material + sampling of the next ray; for a diffuse hit in a scene
+//                  with lights the weight needs Light::pdf of the NEW ray, which is left pending;
+//   apply_pending  Mix::pdf (:95-97) and the throughput update (:33) once that pdf is known.
+// The ray that Light::pdf shoots (pos + EPSILON*dir, dir — ray_sampler.rs:133) is exactly the
+// next path segment (raytrace.rs:32), so one traversal serves both.
+struct Pending {
+    d3 v;               // dot * color / PI  (numerator of raytrace.rs:33)
+    double cos_pdf;     // Cosine::pdf
+};
+enum { kPathEnd = 0, kPathContinue = 1, kPathPendingPdf = 2 };
+RT_D int shade_hit(const DScene &sc, const SceneHit &h, d3 &o, d3 &d, d3 &T, d3 &L, Rng &rng, Pending &pd) {
+    if (h.kind < 0) { L = add(L, mul3(T, sc.bg)); return kPathEnd; }         // :14
     const double2 *mp = reinterpret_cast<const double2 *>(sc.materials + h.material);
     const double2 m0 = __ldg(mp), m1 = __ldg(mp + 1), m2 = __ldg(mp + 2);
     const d3 color = mk3(m0.x, m0.y, m1.x), emission = mk3(m1.y, m2.x, m2.y);
@@ -163,14 +170,15 @@ RT_D bool bounce(const DScene &sc, d3 &o, d3 &d, d3 &T, d3 &L, Rng &rng, Cnt &c)
         if (mix && !rng.gen_bool(0.5)) dir = light_sample(sc, pos, rng);    // Mix::sample :87-93
         else dir = cosine_sample(h.ns, rng);
         const double cosv = dot3(dir, h.ns);
-        if (cosv <= 0.0) return false;                                      // :23-25
-        double pdf = cosine_pdf(h.ns, dir);
-        if (mix) pdf = (pdf + POLICY::light_pdf(sc, pos, dir, c)) / 2.0;    // Mix::pdf :95-97
-        if (pdf == 0.0) return false;                                       // :28-30
-        T = mul3(T, divs(divs(scale_l(cosv, color), kPi), pdf));            // :33
-        o = add(pos, scale_l(kEps, dir));                                   // :32
+        if (cosv <= 0.0) return kPathEnd;                                   // :23-25
+        pd.cos_pdf = cosine_pdf(h.ns, dir);
+        pd.v = divs(scale_l(cosv, color), kPi);
+        o = add(pos, scale_l(kEps, dir));                                   // :32 and ray_sampler.rs:133
         d = dir;
-        return true;
+        if (mix) return kPathPendingPdf;
+        if (pd.cos_pdf == 0.0) return kPathEnd;                             // :28-30
+        T = mul3(T, divs(pd.v, pd.cos_pdf));                                // :33
+        return kPathContinue;
     }
     const d3 refl = sub(d, scale(scale_l(2.0, h.ns), dot3(h.ns, d)));       // reflected_ray :67-73
     if (kind == 2) {                                                        // Dielectric :36-54
@@ -179,34 +187,48 @@ RT_D bool bounce(const DScene &sc, d3 &o, d3 &d, d3 &T, d3 &L, Rng &rng, Cnt &c)
         const double eta = n1 / n2;
         const double cos1 = -dot3(h.ns, d);                                 // refracted_ray :75-88
         const double sin2 = eta * sqrt(1.0 - cos1 * cos1);
-        bool reflect = true;
         if (!(sin2 > 1.0)) {
             const double r0 = powi((n1 - n2) / (n1 + n2), 2);               // reflection_power :62-65
             const double rp = r0 + (1.0 - r0) * powi(1.0 + dot3(d, h.ns), 5);
             const double p = rp < 0.0 ? 0.0 : (rp > 1.0 ? 1.0 : rp);
-            reflect = rng.gen_bool(p);                                      // :46
-            if (!reflect) {
+            if (!rng.gen_bool(p)) {                                         // :46
                 const double cos2 = sqrt(1.0 - sin2 * sin2);
                 const d3 dir = add(scale_l(eta, d), scale_l(eta * cos1 - cos2, h.ns));
                 if (!h.inside) T = mul3(T, color);                          // :50
                 o = add(pos, scale_l(kEps, dir));
                 d = dir;
-                return true;
+                return kPathContinue;
             }
         }
         o = add(pos, scale_l(kEps, refl));
         d = refl;
-        return true;
+        return kPathContinue;
     }
     T = mul3(T, color);                                                     // Metallic :56-58
     o = add(pos, scale_l(kEps, refl));
     d = refl;
+    return kPathContinue;
+}
+// light_pdf = Light::pdf of the ray (o, d) the path continues with.  false: the path ends (:28-30).
+RT_D bool apply_pending(const Pending &pd, double light_pdf, d3 &T) {
+    const double pdf = (pd.cos_pdf + light_pdf) / 2.0;                      // Mix::pdf :95-97
+    if (pdf == 0.0) return false;
+    T = mul3(T, divs(pd.v, pdf));                                           // :33
     return true;
+}
+template <class POLICY>
+RT_D bool bounce(const DScene &sc, d3 &o, d3 &d, d3 &T, d3 &L, Rng &rng, Cnt &c) {
+    ++c.seg;
+    const SceneHit h = POLICY::intersect(sc, o, d, c);
+    Pending pd;
+    const int r = shade_hit(sc, h, o, d, T, L, rng, pd);
+    if (r != kPathPendingPdf) return r == kPathContinue;
+    return apply_pending(pd, POLICY::light_pdf_ray(sc, o, d, c), T);
 }
 
 struct ExactPolicy {
     RT_D static SceneHit intersect(const DScene &sc, d3 o, d3 d, Cnt &c) { return intersect_exact(sc, o, d, c); }
-    RT_D static double light_pdf(const DScene &sc, d3 pos, d3 dir, Cnt &c) { return light_pdf_exact(sc, pos, dir, c); }
+    RT_D static double light_pdf_ray(const DScene &sc, d3 o, d3 dir, Cnt &c) { return light_pdf_exact(sc, o, dir, c); }
 };
 
 }  // namespace rt

@@ -1,0 +1,367 @@
+// wavefront.cu — the wavefront scheduler of generate_image (reference src/main.rs:94-103).
+//
+// Every pixel owns one SLOT holding the path currently in flight for it (ray, throughput, RNG
+// stream position, pending diffuse weight).  An iteration is two kernels over the LIVE slots:
+//
+//   k_wf_shade  one thread per live slot, f64, warp-coherent code.  Confirms the candidates the
+//               previous trace found with the reference's exact triangle arithmetic, finishes
+//               the pending Light::pdf weight, runs one bounce of raytrace_impl
+//               (src/raytrace.rs:12-60), and when a path ends adds it to the pixel and starts the
+//               pixel's next sample at once (samples of a pixel complete in index order, so the
+//               sum is deterministic).  Slots that still have work are appended to the next
+//               live list with a warp ballot + prefix-sum (stream compaction of live paths).
+//   k_wf_trace  persistent warps, fp32 only.  Each lane walks the culling hierarchy for one ray
+//               (closest-hit search and, for a pending diffuse bounce, the all-hits search of
+//               the light hierarchy along the same ray) and writes candidate lists.  A lane that
+//               finishes its ray does not wait for the slowest ray of its warp: when too few
+//               lanes remain busy the warp refills the idle ones from the live list.
+//
+// In a megakernel every lane waits for the slowest of its 32 rays at every bounce (ncu: 7 of 32
+// lanes active in the traversal loop); here the traversal loop stays full and the ~400-instruction
+// f64 confirmation runs with all lanes of a warp at once.  Arithmetic per path is identical to
+// the megakernel in FAST mode, so both schedulers produce bitwise the same accumulation buffer.
+#include <cuda_runtime.h>
+
+#include "../../include/rt_b200.h"
+#include "fast.cuh"
+#include "kernels.hpp"
+
+namespace rt {
+
+constexpr unsigned kFull = 0xFFFFFFFFu;
+constexpr uint32_t kFlagAlive = 1u, kFlagRngHave = 2u, kFlagPendLight = 4u;
+constexpr uint32_t kOverflowClosest = 0x10000u, kOverflowLight = 0x20000u;
+constexpr uint32_t kNoShape = 0xFFFFFFFFu;
+
+RT_D d3 ld_soa(const double *base, uint32_t n, uint32_t i) { return mk3(base[i], base[n + i], base[2u * n + i]); }
+RT_D void st_soa(double *base, uint32_t n, uint32_t i, d3 v) { base[i] = v.x; base[n + i] = v.y; base[2u * n + i] = v.z; }
+
+__device__ __forceinline__ void flush_counters_wf(const Cnt &c, DCounters *out) {
+    unsigned long long v[3] = {c.seg, c.lray, c.paths};
+    unsigned long long *dst[3] = {&out->segments, &out->light_pdf_rays, &out->paths};
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        unsigned long long s = v[k];
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(kFull, s, off);
+        if (lane == 0 && s) atomicAdd(dst[k], s);
+    }
+}
+
+__global__ void k_wf_init(WfBuf b) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < b.n) {
+        b.flags[i] = 0;
+        b.sample[i] = 0;
+        b.live[0][i] = i;
+    }
+    if (i == 0) { b.n_live[0] = b.n; b.n_live[1] = 0; *b.cursor = 0; }
+}
+
+// ---- shade -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_wf_shade(DScene sc, WfBuf b, int cur_list, uint32_t sample_begin, uint32_t sample_count,
+                                                  unsigned long long seed, double *__restrict__ accum, DCounters *ctr) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_live = b.n_live[cur_list], N = b.n;
+    const uint32_t *__restrict__ live = b.live[cur_list];
+    uint32_t *__restrict__ next_live = b.live[cur_list ^ 1];
+    Cnt c;
+    bool keep = false;
+    uint32_t slot = 0;
+    if (i < n_live) {
+        slot = live[i];
+        uint32_t flags = b.flags[slot], s = b.sample[slot];
+        Rng rng;
+        rng.init(seed, slot, sample_begin + s);
+        d3 o = mk3(0.0, 0.0, 0.0), d = o, T = o, L = o;
+        uint32_t left = (flags >> 8) & 0xFFu;
+        bool alive = (flags & kFlagAlive) != 0, ended = false, pend_light = false;
+        Pending pd;
+        pd.v = o; pd.cos_pdf = 0.0;
+        if (alive) {
+            rng.block = b.rng_block[slot]; rng.s0 = b.rng_s0[slot]; rng.s1 = b.rng_s1[slot];
+            rng.have = (flags & kFlagRngHave) != 0;
+            o = ld_soa(b.ro, N, slot); d = ld_soa(b.rd, N, slot);
+            T = ld_soa(b.T, N, slot); L = ld_soa(b.L, N, slot);
+            const uint32_t nc_all = b.ncand[slot];
+            if (flags & kFlagPendLight) {               // finish the previous diffuse bounce: Light::pdf of THIS ray
+                double impact = b.pimp[slot];
+                if (nc_all & kOverflowLight) {
+                    light_hits_fast(sc.fltris, sc.ltri_i, sc.ltri_s, o, d, impact);
+                } else {
+                    const uint32_t nl = (nc_all >> 8) & 0xFFu;
+                    for (uint32_t k = 0; k < nl; ++k) light_confirm(sc.ltri_i, sc.ltri_s, o, d, b.lcand[k * N + slot], impact);
+                }
+                pd.v = ld_soa(b.pv, N, slot);
+                pd.cos_pdf = b.pcos[slot];
+                if (!apply_pending(pd, impact / (double)sc.n_lights, T)) ended = true;
+            }
+            if (!ended) {
+                ++c.seg;
+                ShapeBest sb;
+                const uint32_t sid = b.sh_id[slot];
+                sb.has = sid != kNoShape; sb.kind = sb.has ? (int)(sid >> 28) : -1; sb.prim = sid & 0x0FFFFFFFu; sb.t = b.sh_t[slot];
+                FBest fb;
+                fb.has = false; fb.t = 0.0; fb.u = 0.0; fb.v = 0.0; fb.prim = 0;
+                bool skip;
+                float tmax = shapes_tmax(sb, skip);
+                if (!skip) {
+                    if (nc_all & kOverflowClosest) {
+                        closest_fast(sc.ftris, sc.tri_i, o, d, tmax, fb);
+                    } else {
+                        const uint32_t nc = nc_all & 0xFFu;
+                        for (uint32_t k = 0; k < nc; ++k)
+                            if (b.cand_t[k * N + slot] <= tmax) confirm(sc.tri_i, o, d, b.cand[k * N + slot], fb, tmax);
+                    }
+                }
+                const SceneHit h = finish_hit(sc, o, d, sb, fb);
+                const int r = shade_hit(sc, h, o, d, T, L, rng, pd);
+                --left;
+                if (r == kPathEnd) {
+                    ended = true;
+                } else if (left == 0) {
+                    // the reference evaluates Light::pdf before recursing into a depth-0 call
+                    // that returns at once (raytrace.rs:27-32, :13): count it, nothing to trace
+                    if (r == kPathPendingPdf) ++c.lray;
+                    ended = true;
+                } else {
+                    pend_light = r == kPathPendingPdf;
+                }
+            }
+        }
+        if (!alive || ended) {
+            if (alive) {                                // main.rs:102
+                const size_t p = (size_t)slot * 3;
+                accum[p] += L.x; accum[p + 1] += L.y; accum[p + 2] += L.z;
+                ++s;
+            }
+            alive = s < sample_count;
+            if (alive) {
+                rng.init(seed, slot, sample_begin + s);
+                const double jx = rng.range(0.0, 1.0), jy = rng.range(0.0, 1.0);       // camera.rs:49-50
+                camera_ray(sc.cam, slot % sc.width, slot / sc.width, jx, jy, o, d);
+                ++c.paths;
+                T = mk3(1.0, 1.0, 1.0);
+                L = mk3(0.0, 0.0, 0.0);
+                left = sc.ray_depth;
+                pend_light = false;
+            }
+        }
+        if (alive) {                                    // hand the ray to the trace kernel
+            const ShapeBest sb = shapes_closest(sc, o, d, c);
+            b.sh_id[slot] = sb.has ? (((uint32_t)sb.kind << 28) | sb.prim) : kNoShape;
+            b.sh_t[slot] = sb.t;
+            if (pend_light) {
+                ++c.lray;
+                b.pimp[slot] = light_shapes_impact(sc, o, d, c);
+                st_soa(b.pv, N, slot, pd.v);
+                b.pcos[slot] = pd.cos_pdf;
+            }
+            st_soa(b.ro, N, slot, o); st_soa(b.rd, N, slot, d);
+            st_soa(b.T, N, slot, T); st_soa(b.L, N, slot, L);
+            b.rng_block[slot] = rng.block; b.rng_s0[slot] = rng.s0; b.rng_s1[slot] = rng.s1;
+            b.sample[slot] = s;
+            b.flags[slot] = kFlagAlive | (rng.have ? kFlagRngHave : 0u) | (pend_light ? kFlagPendLight : 0u) | (left << 8);
+            keep = true;
+        } else {
+            b.flags[slot] = 0;
+            b.sample[slot] = s;
+        }
+    }
+    // stream compaction of the live slots: ballot + prefix sum inside the warp, one atomic per warp
+    __syncwarp();
+    const unsigned m = __ballot_sync(kFull, keep);
+    if (m) {
+        const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(&b.n_live[cur_list ^ 1], (uint32_t)__popc(m));
+        base = __shfl_sync(kFull, base, leader);
+        if (keep) next_live[base + __popc(m & ((1u << lane) - 1u))] = slot;
+    }
+    flush_counters_wf(c, ctr);
+}
+
+// ---- trace -------------------------------------------------------------------------------------
+constexpr int kMinBusyLanes = 20;       // refill when fewer lanes than this are still traversing
+
+__global__ void __launch_bounds__(128, 4) k_wf_trace(DScene sc, WfBuf b, int list) {
+    const uint32_t n = b.n_live[list], N = b.n;
+    const uint32_t *__restrict__ live = b.live[list];
+    const int lane = threadIdx.x & 31;
+    const float inf = __int_as_float(0x7F800000);
+    bool has = false, drained = false;      // drained: the live list has no more rays for this warp
+    uint32_t slot = 0, nc = 0, nl = 0, over = 0;
+    FRay r = {};
+    d3 o = mk3(0.0, 0.0, 0.0);
+    float dl1g = 0.0f, tmax = inf;
+    int32_t cur = kFastEmpty;
+    int sp = 0, phase = 0;                  // phase 0: closest hit; 1: light all-hits; 2: finished
+    bool want_light = false;
+    int32_t stk_n[kFastStack];
+    float stk_t[kFastStack];
+    for (;;) {
+        // ---- refill idle lanes from the live list (one atomic per warp)
+        const unsigned need = drained ? 0u : __ballot_sync(kFull, !has);
+        if (need) {
+            const int leader = __ffs(need) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(b.cursor, (uint32_t)__popc(need));
+            base = __shfl_sync(kFull, base, leader);
+            if (!has) {
+                const uint32_t idx = base + __popc(need & ((1u << lane) - 1u));
+                if (idx < n) {
+                    slot = live[idx];
+                    o = ld_soa(b.ro, N, slot);
+                    const d3 d = ld_soa(b.rd, N, slot);
+                    r = make_fray(o, d);
+                    dl1g = kGamma * (fabsf(r.dx) + fabsf(r.dy) + fabsf(r.dz));
+                    const uint32_t sid = b.sh_id[slot];
+                    const double st = b.sh_t[slot];
+                    const bool skip = sid != kNoShape && st != st;
+                    tmax = (sid != kNoShape && !skip) ? up_f32(st) : inf;
+                    want_light = (b.flags[slot] & kFlagPendLight) != 0;
+                    nc = 0; nl = 0; over = 0; sp = 0;
+                    cur = skip ? kFastEmpty : sc.ftris.root;
+                    phase = 0;
+                    has = true;
+                }
+            }
+            if (__any_sync(kFull, !has)) drained = true;       // someone got idx >= n: the list is empty
+        }
+        if (!__any_sync(kFull, has)) break;
+        // ---- traverse until this lane's ray is finished or the warp runs too empty
+        if (has) {
+            bool yield = false;
+            if (phase == 0) {
+                while (cur != kFastEmpty && !yield) {
+                    while (cur >= 0) {
+                        const float4 *np = reinterpret_cast<const float4 *>(sc.ftris.nodes + cur);
+                        const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
+                        const int4 lk = __ldg(reinterpret_cast<const int4 *>(np) + 3);
+                        float t0, t1;
+                        const bool h0 = slab(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tmax, t0);
+                        const bool h1 = slab(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, tmax, t1);
+                        if (h0 && h1) {
+                            const bool first0 = t0 <= t1;
+                            stk_n[sp] = first0 ? lk.y : lk.x;
+                            stk_t[sp] = first0 ? t1 : t0;
+                            ++sp;
+                            cur = first0 ? lk.x : lk.y;
+                        } else if (h0) {
+                            cur = lk.x;
+                        } else if (h1) {
+                            cur = lk.y;
+                        } else {
+                            cur = kFastEmpty;
+                            while (sp > 0) {
+                                --sp;
+                                if (stk_t[sp] <= tmax) { cur = stk_n[sp]; break; }
+                            }
+                        }
+                        if (!drained && __popc(__activemask()) < kMinBusyLanes) { yield = true; break; }
+                    }
+                    if (yield || cur == kFastEmpty) break;
+                    if (cur < 0) {
+                        const uint32_t code = (uint32_t)~cur, first = code >> 3, count = (code & 7u) + 1u;
+                        for (uint32_t i = first; i < first + count; ++i) {
+                            float tlo, thi;
+                            const int cls = tri_classify(sc.ftris.tris + i, r, o, dl1g, tmax, tlo, thi);
+                            if (cls == 0) continue;
+                            if (cls == 2) tmax = fminf(tmax, thi);
+                            if (nc < (uint32_t)kWfCand) {
+                                b.cand[nc * N + slot] = i;
+                                b.cand_t[nc * N + slot] = tlo;
+                                ++nc;
+                            } else {
+                                over |= kOverflowClosest;       // rare: the shade kernel redoes this search
+                            }
+                        }
+                        cur = kFastEmpty;
+                        while (sp > 0) {
+                            --sp;
+                            if (stk_t[sp] <= tmax) { cur = stk_n[sp]; break; }
+                        }
+                    }
+                }
+                if (!yield && cur == kFastEmpty) {              // closest search done
+                    if (want_light && sc.fltris.root != kFastEmpty) {
+                        phase = 1; sp = 0; stk_n[sp++] = sc.fltris.root;
+                    } else {
+                        phase = 2;
+                    }
+                }
+            }
+            if (phase == 1 && !yield) {
+                // all hits along the same ray over the light hierarchy, children left then right:
+                // the reference's visit order (bvh.rs:188-210), which fixes the order of the pdf sum
+                while (sp > 0) {
+                    const int32_t node = stk_n[--sp];
+                    if (node >= 0) {
+                        const float4 *np = reinterpret_cast<const float4 *>(sc.fltris.nodes + node);
+                        const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
+                        const int4 lk = __ldg(reinterpret_cast<const int4 *>(np) + 3);
+                        float t0, t1;
+                        const bool h0 = slab(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, inf, t0);
+                        const bool h1 = slab(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, inf, t1);
+                        if (h1) stk_n[sp++] = lk.y;
+                        if (h0) stk_n[sp++] = lk.x;
+                    } else {
+                        const uint32_t code = (uint32_t)~node, first = code >> 3, count = (code & 7u) + 1u;
+                        for (uint32_t i = first; i < first + count; ++i) {
+                            float tlo, thi;
+                            if (tri_classify(sc.fltris.tris + i, r, o, dl1g, inf, tlo, thi) == 0) continue;
+                            if (nl < (uint32_t)kWfCand) { b.lcand[nl * N + slot] = i; ++nl; }
+                            else over |= kOverflowLight;
+                        }
+                    }
+                }
+                phase = 2;
+            }
+            if (phase == 2) {
+                b.ncand[slot] = nc | (nl << 8) | over;
+                has = false;
+            }
+        }
+    }
+}
+
+// ---- host loop -----------------------------------------------------------------------------------
+size_t wf_bytes_per_slot() { return 15 * 8 + 3 * 8 + 7 * 4 + kWfCand * 12 + 2 * 4; }
+int wf_trace_blocks(int device) {
+    int sms = 148, per_sm = 4;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wf_trace, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+    return sms * per_sm;
+}
+cudaError_t launch_render_wavefront(cudaStream_t st, const DScene &sc, uint32_t sample_begin, uint32_t sample_count,
+                                    uint64_t seed, double *accum, DCounters *ctr, const WfBuf &b, volatile uint32_t *host_live,
+                                    cudaEvent_t ev, int trace_blocks, uint64_t *launches) {
+    const unsigned blocks = (b.n + 127) / 128;
+    k_wf_init<<<blocks, 128, 0, st>>>(b);
+    ++*launches;
+    const uint64_t max_iters = (uint64_t)sample_count * (sc.ray_depth ? sc.ray_depth : 1) + 2;
+    int cur = 0;
+    bool poll_pending = false;
+    for (uint64_t it = 0; it < max_iters; ++it) {
+        // next list starts empty, trace cursor at 0
+        cudaMemsetAsync(&b.n_live[cur ^ 1], 0, sizeof(uint32_t), st);
+        cudaMemsetAsync(b.cursor, 0, sizeof(uint32_t), st);
+        k_wf_shade<<<blocks, 128, 0, st>>>(sc, b, cur, sample_begin, sample_count, seed, accum, ctr);
+        k_wf_trace<<<trace_blocks, 128, 0, st>>>(sc, b, cur ^ 1);
+        *launches += 2;
+        cur ^= 1;
+        if ((it & 7) == 7) {                    // poll the live count without stalling the stream
+            if (poll_pending) {
+                cudaError_t e = cudaEventSynchronize(ev);
+                if (e != cudaSuccess) return e;
+                if (*host_live == 0) break;
+            }
+            cudaMemcpyAsync((void *)host_live, &b.n_live[cur], sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+            cudaEventRecord(ev, st);
+            poll_pending = true;
+        }
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace rt

@@ -155,3 +155,34 @@ def test_fast_mode_equals_exact_mode(orc, ctx, tmp_path, kind):
     e = ctx.accum()
     ctx.render_accum(0, 2, 7, T.MODE_FAST, clear=True)
     assert ctx.accum().tobytes() == e.tobytes()
+
+
+@pytest.mark.parametrize("kind", ["cornell", "heightfield"])
+def test_wavefront_scheduler_equals_megakernel(orc, ctx, tmp_path, kind):
+    """The wavefront scheduler (persistent fp32 trace kernel with dynamic ray fetch + coherent f64
+    shade kernel + ballot/prefix-sum compaction of live slots) runs the same per-path arithmetic
+    as the megakernel: bitwise identical accumulation, identical event counters, and the same
+    additivity over sample ranges."""
+    prod, oracle = _load_pair(orc, tmp_path, kind, w=80, h=56, spp=5)
+    ctx.upload(prod)
+    ctx.reset_counters()
+    ctx.render_accum(0, 5, 0xABCDEF, T.MODE_FAST, T.SCHED_MEGAKERNEL, clear=True)
+    mega, mc = ctx.accum(), ctx.counters()
+    ctx.reset_counters()
+    ctx.render_accum(0, 5, 0xABCDEF, T.MODE_FAST, T.SCHED_WAVEFRONT, clear=True)
+    wave, wc = ctx.accum(), ctx.counters()
+    assert mega.sum() > 0
+    assert wave.tobytes() == mega.tobytes()
+    for k in ("segments", "light_pdf_rays", "paths"):
+        assert wc[k] == mc[k], (k, wc[k], mc[k])
+    ctx.render_accum(0, 2, 0xABCDEF, T.MODE_FAST, T.SCHED_WAVEFRONT, clear=True)
+    ctx.render_accum(2, 3, 0xABCDEF, T.MODE_FAST, T.SCHED_WAVEFRONT)
+    assert ctx.accum().tobytes() == mega.tobytes()
+    # and both agree with the oracle to rounding
+    want, oc = oracle.render_accum(0, 5, 0xABCDEF)
+    err = np.abs(wave - want) / np.maximum(np.abs(want), 1e-300)
+    err[wave == want] = 0.0
+    assert err.max() <= 1e-9
+    assert wc["segments"] == oc["segments"] and wc["light_pdf_rays"] == oc["light_pdf_rays"]
+    with pytest.raises(rtb200.RtError):
+        ctx.render_accum(0, 1, 1, T.MODE_EXACT, T.SCHED_WAVEFRONT, clear=True)

@@ -43,5 +43,14 @@ for mode, name in ((T.MODE_EXACT, "exact"), (T.MODE_FAST, "fast")):
         dt = time.time() - t
     c = ctx.counters()
     print(name, "render %d spp: %.1f ms, %.1f Mseg/s" % (spp, dt * 1e3, c["segments"] / dt / 1e6), c, flush=True)
+for rep in range(2):
+    ctx.reset_counters()
+    ctx.sync()
+    t = time.time()
+    ctx.render_accum(0, spp, 0xC0FFEE, T.MODE_FAST, T.SCHED_WAVEFRONT, clear=True)
+    ctx.sync()
+    dt = time.time() - t
+c = ctx.counters()
+print("wavefront render %d spp: %.1f ms, %.1f Mseg/s" % (spp, dt * 1e3, c["segments"] / dt / 1e6), c, flush=True)
 acc = ctx.accum()
 print("accum mean", acc.mean(axis=(0, 1)))
