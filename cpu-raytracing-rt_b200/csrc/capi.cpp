@@ -636,6 +636,18 @@ int rt_debug_rng(rt_ctx *ctx, uint64_t seed, uint32_t pixel, uint32_t sample, ui
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     return RT_OK;
 }
+int rt_debug_wavefront(rt_ctx *ctx, uint32_t *ncand_out, uint32_t *flags_out, double *rays_out) {
+    if (int r = need_scene(ctx)) return r;
+    if (!ctx->wf_arena) return set_err(ctx, RT_ERR_INVALID_ARG, "no wavefront render has run on this context");
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ncand_out) CK(ctx, cudaMemcpy(ncand_out, ctx->wf.ncand, (size_t)ctx->wf.n * 4, cudaMemcpyDeviceToHost));
+    if (flags_out) CK(ctx, cudaMemcpy(flags_out, ctx->wf.flags, (size_t)ctx->wf.n * 4, cudaMemcpyDeviceToHost));
+    if (rays_out) {
+        CK(ctx, cudaMemcpy(rays_out, ctx->wf.ro, (size_t)ctx->wf.n * 24, cudaMemcpyDeviceToHost));
+        CK(ctx, cudaMemcpy(rays_out + (size_t)ctx->wf.n * 3, ctx->wf.rd, (size_t)ctx->wf.n * 24, cudaMemcpyDeviceToHost));
+    }
+    return RT_OK;
+}
 int rt_sync(rt_ctx *ctx) {
     if (!ctx) return set_err(nullptr, RT_ERR_INVALID_ARG, "null context");
     CK(ctx, cudaSetDevice(ctx->device));

@@ -61,6 +61,16 @@ RT_D bool node_aabb_exact(const DNode *n, d3 o, d3 d, double &t) {
     return aabb_exact(lo, hi, o, d, t);
 }
 
+// IEEE x / y with the exact-zero dividend answered directly: (+-0) / y = +-0 for finite non-zero
+// y.  Axis-aligned triangles have exact zeros in their edge cross products, and the generic
+// division sends a zero dividend down its ~40-instruction special-case path.  Same bits.
+RT_D double divz1(double x, double y) {
+    if (x == 0.0 && y == y && y != 0.0)
+        return __longlong_as_double((__double_as_longlong(x) ^ __double_as_longlong(y)) & (long long)0x8000000000000000ull);
+    return x / y;
+}
+RT_D d3 divz(d3 a, double s) { return mk3(divz1(a.x, s), divz1(a.y, s), divz1(a.z, s)); }
+
 // ---- Triangle::intersection, reference src/primitives/triangle.rs:49-80 ----------------------
 RT_D bool tri_exact(const DTriI *tp, d3 o, d3 d, double &t, double &u, double &v) {
     const double2 *p = reinterpret_cast<const double2 *>(tp);
@@ -70,7 +80,7 @@ RT_D bool tri_exact(const DTriI *tp, d3 o, d3 d, double &t, double &u, double &v
     const double det = c0.x * (c1.y * c2.z - c2.y * c1.z) - c1.x * (c0.y * c2.z - c2.y * c0.z) +
                        c2.x * (c0.y * c1.z - c1.y * c0.z);
     if (fabs(det) < kTriDetMin) return false;
-    const d3 r0 = divs(cross3(c1, c2), det), r1 = divs(cross3(c2, c0), det), r2 = divs(cross3(c0, c1), det);
+    const d3 r0 = divz(cross3(c1, c2), det), r1 = divz(cross3(c2, c0), det), r2 = divz(cross3(c0, c1), det);
     const d3 w = sub(o, a);
     u = dot3(r0, w);
     v = dot3(r1, w);

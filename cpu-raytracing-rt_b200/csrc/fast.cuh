@@ -22,7 +22,11 @@ namespace rt {
 
 constexpr int kFastStack = 64;              // checked against FBvh::depth at upload time
 constexpr float kU = 5.9604645e-8f;         // 2^-24, fp32 unit roundoff
-constexpr float kGamma = 2.0e-6f;           // > 32 u: bound on the relative error of an fp32 triple product
+// Bound on the rounding error of an fp32 triple product w . (d x e) evaluated with FMAs from
+// inputs that were each rounded once to fp32: every product term carries at most 4 roundings of
+// relative size u on top of the 4u of the cross-product component it multiplies, so
+// |computed - exact| <= 8u * sum_k |w_k| (|d_i e_j| + |d_j e_i|) <= 8u * |w|_1 |d|_1 |e|_1.
+constexpr float kGamma = 5.4e-7f;           // 9u > 8u (1 + O(u))
 
 struct FRay {                               // per-ray culling state (12 registers)
     float idx, idy, idz;                    // 1 / d, |d| clamped away from 0
@@ -44,13 +48,17 @@ RT_D FRay make_fray(d3 o, d3 d) {
     return r;
 }
 // Conservative slab test of one fp32 box against [0, tmax]: true => the f64 box may be hit.
+// computed slab value = true * (1 + eta) + delta with |eta| <= 3u, |delta| <= pad, so
+// (near - pad) * (1 - 4u) is a TRUE lower bound of the entry distance and (far + pad) * (1 + 4u)
+// a true upper bound of the exit distance.  tn is that lower bound: it orders the children,
+// decides whether a deferred child can still matter, and anchors the ray-relative triangle test.
 RT_D bool slab(const FRay &r, float lx, float ly, float lz, float hx, float hy, float hz, float tmax, float &tn) {
     const float ax = fmaf(lx, r.idx, r.nx), bx = fmaf(hx, r.idx, r.nx);
     const float ay = fmaf(ly, r.idy, r.ny), by = fmaf(hy, r.idy, r.ny);
     const float az = fmaf(lz, r.idz, r.nz), bz = fmaf(hz, r.idz, r.nz);
-    tn = fmaxf(fmaxf(fminf(ax, bx) - r.px, fminf(ay, by) - r.py), fmaxf(fminf(az, bz) - r.pz, 0.0f));
+    tn = fmaxf(fmaxf(fminf(ax, bx) - r.px, fminf(ay, by) - r.py), fmaxf(fminf(az, bz) - r.pz, 0.0f)) * 0.9999995f;
     const float tf = fminf(fminf(fmaxf(ax, bx) + r.px, fmaxf(ay, by) + r.py), fminf(fmaxf(az, bz) + r.pz, tmax));
-    return tn <= tf * 1.0000006f;           // (1 + 4u) / (1 - 4u) < 1 + 9u
+    return tn <= tf * 1.0000005f;
 }
 
 struct FTriRec {
@@ -72,9 +80,30 @@ RT_D FTriRec load_ftri(const FTri *t) {
 //         1: undecided (within the error bound of an edge / of det = 0);
 //         2: the exact test certainly accepts.
 // For 1 and 2, [tlo, thi] bounds the distance the exact test would report.
-RT_D int tri_classify(const FTri *tp, const FRay &r, d3 o, float dl1g, float tmax, float &tlo, float &thi) {
+//
+// RAY-RELATIVE: the test is evaluated from the point o + tref*d (formed in f64), where tref is
+// the conservative entry distance of the leaf that holds the triangle.  U and V do not change
+// when the origin slides along the ray, but w = origin - a shrinks from the ray length to the
+// leaf size, and the rounding error of the fp32 triple products — proportional to |w| — shrinks
+// with it: distant grazing triangles no longer pile up as undecided candidates.
+// The reference's own determinant (triangle.rs:50, same operation order as tri_exact): used when
+// fp32 cannot tell the sign of det.  Rays lying IN the plane of many coplanar triangles (a path
+// on an emissive quad that light-samples another quad of the same plane) would otherwise turn
+// every one of them into an undecided candidate; the reference rejects them with |det| < 1e-11.
+RT_D bool det_below_threshold(const DTriI *tp, d3 d) {
+    const double2 *p = reinterpret_cast<const double2 *>(tp);
+    const double2 q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3);
+    const double q4 = __ldg(reinterpret_cast<const double *>(tp) + 8);
+    const d3 c0 = mk3(q1.y, q2.x, q2.y), c1 = mk3(q3.x, q3.y, q4), c2 = neg(d);
+    const double det = c0.x * (c1.y * c2.z - c2.y * c1.z) - c1.x * (c0.y * c2.z - c2.y * c0.z) +
+                       c2.x * (c0.y * c1.z - c1.y * c0.z);
+    return fabs(det) < kTriDetMin;
+}
+RT_D int tri_classify(const FTri *tp, const DTriI *xp, const FRay &r, d3 o, d3 d, float tref, float dl1g, float tmax, float &tlo, float &thi) {
     const FTriRec t = load_ftri(tp);
-    const float wx = __double2float_rn(o.x - t.a.x), wy = __double2float_rn(o.y - t.a.y), wz = __double2float_rn(o.z - t.a.z);
+    const double tr = (double)tref;
+    const float wx = __double2float_rn(fma(tr, d.x, o.x - t.a.x)), wy = __double2float_rn(fma(tr, d.y, o.y - t.a.y)),
+                wz = __double2float_rn(fma(tr, d.z, o.z - t.a.z));
     const float ppx = fmaf(r.dy, t.caz, -(r.dz * t.cay)), ppy = fmaf(r.dz, t.cax, -(r.dx * t.caz)), ppz = fmaf(r.dx, t.cay, -(r.dy * t.cax));
     const float det = fmaf(t.bax, ppx, fmaf(t.bay, ppy, t.baz * ppz));
     const float U = fmaf(wx, ppx, fmaf(wy, ppy, wz * ppz));
@@ -86,14 +115,19 @@ RT_D int tri_classify(const FTri *tp, const FRay &r, d3 o, float dl1g, float tma
     const float eu = dl1g * w1 * lc, ev = dl1g * w1 * lb, et = kGamma * w1 * lb * lc, ed = dl1g * lb * lc;
     const float ad = fabsf(det);
     const float inf = __int_as_float(0x7F800000);
-    if (!(ad > ed)) { tlo = 0.0f; thi = inf; return 1; }       // sign of det unknown (or NaN)
+    if (!(ad > ed)) {                                           // sign of det unknown (or NaN)
+        if (det_below_threshold(xp, d)) return 0;               // the exact test returns None at :51
+        tlo = 0.0f; thi = inf;
+        return 1;
+    }
     const float s = det < 0.0f ? -1.0f : 1.0f;
-    const float us = s * U, vs = s * V, ts = s * Tn;
+    const float us = s * U, vs = s * V, ts = s * Tn;            // ts / ad = distance measured from tref
     if (us < -eu || vs < -ev || us + vs > ad + eu + ev + ed || ts < -et) return 0;
-    if (ts > fmaf(tmax, ad + ed, et)) return 0;
-    tlo = fmaxf(0.0f, __fdividef(ts - et, ad + ed) * 0.9999995f);
+    const float trem = __fadd_ru(tmax, -tref);                  // remaining range, rounded up
+    if (ts > fmaf(trem, ad + ed, et)) return 0;
+    tlo = __fadd_rd(tref, fmaxf(0.0f, __fdividef(ts - et, ad + ed) * 0.9999995f));
     const float den = ad - ed;
-    thi = den > 1e-30f ? __fdividef(ts + et, den) * 1.0000005f : inf;
+    thi = den > 1e-30f ? __fadd_ru(tref, __fdividef(ts + et, den) * 1.0000005f) : inf;
     if (!(thi == thi)) thi = inf;
     // the exact test also rejects |det| < 1e-11 (triangle.rs:51): "certain" needs det well above it
     const bool certain = us >= eu && vs >= ev && us + vs <= ad - (eu + ev + ed) && ts >= et && den > 1e-9f;
@@ -121,8 +155,16 @@ RT_D void confirm(const DTriI *tri_i, d3 o, d3 d, uint32_t prim, FBest &best, fl
         tmax = fminf(tmax, up_f32(t));
     }
 }
+// A ray with a NaN component can never produce a hit: every comparison of the reference's box
+// and triangle tests is false, so it walks the WHOLE hierarchy, "hits" the first triangle with
+// t = NaN and then fails `t * |dir| <= max_dist` (intersections.rs:56) -> None.  Such rays do occur
+// (a dielectric hit at normal incidence can give 1 - cos^2 < 0 by one ulp, raytrace.rs:77; the
+// reference itself panics on the NaN probability it then passes to gen_bool).  FAST mode answers
+// "miss" directly instead of testing a million triangles.
+RT_D bool ray_is_nan(d3 o, d3 d) { return !(o.x == o.x && o.y == o.y && o.z == o.z && d.x == d.x && d.y == d.y && d.z == d.z); }
+
 RT_D void closest_fast(const FBvh f, const DTriI *tri_i, d3 o, d3 d, float tmax, FBest &best) {
-    if (f.root == kFastEmpty) return;
+    if (f.root == kFastEmpty || ray_is_nan(o, d)) return;
     const FRay r = make_fray(o, d);
     const float dl1g = kGamma * (fabsf(r.dx) + fabsf(r.dy) + fabsf(r.dz));
     int32_t stk_n[kFastStack];
@@ -131,6 +173,7 @@ RT_D void closest_fast(const FBvh f, const DTriI *tri_i, d3 o, d3 d, float tmax,
     float cand_t[kCand];
     int nc = 0, sp = 0;
     int32_t cur = f.root;
+    float cur_t = 0.0f;                     // conservative entry distance of `cur`
     // "while-while": all lanes first walk inner nodes until each holds a leaf (or is done), then
     // all lanes that hold a leaf run the triangle pre-tests together.  kFastEmpty doubles as the
     // "nothing left" marker (it is negative and never a valid leaf code of a non-empty tree).
@@ -148,15 +191,16 @@ RT_D void closest_fast(const FBvh f, const DTriI *tri_i, d3 o, d3 d, float tmax,
                 stk_t[sp] = first0 ? t1 : t0;
                 ++sp;
                 cur = first0 ? lk.x : lk.y;
+                cur_t = first0 ? t0 : t1;
             } else if (h0) {
-                cur = lk.x;
+                cur = lk.x; cur_t = t0;
             } else if (h1) {
-                cur = lk.y;
+                cur = lk.y; cur_t = t1;
             } else {
                 cur = kFastEmpty;
                 while (sp > 0) {                    // pop, skipping children the bound now excludes
                     --sp;
-                    if (stk_t[sp] <= tmax) { cur = stk_n[sp]; break; }
+                    if (stk_t[sp] <= tmax) { cur = stk_n[sp]; cur_t = stk_t[sp]; break; }
                 }
             }
         }
@@ -165,7 +209,7 @@ RT_D void closest_fast(const FBvh f, const DTriI *tri_i, d3 o, d3 d, float tmax,
             const uint32_t code = (uint32_t)~cur, first = code >> 3, count = (code & 7u) + 1u;
             for (uint32_t i = first; i < first + count; ++i) {
                 float tlo, thi;
-                const int cls = tri_classify(f.tris + i, r, o, dl1g, tmax, tlo, thi);
+                const int cls = tri_classify(f.tris + i, tri_i + i, r, o, d, cur_t, dl1g, tmax, tlo, thi);
                 if (cls == 0) continue;
                 if (cls == 2) tmax = fminf(tmax, thi);
                 if (nc == kCand) {                  // rare: drop entries the new bound excludes
@@ -181,7 +225,7 @@ RT_D void closest_fast(const FBvh f, const DTriI *tri_i, d3 o, d3 d, float tmax,
         cur = kFastEmpty;
         while (sp > 0) {
             --sp;
-            if (stk_t[sp] <= tmax) { cur = stk_n[sp]; break; }
+            if (stk_t[sp] <= tmax) { cur = stk_n[sp]; cur_t = stk_t[sp]; break; }
         }
     }
     for (int j = 0; j < nc; ++j)                    // warp-converged f64 confirmation
@@ -274,11 +318,14 @@ RT_D void light_hits_fast(const FBvh f, const DTriI *tri_i, const DTriS *tri_s, 
     const float dl1g = kGamma * (fabsf(r.dx) + fabsf(r.dy) + fabsf(r.dz));
     const float inf = __int_as_float(0x7F800000);
     int32_t stk[kFastStack];
+    float stk_t[kFastStack];
     uint32_t cand[kCand];
     int sp = 0, nc = 0;
-    stk[sp++] = f.root;
+    stk[sp] = f.root; stk_t[sp] = 0.0f; ++sp;
     while (sp > 0) {
-        const int32_t cur = stk[--sp];
+        --sp;
+        const int32_t cur = stk[sp];
+        const float cur_t = stk_t[sp];
         if (cur >= 0) {
             const float4 *np = reinterpret_cast<const float4 *>(f.nodes + cur);
             const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
@@ -286,13 +333,13 @@ RT_D void light_hits_fast(const FBvh f, const DTriI *tri_i, const DTriS *tri_s, 
             float t0, t1;
             const bool h0 = slab(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, inf, t0);
             const bool h1 = slab(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, inf, t1);
-            if (h1) stk[sp++] = lk.y;
-            if (h0) stk[sp++] = lk.x;
+            if (h1) { stk[sp] = lk.y; stk_t[sp] = t1; ++sp; }
+            if (h0) { stk[sp] = lk.x; stk_t[sp] = t0; ++sp; }
         } else {
             const uint32_t code = (uint32_t)~cur, first = code >> 3, count = (code & 7u) + 1u;
             for (uint32_t i = first; i < first + count; ++i) {
                 float tlo, thi;
-                if (tri_classify(f.tris + i, r, o, dl1g, inf, tlo, thi) == 0) continue;
+                if (tri_classify(f.tris + i, tri_i + i, r, o, d, cur_t, dl1g, inf, tlo, thi) == 0) continue;
                 if (nc == kCand) {                  // flush in visit order, then keep collecting
                     for (int j = 0; j < kCand; ++j) light_confirm(tri_i, tri_s, o, d, cand[j], impact);
                     nc = 0;

@@ -17,7 +17,7 @@ cudaError_t launch_light_pdf(cudaStream_t st, const DScene &sc, int mode, uint64
 cudaError_t launch_render_mega(cudaStream_t st, const DScene &sc, int mode, uint32_t sample_begin, uint32_t sample_count,
                                uint64_t seed, double *accum, DCounters *ctr);
 // ---- wavefront scheduler (wavefront.cu) ----------------------------------------------------------
-constexpr int kWfCand = 4;              // deferred candidates kept per ray and per search
+constexpr int kWfCand = 6;              // deferred candidates kept per ray and per search
 struct WfBuf {                          // per-pixel path slots, structure of arrays; n = width * height
     uint32_t n;
     double *ro, *rd, *T, *L, *pv;       // 3 * n: ray origin / direction, throughput, radiance, pending weight

@@ -182,146 +182,163 @@ __global__ void __launch_bounds__(128) k_wf_shade(DScene sc, WfBuf b, int cur_li
 }
 
 // ---- trace -------------------------------------------------------------------------------------
-constexpr int kMinBusyLanes = 20;       // refill when fewer lanes than this are still traversing
+// Warp-synchronous state machine.  A lane with a ray is in one of two states: at an INNER node
+// (one step = fetch a 64-byte node, two slab tests, descend / push / pop) or at a LEAF with
+// triangles left (one step = one fp32 pre-test).  Every iteration the warp votes and runs the
+// step kind more lanes are waiting for, so the 32 lanes always execute the same code and a
+// finished lane is refilled from the live list as soon as enough lanes are idle — no lane waits
+// for the slowest ray of its warp.  The closest-hit search of the scene hierarchy and the all-hits
+// search of the light hierarchy use the same two steps with per-lane node / triangle pointers.
+constexpr int kRefillLanes = 8;         // refill once this many lanes are idle
 
-__global__ void __launch_bounds__(128, 4) k_wf_trace(DScene sc, WfBuf b, int list) {
+__global__ void __launch_bounds__(128, 4) k_wf_trace(DScene sc, WfBuf b, int list, DCounters *ctr) {
     const uint32_t n = b.n_live[list], N = b.n;
     const uint32_t *__restrict__ live = b.live[list];
     const int lane = threadIdx.x & 31;
     const float inf = __int_as_float(0x7F800000);
-    bool has = false, drained = false;      // drained: the live list has no more rays for this warp
-    uint32_t slot = 0, nc = 0, nl = 0, over = 0;
+    bool has = false, drained = false, closest = true, want_light = false;
+    uint32_t slot = 0, nc = 0, nl = 0, over = 0, tri_i = 0, tri_end = 0;
+    uint32_t n_inner = 0, n_tri = 0, n_cand = 0, n_over = 0;
     FRay r = {};
-    d3 o = mk3(0.0, 0.0, 0.0);
-    float dl1g = 0.0f, tmax = inf;
+    d3 o = mk3(0.0, 0.0, 0.0), dd = o;
+    float dl1g = 0.0f, tmax = inf, cur_t = 0.0f;     // cur_t: conservative entry distance of `cur`
+    const FNode *nodes = sc.ftris.nodes;
+    const FTri *tris = sc.ftris.tris;
+    const DTriI *xtris = sc.tri_i;
     int32_t cur = kFastEmpty;
-    int sp = 0, phase = 0;                  // phase 0: closest hit; 1: light all-hits; 2: finished
-    bool want_light = false;
+    int sp = 0;
     int32_t stk_n[kFastStack];
     float stk_t[kFastStack];
+#define WF_ENTER_LEAF()                                                                     \
+    if (cur < 0 && cur != kFastEmpty) {                                                     \
+        const uint32_t code_ = (uint32_t)~cur;                                              \
+        tri_i = code_ >> 3;                                                                 \
+        tri_end = tri_i + (code_ & 7u) + 1u;                                                \
+    }
+#define WF_POP()                                                                            \
+    {                                                                                       \
+        cur = kFastEmpty;                                                                   \
+        while (sp > 0) {                                                                    \
+            --sp;                                                                           \
+            if (stk_t[sp] <= tmax) { cur = stk_n[sp]; cur_t = stk_t[sp]; break; } \
+        }                                                                                   \
+        WF_ENTER_LEAF()                                                                     \
+    }
     for (;;) {
-        // ---- refill idle lanes from the live list (one atomic per warp)
-        const unsigned need = drained ? 0u : __ballot_sync(kFull, !has);
-        if (need) {
-            const int leader = __ffs(need) - 1;
-            uint32_t base = 0;
-            if (lane == leader) base = atomicAdd(b.cursor, (uint32_t)__popc(need));
-            base = __shfl_sync(kFull, base, leader);
-            if (!has) {
-                const uint32_t idx = base + __popc(need & ((1u << lane) - 1u));
-                if (idx < n) {
-                    slot = live[idx];
-                    o = ld_soa(b.ro, N, slot);
-                    const d3 d = ld_soa(b.rd, N, slot);
-                    r = make_fray(o, d);
-                    dl1g = kGamma * (fabsf(r.dx) + fabsf(r.dy) + fabsf(r.dz));
-                    const uint32_t sid = b.sh_id[slot];
-                    const double st = b.sh_t[slot];
-                    const bool skip = sid != kNoShape && st != st;
-                    tmax = (sid != kNoShape && !skip) ? up_f32(st) : inf;
-                    want_light = (b.flags[slot] & kFlagPendLight) != 0;
-                    nc = 0; nl = 0; over = 0; sp = 0;
-                    cur = skip ? kFastEmpty : sc.ftris.root;
-                    phase = 0;
-                    has = true;
-                }
-            }
-            if (__any_sync(kFull, !has)) drained = true;       // someone got idx >= n: the list is empty
-        }
-        if (!__any_sync(kFull, has)) break;
-        // ---- traverse until this lane's ray is finished or the warp runs too empty
-        if (has) {
-            bool yield = false;
-            if (phase == 0) {
-                while (cur != kFastEmpty && !yield) {
-                    while (cur >= 0) {
-                        const float4 *np = reinterpret_cast<const float4 *>(sc.ftris.nodes + cur);
-                        const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
-                        const int4 lk = __ldg(reinterpret_cast<const int4 *>(np) + 3);
-                        float t0, t1;
-                        const bool h0 = slab(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tmax, t0);
-                        const bool h1 = slab(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, tmax, t1);
-                        if (h0 && h1) {
-                            const bool first0 = t0 <= t1;
-                            stk_n[sp] = first0 ? lk.y : lk.x;
-                            stk_t[sp] = first0 ? t1 : t0;
-                            ++sp;
-                            cur = first0 ? lk.x : lk.y;
-                        } else if (h0) {
-                            cur = lk.x;
-                        } else if (h1) {
-                            cur = lk.y;
-                        } else {
-                            cur = kFastEmpty;
-                            while (sp > 0) {
-                                --sp;
-                                if (stk_t[sp] <= tmax) { cur = stk_n[sp]; break; }
-                            }
-                        }
-                        if (!drained && __popc(__activemask()) < kMinBusyLanes) { yield = true; break; }
-                    }
-                    if (yield || cur == kFastEmpty) break;
-                    if (cur < 0) {
-                        const uint32_t code = (uint32_t)~cur, first = code >> 3, count = (code & 7u) + 1u;
-                        for (uint32_t i = first; i < first + count; ++i) {
-                            float tlo, thi;
-                            const int cls = tri_classify(sc.ftris.tris + i, r, o, dl1g, tmax, tlo, thi);
-                            if (cls == 0) continue;
-                            if (cls == 2) tmax = fminf(tmax, thi);
-                            if (nc < (uint32_t)kWfCand) {
-                                b.cand[nc * N + slot] = i;
-                                b.cand_t[nc * N + slot] = tlo;
-                                ++nc;
-                            } else {
-                                over |= kOverflowClosest;       // rare: the shade kernel redoes this search
-                            }
-                        }
-                        cur = kFastEmpty;
-                        while (sp > 0) {
-                            --sp;
-                            if (stk_t[sp] <= tmax) { cur = stk_n[sp]; break; }
-                        }
-                    }
-                }
-                if (!yield && cur == kFastEmpty) {              // closest search done
-                    if (want_light && sc.fltris.root != kFastEmpty) {
-                        phase = 1; sp = 0; stk_n[sp++] = sc.fltris.root;
-                    } else {
-                        phase = 2;
-                    }
-                }
-            }
-            if (phase == 1 && !yield) {
-                // all hits along the same ray over the light hierarchy, children left then right:
-                // the reference's visit order (bvh.rs:188-210), which fixes the order of the pdf sum
-                while (sp > 0) {
-                    const int32_t node = stk_n[--sp];
-                    if (node >= 0) {
-                        const float4 *np = reinterpret_cast<const float4 *>(sc.fltris.nodes + node);
-                        const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
-                        const int4 lk = __ldg(reinterpret_cast<const int4 *>(np) + 3);
-                        float t0, t1;
-                        const bool h0 = slab(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, inf, t0);
-                        const bool h1 = slab(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, inf, t1);
-                        if (h1) stk_n[sp++] = lk.y;
-                        if (h0) stk_n[sp++] = lk.x;
-                    } else {
-                        const uint32_t code = (uint32_t)~node, first = code >> 3, count = (code & 7u) + 1u;
-                        for (uint32_t i = first; i < first + count; ++i) {
-                            float tlo, thi;
-                            if (tri_classify(sc.fltris.tris + i, r, o, dl1g, inf, tlo, thi) == 0) continue;
-                            if (nl < (uint32_t)kWfCand) { b.lcand[nl * N + slot] = i; ++nl; }
-                            else over |= kOverflowLight;
-                        }
-                    }
-                }
-                phase = 2;
-            }
-            if (phase == 2) {
+        // ---- lanes whose search is complete: start the light search or publish and go idle
+        if (has && cur == kFastEmpty) {
+            if (closest && want_light && sc.fltris.root != kFastEmpty) {
+                closest = false;
+                nodes = sc.fltris.nodes; tris = sc.fltris.tris; xtris = sc.ltri_i;
+                tmax = inf; sp = 0;
+                cur = sc.fltris.root; cur_t = 0.0f;
+                WF_ENTER_LEAF()
+            } else {
                 b.ncand[slot] = nc | (nl << 8) | over;
                 has = false;
             }
         }
+        // ---- refill idle lanes from the live list: ballot + prefix sum, one atomic per warp
+        const unsigned idle = __ballot_sync(kFull, !has);
+        if (!drained && (__popc(idle) >= kRefillLanes)) {
+            const int leader = __ffs(idle) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(b.cursor, (uint32_t)__popc(idle));
+            base = __shfl_sync(kFull, base, leader);
+            if (!has) {
+                const uint32_t idx = base + __popc(idle & ((1u << lane) - 1u));
+                if (idx < n) {
+                    slot = live[idx];
+                    o = ld_soa(b.ro, N, slot);
+                    dd = ld_soa(b.rd, N, slot);
+                    r = make_fray(o, dd);
+                    dl1g = kGamma * (fabsf(r.dx) + fabsf(r.dy) + fabsf(r.dz));
+                    const uint32_t sid = b.sh_id[slot];
+                    const double st = b.sh_t[slot];
+                    const bool skip = (sid != kNoShape && st != st) || ray_is_nan(o, dd);
+                    tmax = (sid != kNoShape && !skip) ? up_f32(st) : inf;
+                    want_light = (b.flags[slot] & kFlagPendLight) != 0;
+                    nc = 0; nl = 0; over = 0; sp = 0;
+                    closest = true;
+                    nodes = sc.ftris.nodes; tris = sc.ftris.tris; xtris = sc.tri_i;
+                    cur = skip ? kFastEmpty : sc.ftris.root; cur_t = 0.0f;
+                    WF_ENTER_LEAF()
+                    has = true;
+                }
+            }
+            if (__any_sync(kFull, !has)) drained = true;       // an index fell off the list: it is empty
+        }
+        if (!__any_sync(kFull, has)) {
+            if (drained) break;
+            continue;                                           // fewer than kRefillLanes... cannot happen with 32 idle
+        }
+        // ---- vote: which step do more lanes wait for?
+        const bool wi = has && cur >= 0;
+        const bool wt = has && cur < 0 && cur != kFastEmpty;
+        const int ni = __popc(__ballot_sync(kFull, wi)), nt = __popc(__ballot_sync(kFull, wt));
+        if (ni >= nt) {
+            if (wi) {                                           // INNER step
+                ++n_inner;
+                const float4 *np = reinterpret_cast<const float4 *>(nodes + cur);
+                const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
+                const int4 lk = __ldg(reinterpret_cast<const int4 *>(np) + 3);
+                float t0, t1;
+                const bool h0 = slab(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tmax, t0);
+                const bool h1 = slab(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, tmax, t1);
+                if (h0 && h1) {
+                    // closest: nearer child first.  light (all hits): left first — the reference's
+                    // visit order (bvh.rs:188-210), which fixes the order of the pdf sum
+                    const bool first0 = closest ? (t0 <= t1) : true;
+                    stk_n[sp] = first0 ? lk.y : lk.x;
+                    stk_t[sp] = first0 ? t1 : t0;
+                    ++sp;
+                    cur = first0 ? lk.x : lk.y;
+                    cur_t = first0 ? t0 : t1;
+                    WF_ENTER_LEAF()
+                } else if (h0) {
+                    cur = lk.x; cur_t = t0;
+                    WF_ENTER_LEAF()
+                } else if (h1) {
+                    cur = lk.y; cur_t = t1;
+                    WF_ENTER_LEAF()
+                } else {
+                    WF_POP()
+                }
+            }
+        } else if (wt) {                                        // TRIANGLE step
+            ++n_tri;
+            float tlo, thi;
+            const int cls = tri_classify(tris + tri_i, xtris + tri_i, r, o, dd, cur_t, dl1g, tmax, tlo, thi);
+            if (cls != 0) {
+                ++n_cand;
+                if (closest) {
+                    if (cls == 2) tmax = fminf(tmax, thi);
+                    if (nc < (uint32_t)kWfCand) {
+                        b.cand[nc * N + slot] = tri_i;
+                        b.cand_t[nc * N + slot] = tlo;
+                        ++nc;
+                    } else {
+                        over |= kOverflowClosest;               // rare: the shade kernel redoes this search
+                        ++n_over;
+                    }
+                } else {
+                    if (nl < (uint32_t)kWfCand) { b.lcand[nl * N + slot] = tri_i; ++nl; }
+                    else { over |= kOverflowLight; ++n_over; }
+                }
+            }
+            if (++tri_i == tri_end) WF_POP()
+        }
+    }
+#undef WF_ENTER_LEAF
+#undef WF_POP
+    // diagnostics: fp32 node visits / pre-tests / candidates / overflows of this launch
+    unsigned long long v[4] = {n_inner, n_tri, n_cand, n_over};
+    unsigned long long *dst[4] = {&ctr->aabb_tests, &ctr->prim_tests, &ctr->light_aabb_tests, &ctr->light_prim_tests};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        unsigned long long s = v[k];
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(kFull, s, off);
+        if (lane == 0 && s) atomicAdd(dst[k], s);
     }
 }
 
@@ -347,7 +364,7 @@ cudaError_t launch_render_wavefront(cudaStream_t st, const DScene &sc, uint32_t 
         cudaMemsetAsync(&b.n_live[cur ^ 1], 0, sizeof(uint32_t), st);
         cudaMemsetAsync(b.cursor, 0, sizeof(uint32_t), st);
         k_wf_shade<<<blocks, 128, 0, st>>>(sc, b, cur, sample_begin, sample_count, seed, accum, ctr);
-        k_wf_trace<<<trace_blocks, 128, 0, st>>>(sc, b, cur ^ 1);
+        k_wf_trace<<<trace_blocks, 128, 0, st>>>(sc, b, cur ^ 1, ctr);
         *launches += 2;
         cur ^= 1;
         if ((it & 7) == 7) {                    // poll the live count without stalling the stream
