@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(128) k_wf_shade(DScene sc, WfBuf b, int cur_li
 // search of the light hierarchy use the same two steps with per-lane node / triangle pointers.
 constexpr int kRefillLanes = 8;         // refill once this many lanes are idle
 
-__global__ void __launch_bounds__(128, 4) k_wf_trace(DScene sc, WfBuf b, int list, DCounters *ctr) {
+__global__ void __launch_bounds__(128, 6) k_wf_trace(DScene sc, WfBuf b, int list, DCounters *ctr) {
     const uint32_t n = b.n_live[list], N = b.n;
     const uint32_t *__restrict__ live = b.live[list];
     const int lane = threadIdx.x & 31;
@@ -225,57 +225,62 @@ __global__ void __launch_bounds__(128, 4) k_wf_trace(DScene sc, WfBuf b, int lis
         WF_ENTER_LEAF()                                                                     \
     }
     for (;;) {
-        // ---- lanes whose search is complete: start the light search or publish and go idle
-        if (has && cur == kFastEmpty) {
-            if (closest && want_light && sc.fltris.root != kFastEmpty) {
-                closest = false;
-                nodes = sc.fltris.nodes; tris = sc.fltris.tris; xtris = sc.ltri_i;
-                tmax = inf; sp = 0;
-                cur = sc.fltris.root; cur_t = 0.0f;
-                WF_ENTER_LEAF()
-            } else {
-                b.ncand[slot] = nc | (nl << 8) | over;
-                has = false;
-            }
-        }
-        // ---- refill idle lanes from the live list: ballot + prefix sum, one atomic per warp
-        const unsigned idle = __ballot_sync(kFull, !has);
-        if (!drained && (__popc(idle) >= kRefillLanes)) {
-            const int leader = __ffs(idle) - 1;
-            uint32_t base = 0;
-            if (lane == leader) base = atomicAdd(b.cursor, (uint32_t)__popc(idle));
-            base = __shfl_sync(kFull, base, leader);
-            if (!has) {
-                const uint32_t idx = base + __popc(idle & ((1u << lane) - 1u));
-                if (idx < n) {
-                    slot = live[idx];
-                    o = ld_soa(b.ro, N, slot);
-                    dd = ld_soa(b.rd, N, slot);
-                    r = make_fray(o, dd);
-                    dl1g = kGamma * (fabsf(r.dx) + fabsf(r.dy) + fabsf(r.dz));
-                    const uint32_t sid = b.sh_id[slot];
-                    const double st = b.sh_t[slot];
-                    const bool skip = (sid != kNoShape && st != st) || ray_is_nan(o, dd);
-                    tmax = (sid != kNoShape && !skip) ? up_f32(st) : inf;
-                    want_light = (b.flags[slot] & kFlagPendLight) != 0;
-                    nc = 0; nl = 0; over = 0; sp = 0;
-                    closest = true;
-                    nodes = sc.ftris.nodes; tris = sc.ftris.tris; xtris = sc.tri_i;
-                    cur = skip ? kFastEmpty : sc.ftris.root; cur_t = 0.0f;
+        // ---- vote: which step do more lanes wait for?  (two ballots are the whole loop control
+        // while every lane is busy)
+        bool wi = has && cur >= 0;
+        bool wt = has && cur < 0 && cur != kFastEmpty;
+        unsigned mi = __ballot_sync(kFull, wi), mt = __ballot_sync(kFull, wt);
+        if ((mi | mt) != kFull) {
+            // some lanes are finished or idle
+            if (has && cur == kFastEmpty) {
+                if (closest && want_light && sc.fltris.root != kFastEmpty) {       // start the light search
+                    closest = false;
+                    nodes = sc.fltris.nodes; tris = sc.fltris.tris; xtris = sc.ltri_i;
+                    tmax = inf; sp = 0;
+                    cur = sc.fltris.root; cur_t = 0.0f;
                     WF_ENTER_LEAF()
-                    has = true;
+                } else {                                                            // publish, go idle
+                    b.ncand[slot] = nc | (nl << 8) | over;
+                    has = false;
                 }
             }
-            if (__any_sync(kFull, !has)) drained = true;       // an index fell off the list: it is empty
+            // refill idle lanes from the live list: ballot + prefix sum, one atomic per warp
+            const unsigned idle = __ballot_sync(kFull, !has);
+            if (!drained && __popc(idle) >= kRefillLanes) {
+                const int leader = __ffs(idle) - 1;
+                uint32_t base = 0;
+                if (lane == leader) base = atomicAdd(b.cursor, (uint32_t)__popc(idle));
+                base = __shfl_sync(kFull, base, leader);
+                if (!has) {
+                    const uint32_t idx = base + __popc(idle & ((1u << lane) - 1u));
+                    if (idx < n) {
+                        slot = live[idx];
+                        o = ld_soa(b.ro, N, slot);
+                        dd = ld_soa(b.rd, N, slot);
+                        r = make_fray(o, dd);
+                        dl1g = kGamma * (fabsf(r.dx) + fabsf(r.dy) + fabsf(r.dz));
+                        const uint32_t sid = b.sh_id[slot];
+                        const double st = b.sh_t[slot];
+                        const bool skip = (sid != kNoShape && st != st) || ray_is_nan(o, dd);
+                        tmax = (sid != kNoShape && !skip) ? up_f32(st) : inf;
+                        want_light = (b.flags[slot] & kFlagPendLight) != 0;
+                        nc = 0; nl = 0; over = 0; sp = 0;
+                        closest = true;
+                        nodes = sc.ftris.nodes; tris = sc.ftris.tris; xtris = sc.tri_i;
+                        cur = skip ? kFastEmpty : sc.ftris.root; cur_t = 0.0f;
+                        WF_ENTER_LEAF()
+                        has = true;
+                    }
+                }
+                if (__any_sync(kFull, !has)) drained = true;   // an index fell off the list: it is empty
+            }
+            if (drained && !__any_sync(kFull, has)) break;
+            wi = has && cur >= 0;
+            wt = has && cur < 0 && cur != kFastEmpty;
+            mi = __ballot_sync(kFull, wi);
+            mt = __ballot_sync(kFull, wt);
         }
-        if (!__any_sync(kFull, has)) {
-            if (drained) break;
-            continue;                                           // fewer than kRefillLanes... cannot happen with 32 idle
-        }
-        // ---- vote: which step do more lanes wait for?
-        const bool wi = has && cur >= 0;
-        const bool wt = has && cur < 0 && cur != kFastEmpty;
-        const int ni = __popc(__ballot_sync(kFull, wi)), nt = __popc(__ballot_sync(kFull, wt));
+        const int ni = __popc(mi), nt = __popc(mt);
         if (ni >= nt) {
             if (wi) {                                           // INNER step
                 ++n_inner;
