@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument("--nx", type=int, default=500, help="heightfield quads in x (500 x 1000 = 1M triangles)")
     ap.add_argument("--nz", type=int, default=1000)
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
-    ap.add_argument("--sched", default="megakernel", choices=["megakernel", "wavefront"])
+    ap.add_argument("--sched", default="wavefront", choices=["megakernel", "wavefront"])
     ap.add_argument("--seed", type=lambda s: int(s, 0), default=0xC0FFEE)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-spp", type=int, default=1, help="samples per step of the CPU reference arm")
@@ -158,6 +158,7 @@ def main():
 
     import rtb200
     import rtb200.ctypes_types as T
+    from rtb200 import sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -217,7 +218,7 @@ def main():
     ev[0].record(stream)
     for k in range(args.steps):
         k_ev[k][0].record(stream)
-        ctx.render_accum((k * world + rank) * S, S, args.seed, mode, sched, clear=True)
+        ctx.render_accum(*sharding.step_sample_range(rank, world, k, S), args.seed, mode, sched, clear=True)
         k_ev[k][1].record(stream)
         if world > 1:
             with torch.cuda.stream(stream):
@@ -297,7 +298,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(scene_bytes), "d2h_bytes_per_step": int(img.nbytes),
                     "ms_per_step": e2e_s / max(1, args.steps) * 1e3},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": prof.get("dram_bytes_per_launch"), "peak_source": peak_src, "kernel": "k_render_mega<FastPolicy>" if args.mode == "fast" else "k_render_mega<ExactPolicy>",
+                         "traffic": prof.get("dram_bytes_per_launch"), "peak_source": peak_src, "kernel": ("k_wf_trace + k_wf_shade (one wavefront render call)" if args.sched == "wavefront" else "k_render_mega<FastPolicy>") if args.mode == "fast" else "k_render_mega<ExactPolicy>",
                          "kernel_ms_per_launch": kernel_ms, "algorithmic_bytes_per_segment": bytes_per_segment,
                          "aabb_tests_per_segment": exact_c["aabb_tests"] / max(1, exact_c["segments"]),
                          "prim_tests_per_segment": exact_c["prim_tests"] / max(1, exact_c["segments"])},

@@ -1,0 +1,65 @@
+"""Multi-GPU host logic on the CPU: sample-range sharding + sum-reduce over a 2-rank gloo group,
+with the oracle standing in for the GPU renderer (the reduce and the partition are what is under
+test; the device path is covered by the -m gpu tests)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import rtb200
+from rtb200 import scenes, sharding
+
+
+def test_sample_range_partitions_exactly():
+    for total in (0, 1, 7, 64, 1024):
+        for world in (1, 2, 3, 4, 8):
+            covered = []
+            for r in range(world):
+                b, c = sharding.sample_range(r, world, total, first_sample=5)
+                covered += list(range(b, b + c))
+            assert covered == list(range(5, 5 + total))
+    seen = set()
+    for k in range(3):
+        for r in range(4):
+            b, c = sharding.step_sample_range(r, 4, k, 8)
+            s = set(range(b, b + c))
+            assert not (s & seen)
+            seen |= s
+    assert seen == set(range(96))
+    with pytest.raises(ValueError):
+        sharding.sample_range(2, 2, 10)
+
+
+def _worker(rank, world, port, text, total, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import loaders, orc
+    scene = orc.OracleScene(loaders.parse_text_scene(text))
+    begin, count = sharding.sample_range(rank, world, total)
+    accum, _ = scene.render_accum(begin, count, 0xC0FFEE, 1)
+    t = torch.from_numpy(accum)
+    sharding.reduce_accum(t, dst=0)
+    if rank == 0:
+        np.save(out_path, t.numpy())
+    dist.destroy_process_group()
+
+
+def test_two_rank_reduce_equals_single_rank(orc, tmp_path):
+    from oracle import loaders
+    text = scenes.cornell_text(24, 16, 6, 4, scenes.CORNELL_EXTRA)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = os.path.join(str(tmp_path), "acc.npy")
+    mp.spawn(_worker, args=(2, port, text, 6, out), nprocs=2, join=True)
+    got = np.load(out)
+    want, _ = orc.OracleScene(loaders.parse_text_scene(text)).render_accum(0, 6, 0xC0FFEE, 1)
+    assert want.sum() > 0
+    # same paths, per-pixel sums formed in a different order: equal to rounding
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-300)
+    # and the tonemapped image agrees
+    np.testing.assert_allclose(orc.postprocess(got, 6), orc.postprocess(want, 6), rtol=1e-12, atol=1e-15)
