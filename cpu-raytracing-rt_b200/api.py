@@ -12,7 +12,7 @@ import numpy as np
 from . import ctypes_types as T
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "librt_b200.so")
+_LIB_PATH = os.environ.get("RT_B200_LIB") or os.path.join(_HERE, "librt_b200.so")     # env override: tuning builds only
 _LIB = None
 
 # every symbol include/rt_b200.h declares (tests check that the library exports each of them)

@@ -51,17 +51,21 @@ struct __align__(16) DMaterial {        // Metadata, 64 B (scene.rs:13-18)
 static_assert(sizeof(DMaterial) == 64, "DMaterial must be 64 bytes");
 
 // ---- FAST mode structures -------------------------------------------------------------------
-// Inner node of the fp32 culling hierarchy, derived on the host from the reference's binary tree:
-// the boxes of BOTH children, rounded OUTWARD from the f64 boxes, so one 64-byte fetch (4 x 16 B)
-// decides both descents.  child >= 0: FNode index; child < 0: leaf, ~child = (first << 3) |
-// (count - 1) with 1 <= count <= 8 (longer reference leaves are split on the host).
-struct __align__(16) FNode {            // 64 B
-    float lo0[3], hi0[3];               // left child box  (order: lo0.xyz hi0.xyz lo1.xyz hi1.xyz)
-    float lo1[3], hi1[3];               // right child box
-    int32_t child0, child1;
-    uint32_t _pad[2];
+// Inner node of the fp32 culling hierarchy, derived on the host by collapsing the reference's
+// binary tree into 4-wide nodes: the boxes of up to FOUR children, rounded OUTWARD from the f64
+// boxes, one plane per 16-byte vector (lo.x of the 4 children, lo.y, lo.z, hi.x, hi.y, hi.z), so
+// a ray loads the NEAR planes of all four children with three 16-byte loads whose offsets depend
+// only on the ray's direction signs, and the FAR planes with three more.  128 B = one cache line.
+// child >= 0: FNode index; child < 0: leaf, ~child = (first << 3) | (count - 1) with
+// 1 <= count <= 8 (longer reference leaves are split on the host); kFastEmpty: unused slot
+// (its box is +inf / -inf: never hit).  Child order = the reference's left-to-right order.
+struct __align__(16) FNode {            // 128 B
+    float lo[3][4];                     // lo[axis][child]
+    float hi[3][4];
+    int32_t child[4];
+    uint32_t _pad[4];
 };
-static_assert(sizeof(FNode) == 64, "FNode must be 64 bytes");
+static_assert(sizeof(FNode) == 128, "FNode must be 128 bytes");
 
 // fp32 pre-test record: anchor vertex in f64 (the subtraction origin - a is done in f64, then
 // rounded once), edges in fp32.  48 B = 3 x 16 B.

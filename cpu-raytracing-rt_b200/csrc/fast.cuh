@@ -4,9 +4,10 @@
 // division costs ~20 instructions.  The reference spends 12 f64 divisions per node visit
 // (reference src/aabb.rs:62-63) and 9 per triangle test (src/primitives/triangle.rs:56-58).
 // FAST mode never divides while culling:
-//   * boxes: fp32 slabs with a precomputed reciprocal direction.  The fp32 boxes are rounded
-//     outward on the host and every rounding error of the slab arithmetic is bounded and added to
-//     the accepted interval, so any ray that touches the f64 box passes the fp32 test;
+//   * boxes: a 4-wide hierarchy of fp32 boxes (collapsed from the reference's binary tree, rounded
+//     outward on the host), slab-tested with a precomputed reciprocal direction; every rounding
+//     error of the slab arithmetic is bounded and folded into per-ray constants, so any ray that
+//     touches the f64 box passes the fp32 test;
 //   * triangles: an fp32 Moller-Trumbore pre-test in determinant-scaled form whose rejection
 //     thresholds carry the error bound of each triple product, so it can only reject triangles
 //     the exact test also rejects;
@@ -28,11 +29,19 @@ constexpr float kU = 5.9604645e-8f;         // 2^-24, fp32 unit roundoff
 // |computed - exact| <= 8u * sum_k |w_k| (|d_i e_j| + |d_j e_i|) <= 8u * |w|_1 |d|_1 |e|_1.
 constexpr float kGamma = 5.4e-7f;           // 9u > 8u (1 + O(u))
 
-struct FRay {                               // per-ray culling state (12 registers)
-    float idx, idy, idz;                    // 1 / d, |d| clamped away from 0
-    float nx, ny, nz;                       // -(o * id)
-    float px, py, pz;                       // slack covering the rounding of o, id and o * id
+// Per-ray culling state.  For a box plane b the slab distance (b - o) / d is evaluated as
+// fma(b, id, n) with id = 1/fl(d), n = -(fl(o) * id):  computed = true*(1+eta) + delta with
+// |eta| <= 3u and |delta| <= 2.2u|n|.  The constants below fold that bound in once per ray:
+//   NEAR planes use (idn, nn) = (id, n - 8u|n|) * (1 - 8u)  -> a true LOWER bound when >= 0,
+//   FAR  planes use (idf, nf) = (id, n + 8u|n|) * (1 + 8u)  -> a true UPPER bound when >= 0
+// (8u leaves room for the two extra roundings of the scaled constants), so the per-box work is
+// 6 FMAs and 6 min/max with no pad arithmetic.  Which plane of a box is the near one depends only
+// on the sign of d: `sx/sy/sz` select the 16-byte vector to load (lo or hi of the four children).
+struct FRay {
+    float inx, iny, inz, nnx, nny, nnz;     // near-plane constants
+    float ifx, ify, ifz, nfx, nfy, nfz;     // far-plane constants
     float dx, dy, dz;                       // d rounded to fp32 (triangle pre-test)
+    uint32_t sx, sy, sz;                    // 1 when the component of d is negative
 };
 RT_D float clamp_recip(float d) {
     const float a = fabsf(d) < 1e-30f ? copysignf(1e-30f, d) : d;
@@ -41,24 +50,56 @@ RT_D float clamp_recip(float d) {
 RT_D FRay make_fray(d3 o, d3 d) {
     FRay r;
     r.dx = __double2float_rn(d.x); r.dy = __double2float_rn(d.y); r.dz = __double2float_rn(d.z);
-    r.idx = clamp_recip(r.dx); r.idy = clamp_recip(r.dy); r.idz = clamp_recip(r.dz);
-    r.nx = -(__double2float_rn(o.x) * r.idx); r.ny = -(__double2float_rn(o.y) * r.idy); r.nz = -(__double2float_rn(o.z) * r.idz);
-    // computed slab value = true * (1 + <=3u) + delta, |delta| <= 2.1 u |o / d|  
-    r.px = 3.0f * kU * fabsf(r.nx); r.py = 3.0f * kU * fabsf(r.ny); r.pz = 3.0f * kU * fabsf(r.nz);
+    const float idx = clamp_recip(r.dx), idy = clamp_recip(r.dy), idz = clamp_recip(r.dz);
+    const float nx = -(__double2float_rn(o.x) * idx), ny = -(__double2float_rn(o.y) * idy), nz = -(__double2float_rn(o.z) * idz);
+    const float lo = 1.0f - 8.0f * kU, hi = 1.0f + 8.0f * kU, pad = 8.0f * kU;
+    r.inx = idx * lo; r.iny = idy * lo; r.inz = idz * lo;
+    r.ifx = idx * hi; r.ify = idy * hi; r.ifz = idz * hi;
+    r.nnx = (nx - pad * fabsf(nx)) * lo; r.nny = (ny - pad * fabsf(ny)) * lo; r.nnz = (nz - pad * fabsf(nz)) * lo;
+    r.nfx = (nx + pad * fabsf(nx)) * hi; r.nfy = (ny + pad * fabsf(ny)) * hi; r.nfz = (nz + pad * fabsf(nz)) * hi;
+    r.sx = idx < 0.0f; r.sy = idy < 0.0f; r.sz = idz < 0.0f;
     return r;
 }
-// Conservative slab test of one fp32 box against [0, tmax]: true => the f64 box may be hit.
-// computed slab value = true * (1 + eta) + delta with |eta| <= 3u, |delta| <= pad, so
-// (near - pad) * (1 - 4u) is a TRUE lower bound of the entry distance and (far + pad) * (1 + 4u)
-// a true upper bound of the exit distance.  tn is that lower bound: it orders the children,
-// decides whether a deferred child can still matter, and anchors the ray-relative triangle test.
-RT_D bool slab(const FRay &r, float lx, float ly, float lz, float hx, float hy, float hz, float tmax, float &tn) {
-    const float ax = fmaf(lx, r.idx, r.nx), bx = fmaf(hx, r.idx, r.nx);
-    const float ay = fmaf(ly, r.idy, r.ny), by = fmaf(hy, r.idy, r.ny);
-    const float az = fmaf(lz, r.idz, r.nz), bz = fmaf(hz, r.idz, r.nz);
-    tn = fmaxf(fmaxf(fminf(ax, bx) - r.px, fminf(ay, by) - r.py), fmaxf(fminf(az, bz) - r.pz, 0.0f)) * 0.9999995f;
-    const float tf = fminf(fminf(fmaxf(ax, bx) + r.px, fmaxf(ay, by) + r.py), fminf(fmaxf(az, bz) + r.pz, tmax));
-    return tn <= tf * 1.0000005f;
+// One visit of a 4-wide node: conservative slab tests of its four child boxes against [0, tmax].
+// key[k] = conservative entry distance of child k (a true lower bound) when the f64 box may be
+// hit, +inf otherwise.  7 x 16-byte loads: 3 near-plane vectors, 3 far-plane vectors, the links.
+struct Visit4 {
+    float key[4];
+    int32_t child[4];
+};
+RT_D Visit4 visit4(const FNode *node, const FRay &r, float tmax) {
+    const float4 *p = reinterpret_cast<const float4 *>(node);
+    // vectors 0..2 = lo.x lo.y lo.z, 3..5 = hi.x hi.y hi.z of the four children
+    const float4 ax = __ldg(p + 0 + 3 * r.sx), ay = __ldg(p + 1 + 3 * r.sy), az = __ldg(p + 2 + 3 * r.sz);
+    const float4 bx = __ldg(p + 3 - 3 * r.sx), by = __ldg(p + 4 - 3 * r.sy), bz = __ldg(p + 5 - 3 * r.sz);
+    const int4 lk = __ldg(reinterpret_cast<const int4 *>(p) + 6);
+    const float inf = __int_as_float(0x7F800000);
+    Visit4 v;
+#define RT_SLAB(K, C)                                                                                          \
+    {                                                                                                          \
+        const float tn = fmaxf(fmaxf(fmaf(ax.C, r.inx, r.nnx), fmaf(ay.C, r.iny, r.nny)),                      \
+                               fmaxf(fmaf(az.C, r.inz, r.nnz), 0.0f));                                         \
+        const float tf = fminf(fminf(fmaf(bx.C, r.ifx, r.nfx), fmaf(by.C, r.ify, r.nfy)),                      \
+                               fminf(fmaf(bz.C, r.ifz, r.nfz), tmax));                                         \
+        v.key[K] = tn <= tf ? tn : inf;                                                                        \
+    }
+    RT_SLAB(0, x) RT_SLAB(1, y) RT_SLAB(2, z) RT_SLAB(3, w)
+#undef RT_SLAB
+    v.child[0] = lk.x; v.child[1] = lk.y; v.child[2] = lk.z; v.child[3] = lk.w;
+    return v;
+}
+// ascending sort of the four (key, child) pairs: 5 compare-exchanges
+RT_D void sort4(Visit4 &v) {
+#define RT_CE(A, B)                                                                     \
+    {                                                                                   \
+        const bool sw = v.key[B] < v.key[A];                                            \
+        const float ka = v.key[A], kb = v.key[B];                                       \
+        const int32_t ca = v.child[A], cb = v.child[B];                                 \
+        v.key[A] = sw ? kb : ka; v.key[B] = sw ? ka : kb;                               \
+        v.child[A] = sw ? cb : ca; v.child[B] = sw ? ca : cb;                           \
+    }
+    RT_CE(0, 1) RT_CE(2, 3) RT_CE(0, 2) RT_CE(1, 3) RT_CE(1, 2)
+#undef RT_CE
 }
 
 struct FTriRec {
@@ -174,28 +215,19 @@ RT_D void closest_fast(const FBvh f, const DTriI *tri_i, d3 o, d3 d, float tmax,
     int nc = 0, sp = 0;
     int32_t cur = f.root;
     float cur_t = 0.0f;                     // conservative entry distance of `cur`
+    const float inf = __int_as_float(0x7F800000);
     // "while-while": all lanes first walk inner nodes until each holds a leaf (or is done), then
     // all lanes that hold a leaf run the triangle pre-tests together.  kFastEmpty doubles as the
     // "nothing left" marker (it is negative and never a valid leaf code of a non-empty tree).
     while (cur != kFastEmpty) {
         while (cur >= 0) {
-            const float4 *np = reinterpret_cast<const float4 *>(f.nodes + cur);
-            const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
-            const int4 lk = __ldg(reinterpret_cast<const int4 *>(np) + 3);
-            float t0, t1;
-            const bool h0 = slab(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tmax, t0);
-            const bool h1 = slab(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, tmax, t1);
-            if (h0 && h1) {
-                const bool first0 = t0 <= t1;
-                stk_n[sp] = first0 ? lk.y : lk.x;
-                stk_t[sp] = first0 ? t1 : t0;
-                ++sp;
-                cur = first0 ? lk.x : lk.y;
-                cur_t = first0 ? t0 : t1;
-            } else if (h0) {
-                cur = lk.x; cur_t = t0;
-            } else if (h1) {
-                cur = lk.y; cur_t = t1;
+            Visit4 v = visit4(f.nodes + cur, r, tmax);
+            sort4(v);                               // nearest first
+            if (v.key[3] < inf) { stk_n[sp] = v.child[3]; stk_t[sp] = v.key[3]; ++sp; }
+            if (v.key[2] < inf) { stk_n[sp] = v.child[2]; stk_t[sp] = v.key[2]; ++sp; }
+            if (v.key[1] < inf) { stk_n[sp] = v.child[1]; stk_t[sp] = v.key[1]; ++sp; }
+            if (v.key[0] < inf) {
+                cur = v.child[0]; cur_t = v.key[0];
             } else {
                 cur = kFastEmpty;
                 while (sp > 0) {                    // pop, skipping children the bound now excludes
@@ -327,14 +359,10 @@ RT_D void light_hits_fast(const FBvh f, const DTriI *tri_i, const DTriS *tri_s, 
         const int32_t cur = stk[sp];
         const float cur_t = stk_t[sp];
         if (cur >= 0) {
-            const float4 *np = reinterpret_cast<const float4 *>(f.nodes + cur);
-            const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
-            const int4 lk = __ldg(reinterpret_cast<const int4 *>(np) + 3);
-            float t0, t1;
-            const bool h0 = slab(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, inf, t0);
-            const bool h1 = slab(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, inf, t1);
-            if (h1) { stk[sp] = lk.y; stk_t[sp] = t1; ++sp; }
-            if (h0) { stk[sp] = lk.x; stk_t[sp] = t0; ++sp; }
+            const Visit4 v = visit4(f.nodes + cur, r, inf);     // children pushed right to left: popped left first
+#pragma unroll
+            for (int k = 3; k >= 0; --k)
+                if (v.key[k] < inf) { stk[sp] = v.child[k]; stk_t[sp] = v.key[k]; ++sp; }
         } else {
             const uint32_t code = (uint32_t)~cur, first = code >> 3, count = (code & 7u) + 1u;
             for (uint32_t i = first; i < first + count; ++i) {

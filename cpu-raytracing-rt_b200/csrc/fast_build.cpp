@@ -1,12 +1,14 @@
 // fast_build.cpp — host: FAST-mode culling structure.
 //
-// The reference hierarchy (reference src/bvh.rs:49-54, one f64 box per node, children fetched
-// separately) is re-packed so that a parent carries BOTH child boxes in fp32.  Boxes are rounded
-// outward, so every ray that touches an f64 box touches its fp32 image; topology, child order
-// (left = first) and primitive order are unchanged, which keeps the all-hits visit order of
-// Light::pdf (src/bvh.rs:188-210) identical.
+// The reference hierarchy (reference src/bvh.rs:49-54: binary, one f64 box per node, children
+// fetched separately) is COLLAPSED into 4-wide nodes that carry the fp32 boxes of their children:
+// starting from a node's two children, the child with the largest surface area is opened in place
+// until four slots are filled.  Boxes are rounded outward, so every ray that touches an f64 box
+// touches its fp32 image; the left-to-right order of children and the primitive order are kept,
+// which keeps the all-hits visit order of Light::pdf (src/bvh.rs:188-210) identical.
 #include "fast_build.hpp"
 
+#include <algorithm>
 #include <cmath>
 #include <limits>
 #include <stdexcept>
@@ -28,8 +30,13 @@ float round_up(double x) {
 struct Builder {
     const HostBvh<HostTri> &bvh;
     FastHierarchy &out;
-    uint32_t max_depth = 0;
+    uint32_t max_stack = 0;
 
+    struct Item {                       // a child slot being assembled: a binary node or a primitive run
+        bool is_node;
+        uint32_t node, first, count;
+        Box6 box;
+    };
     Box6 range_box(uint32_t first, uint32_t count) const {
         const double inf = std::numeric_limits<double>::infinity();
         Box6 b{{inf, inf, inf}, {-inf, -inf, -inf}};
@@ -40,40 +47,69 @@ struct Builder {
             }
         return b;
     }
-    static void put_box(float *lo, float *hi, const Box6 &b) {
-        for (int k = 0; k < 3; ++k) { lo[k] = round_down(b.lo[k]); hi[k] = round_up(b.hi[k]); }
+    static double half_area(const Box6 &b) {
+        const double sx = b.hi[0] - b.lo[0], sy = b.hi[1] - b.lo[1], sz = b.hi[2] - b.lo[2];
+        return sx * sy + sx * sz + sy * sz;
     }
-    // a run of primitives as a child: a leaf code, or (count > 8) a synthesized split
-    int32_t emit_range(uint32_t first, uint32_t count, uint32_t depth) {
-        if (count == 0) throw std::runtime_error("empty leaf inside a non-empty hierarchy");
-        if (count <= 8) {
-            if (first >= (1u << 28)) throw std::runtime_error("too many triangles for the leaf encoding");
-            return ~(int32_t)((first << 3) | (count - 1));
+    Item node_item(uint32_t n) const {
+        const HostNode &h = bvh.nodes[n];
+        if (h.left == RT_NO_CHILD) return Item{false, 0, h.first, h.count, h.box};
+        return Item{true, n, 0, 0, h.box};
+    }
+    static bool expandable(const Item &it) { return it.is_node || it.count > 8; }
+    // children of an item, in the reference's left-to-right order
+    void split(const Item &it, Item &a, Item &b) const {
+        if (it.is_node) {
+            a = node_item(bvh.nodes[it.node].left);
+            b = node_item(bvh.nodes[it.node].right);
+        } else {                        // a reference leaf longer than 8 primitives: halve the run
+            const uint32_t half = it.count / 2;
+            a = Item{false, 0, it.first, half, range_box(it.first, half)};
+            b = Item{false, 0, it.first + half, it.count - half, range_box(it.first + half, it.count - half)};
         }
-        const uint32_t half = count / 2;
-        const int32_t me = (int32_t)out.nodes.size();
-        out.nodes.push_back(FNode{});
-        max_depth = std::max(max_depth, depth + 1);
-        const int32_t c0 = emit_range(first, half, depth + 1), c1 = emit_range(first + half, count - half, depth + 1);
-        FNode &n = out.nodes[me];
-        put_box(n.lo0, n.hi0, range_box(first, half));
-        put_box(n.lo1, n.hi1, range_box(first + half, count - half));
-        n.child0 = c0;
-        n.child1 = c1;
-        return me;
     }
-    int32_t emit(uint32_t node, uint32_t depth) {
-        const HostNode &h = bvh.nodes[node];
-        if (h.left == RT_NO_CHILD) return emit_range(h.first, h.count, depth);
+    // emits the 4-wide node for `it` (which must be expandable); returns its index
+    int32_t emit(const Item &it, uint32_t stack_above) {
+        std::vector<Item> kids(2);
+        split(it, kids[0], kids[1]);
+        while (kids.size() < 4) {       // open the largest expandable child, keeping the order
+            int best = -1;
+            double best_area = -1.0;
+            for (size_t k = 0; k < kids.size(); ++k)
+                if (expandable(kids[k]) && half_area(kids[k].box) > best_area) { best = (int)k; best_area = half_area(kids[k].box); }
+            if (best < 0) break;
+            Item a, b;
+            split(kids[best], a, b);
+            kids[best] = a;
+            kids.insert(kids.begin() + best + 1, b);
+        }
         const int32_t me = (int32_t)out.nodes.size();
         out.nodes.push_back(FNode{});
-        max_depth = std::max(max_depth, depth + 1);
-        const int32_t c0 = emit(h.left, depth + 1), c1 = emit(h.right, depth + 1);
+        // a visit can leave up to (children - 1) entries on the traversal stack
+        const uint32_t stack_here = stack_above + (uint32_t)kids.size() - 1;
+        max_stack = std::max(max_stack, stack_here);
+        int32_t codes[4];
+        for (size_t k = 0; k < kids.size(); ++k) {
+            const Item &c = kids[k];
+            if (expandable(c)) {
+                codes[k] = emit(c, stack_here);
+            } else {
+                if (c.count == 0) throw std::runtime_error("empty leaf inside a non-empty hierarchy");
+                if (c.first >= (1u << 28)) throw std::runtime_error("too many triangles for the leaf encoding");
+                codes[k] = ~(int32_t)((c.first << 3) | (c.count - 1));
+            }
+        }
         FNode &n = out.nodes[me];
-        put_box(n.lo0, n.hi0, bvh.nodes[h.left].box);
-        put_box(n.lo1, n.hi1, bvh.nodes[h.right].box);
-        n.child0 = c0;
-        n.child1 = c1;
+        const float inf = std::numeric_limits<float>::infinity();
+        for (int k = 0; k < 4; ++k) {
+            if (k < (int)kids.size()) {
+                for (int a = 0; a < 3; ++a) { n.lo[a][k] = round_down(kids[k].box.lo[a]); n.hi[a][k] = round_up(kids[k].box.hi[a]); }
+                n.child[k] = codes[k];
+            } else {
+                for (int a = 0; a < 3; ++a) { n.lo[a][k] = inf; n.hi[a][k] = -inf; }
+                n.child[k] = kFastEmpty;
+            }
+        }
         return me;
     }
 };
@@ -93,9 +129,14 @@ void build_fast_hierarchy(const HostBvh<HostTri> &bvh, FastHierarchy &out) {
         out.tris[i] = f;
     }
     Builder b{bvh, out};
-    out.nodes.reserve(bvh.nodes.size() / 2 + 1);
-    out.root = b.emit(0, 0);
-    out.depth = b.max_depth;
+    out.nodes.reserve(bvh.nodes.size() / 3 + 1);
+    const Builder::Item root = b.node_item(0);
+    if (Builder::expandable(root)) {
+        out.root = b.emit(root, 0);
+    } else {
+        out.root = ~(int32_t)((root.first << 3) | (root.count - 1));
+    }
+    out.depth = b.max_stack;
 }
 
 }  // namespace rt

@@ -183,15 +183,21 @@ __global__ void __launch_bounds__(128) k_wf_shade(DScene sc, WfBuf b, int cur_li
 
 // ---- trace -------------------------------------------------------------------------------------
 // Warp-synchronous state machine.  A lane with a ray is in one of two states: at an INNER node
-// (one step = fetch a 64-byte node, two slab tests, descend / push / pop) or at a LEAF with
+// (one step = fetch a 128-byte 4-wide node, four slab tests, sort, descend / push / pop) or at a LEAF with
 // triangles left (one step = one fp32 pre-test).  Every iteration the warp votes and runs the
 // step kind more lanes are waiting for, so the 32 lanes always execute the same code and a
 // finished lane is refilled from the live list as soon as enough lanes are idle — no lane waits
 // for the slowest ray of its warp.  The closest-hit search of the scene hierarchy and the all-hits
 // search of the light hierarchy use the same two steps with per-lane node / triangle pointers.
-constexpr int kRefillLanes = 8;         // refill once this many lanes are idle
+#ifndef WF_REFILL
+#define WF_REFILL 8
+#endif
+#ifndef WF_TRACE_BLOCKS
+#define WF_TRACE_BLOCKS 6
+#endif
+constexpr int kRefillLanes = WF_REFILL;  // refill once this many lanes are idle
 
-__global__ void __launch_bounds__(128, 6) k_wf_trace(DScene sc, WfBuf b, int list, DCounters *ctr) {
+__global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, WfBuf b, int list, DCounters *ctr) {
     const uint32_t n = b.n_live[list], N = b.n;
     const uint32_t *__restrict__ live = b.live[list];
     const int lane = threadIdx.x & 31;
@@ -282,29 +288,25 @@ __global__ void __launch_bounds__(128, 6) k_wf_trace(DScene sc, WfBuf b, int lis
         }
         const int ni = __popc(mi), nt = __popc(mt);
         if (ni >= nt) {
-            if (wi) {                                           // INNER step
+            if (wi) {                                           // INNER step: one 4-wide node
                 ++n_inner;
-                const float4 *np = reinterpret_cast<const float4 *>(nodes + cur);
-                const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
-                const int4 lk = __ldg(reinterpret_cast<const int4 *>(np) + 3);
-                float t0, t1;
-                const bool h0 = slab(r, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tmax, t0);
-                const bool h1 = slab(r, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, tmax, t1);
-                if (h0 && h1) {
-                    // closest: nearer child first.  light (all hits): left first — the reference's
-                    // visit order (bvh.rs:188-210), which fixes the order of the pdf sum
-                    const bool first0 = closest ? (t0 <= t1) : true;
-                    stk_n[sp] = first0 ? lk.y : lk.x;
-                    stk_t[sp] = first0 ? t1 : t0;
-                    ++sp;
-                    cur = first0 ? lk.x : lk.y;
-                    cur_t = first0 ? t0 : t1;
-                    WF_ENTER_LEAF()
-                } else if (h0) {
-                    cur = lk.x; cur_t = t0;
-                    WF_ENTER_LEAF()
-                } else if (h1) {
-                    cur = lk.y; cur_t = t1;
+                Visit4 v = visit4(nodes + cur, r, tmax);
+                if (closest) {
+                    sort4(v);                                   // nearest child first
+                } else {
+                    // light search (all hits): children in the reference's left-to-right order
+                    // (bvh.rs:188-210), which fixes the order of the pdf sum; entry distance 0
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) v.key[k] = v.key[k] < inf ? (float)k : inf;
+                    sort4(v);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) v.key[k] = v.key[k] < inf ? 0.0f : inf;
+                }
+                if (v.key[3] < inf) { stk_n[sp] = v.child[3]; stk_t[sp] = v.key[3]; ++sp; }
+                if (v.key[2] < inf) { stk_n[sp] = v.child[2]; stk_t[sp] = v.key[2]; ++sp; }
+                if (v.key[1] < inf) { stk_n[sp] = v.child[1]; stk_t[sp] = v.key[1]; ++sp; }
+                if (v.key[0] < inf) {
+                    cur = v.child[0]; cur_t = v.key[0];
                     WF_ENTER_LEAF()
                 } else {
                     WF_POP()
