@@ -349,6 +349,66 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
     }
 }
 
+// ---- tail ----------------------------------------------------------------------------------------
+// When few slots are left alive an iteration costs the latency of its single slowest ray, not
+// its throughput.  The remaining slots are then finished by one kernel in which every thread
+// runs its pixel's paths to completion (the megakernel loop, same arithmetic), starting from the
+// ray the last shade step handed over.
+__global__ void __launch_bounds__(128) k_wf_finish(DScene sc, WfBuf b, int list, uint32_t sample_begin, uint32_t sample_count,
+                                                   unsigned long long seed, double *__restrict__ accum, DCounters *ctr) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_live = b.n_live[list], N = b.n;
+    Cnt c;
+    if (i < n_live) {
+        const uint32_t slot = b.live[list][i];
+        const uint32_t flags = b.flags[slot];
+        uint32_t s = b.sample[slot], left = (flags >> 8) & 0xFFu;
+        Rng rng;
+        rng.init(seed, slot, sample_begin + s);
+        rng.block = b.rng_block[slot]; rng.s0 = b.rng_s0[slot]; rng.s1 = b.rng_s1[slot];
+        rng.have = (flags & kFlagRngHave) != 0;
+        d3 o = ld_soa(b.ro, N, slot), d = ld_soa(b.rd, N, slot), T = ld_soa(b.T, N, slot), L = ld_soa(b.L, N, slot);
+        const size_t p = (size_t)slot * 3;
+        d3 sum = mk3(accum[p], accum[p + 1], accum[p + 2]);
+        bool alive = (flags & kFlagAlive) != 0;
+        if (alive && (flags & kFlagPendLight)) {        // Light::pdf of the ray in flight (already counted)
+            Pending pd;
+            pd.v = ld_soa(b.pv, N, slot);
+            pd.cos_pdf = b.pcos[slot];
+            Cnt scratch;
+            if (!apply_pending(pd, light_pdf_fast(sc, o, d, scratch), T)) { sum = add(sum, L); alive = false; ++s; }
+        }
+        for (;;) {
+            if (!alive) {
+                if (s >= sample_count) break;
+                rng.init(seed, slot, sample_begin + s);
+                const double jx = rng.range(0.0, 1.0), jy = rng.range(0.0, 1.0);
+                camera_ray(sc.cam, slot % sc.width, slot / sc.width, jx, jy, o, d);
+                ++c.paths;
+                T = mk3(1.0, 1.0, 1.0);
+                L = mk3(0.0, 0.0, 0.0);
+                left = sc.ray_depth;
+                alive = true;
+            }
+            bool more = false;
+            if (left > 0) {
+                more = bounce<FastPolicy>(sc, o, d, T, L, rng, c);
+                --left;
+            }
+            if (!more || left == 0) {
+                sum = add(sum, L);
+                alive = false;
+                ++s;
+            }
+        }
+        accum[p] = sum.x; accum[p + 1] = sum.y; accum[p + 2] = sum.z;
+        b.flags[slot] = 0;
+        b.sample[slot] = s;
+    }
+    __syncwarp();
+    flush_counters_wf(c, ctr);
+}
+
 // ---- host loop -----------------------------------------------------------------------------------
 size_t wf_bytes_per_slot() { return 15 * 8 + 3 * 8 + 7 * 4 + kWfCand * 12 + 2 * 4; }
 int wf_trace_blocks(int device) {
@@ -366,6 +426,7 @@ cudaError_t launch_render_wavefront(cudaStream_t st, const DScene &sc, uint32_t 
     const uint64_t max_iters = (uint64_t)sample_count * (sc.ray_depth ? sc.ray_depth : 1) + 2;
     int cur = 0;
     bool poll_pending = false;
+    const uint32_t tail_threshold = b.n / 16 + 1;       // below this many live slots, finish in one kernel
     for (uint64_t it = 0; it < max_iters; ++it) {
         // next list starts empty, trace cursor at 0
         cudaMemsetAsync(&b.n_live[cur ^ 1], 0, sizeof(uint32_t), st);
@@ -374,11 +435,17 @@ cudaError_t launch_render_wavefront(cudaStream_t st, const DScene &sc, uint32_t 
         k_wf_trace<<<trace_blocks, 128, 0, st>>>(sc, b, cur ^ 1, ctr);
         *launches += 2;
         cur ^= 1;
-        if ((it & 7) == 7) {                    // poll the live count without stalling the stream
+        if ((it & 3) == 3) {                    // poll the live count without stalling the stream
             if (poll_pending) {
                 cudaError_t e = cudaEventSynchronize(ev);
                 if (e != cudaSuccess) return e;
                 if (*host_live == 0) break;
+                if (*host_live < tail_threshold) {
+                    // few slots left: finish them in one kernel (the count can only have shrunk since)
+                    k_wf_finish<<<(tail_threshold + 127) / 128, 128, 0, st>>>(sc, b, cur, sample_begin, sample_count, seed, accum, ctr);
+                    ++*launches;
+                    break;
+                }
             }
             cudaMemcpyAsync((void *)host_live, &b.n_live[cur], sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
             cudaEventRecord(ev, st);
