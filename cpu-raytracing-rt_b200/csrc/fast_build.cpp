@@ -13,6 +13,13 @@
 #include <limits>
 #include <stdexcept>
 
+// Longest run of triangles kept as one leaf of the culling hierarchy (<= 8, the leaf encoding).
+// The reference's leaves hold up to 4 triangles (or more after a SameNode decision); shorter
+// leaves here mean the cheap 4-wide box test culls single triangles before the fp32 pre-test.
+#ifndef RT_MAX_LEAF
+#define RT_MAX_LEAF 2
+#endif
+
 namespace rt {
 namespace {
 
@@ -56,7 +63,7 @@ struct Builder {
         if (h.left == RT_NO_CHILD) return Item{false, 0, h.first, h.count, h.box};
         return Item{true, n, 0, 0, h.box};
     }
-    static bool expandable(const Item &it) { return it.is_node || it.count > 8; }
+    static bool expandable(const Item &it) { return it.is_node || it.count > RT_MAX_LEAF; }
     // children of an item, in the reference's left-to-right order
     void split(const Item &it, Item &a, Item &b) const {
         if (it.is_node) {
