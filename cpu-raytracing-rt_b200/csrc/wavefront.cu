@@ -312,28 +312,30 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
                     WF_POP()
                 }
             }
-        } else if (wt) {                                        // TRIANGLE step
-            ++n_tri;
-            float tlo, thi;
-            const int cls = tri_classify(tris + tri_i, xtris + tri_i, r, o, dd, cur_t, dl1g, tmax, tlo, thi);
-            if (cls != 0) {
-                ++n_cand;
-                if (closest) {
-                    if (cls == 2) tmax = fminf(tmax, thi);
-                    if (nc < (uint32_t)kWfCand) {
-                        b.cand[nc * N + slot] = tri_i;
-                        b.cand_t[nc * N + slot] = tlo;
-                        ++nc;
+        } else if (wt) {                                        // TRIANGLE step: the whole (<= 2 triangle) leaf
+            do {
+                ++n_tri;
+                float tlo, thi;
+                const int cls = tri_classify(tris + tri_i, xtris + tri_i, r, o, dd, cur_t, dl1g, tmax, tlo, thi);
+                if (cls != 0) {
+                    ++n_cand;
+                    if (closest) {
+                        if (cls == 2) tmax = fminf(tmax, thi);
+                        if (nc < (uint32_t)kWfCand) {
+                            b.cand[nc * N + slot] = tri_i;
+                            b.cand_t[nc * N + slot] = tlo;
+                            ++nc;
+                        } else {
+                            over |= kOverflowClosest;           // rare: the shade kernel redoes this search
+                            ++n_over;
+                        }
                     } else {
-                        over |= kOverflowClosest;               // rare: the shade kernel redoes this search
-                        ++n_over;
+                        if (nl < (uint32_t)kWfCand) { b.lcand[nl * N + slot] = tri_i; ++nl; }
+                        else { over |= kOverflowLight; ++n_over; }
                     }
-                } else {
-                    if (nl < (uint32_t)kWfCand) { b.lcand[nl * N + slot] = tri_i; ++nl; }
-                    else { over |= kOverflowLight; ++n_over; }
                 }
-            }
-            if (++tri_i == tri_end) WF_POP()
+            } while (++tri_i != tri_end);
+            WF_POP()
         }
     }
 #undef WF_ENTER_LEAF
