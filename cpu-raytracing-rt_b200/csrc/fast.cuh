@@ -300,6 +300,9 @@ RT_D float shapes_tmax(const ShapeBest &sb, bool &skip) {
     skip = sb.has && sb.t != sb.t;
     return (sb.has && !skip) ? up_f32(sb.t) : __int_as_float(0x7F800000);
 }
+// SHAPES = false compiles the analytic-primitive code out (glTF scenes have none): the wavefront
+// shade kernel is instruction-cache bound, every kilobyte of cold code in it costs.
+template <bool SHAPES = true>
 RT_D SceneHit finish_hit(const DScene &sc, d3 o, d3 d, const ShapeBest &sb, const FBest &fb) {
     SceneHit h;
     h.kind = sb.kind; h.prim = sb.prim; h.material = 0; h.t = sb.t; h.inside = false;
@@ -316,7 +319,7 @@ RT_D SceneHit finish_hit(const DScene &sc, d3 o, d3 d, const ShapeBest &sb, cons
         h.ng = unit3(qrot(ident, ng));
         h.ns = unit3(qrot(ident, ns));
         h.material = __ldg(&sc.tri_i[h.prim].material);
-    } else {
+    } else if (SHAPES) {
         const DShape *sp = h.kind == 0 ? sc.planes + h.prim : (h.kind == 1 ? sc.box_prims + h.prim : sc.ell_prims + h.prim);
         finish_shape_hit(sp, o, d, h);
     }

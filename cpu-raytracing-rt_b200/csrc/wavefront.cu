@@ -59,6 +59,7 @@ __global__ void k_wf_init(WfBuf b) {
 }
 
 // ---- shade -------------------------------------------------------------------------------------
+template <bool SHAPES>
 __global__ void __launch_bounds__(128) k_wf_shade(DScene sc, WfBuf b, int cur_list, uint32_t sample_begin, uint32_t sample_count,
                                                   unsigned long long seed, double *__restrict__ accum, DCounters *ctr) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(128) k_wf_shade(DScene sc, WfBuf b, int cur_li
                             if (b.cand_t[k * N + slot] <= tmax) confirm(sc.tri_i, o, d, b.cand[k * N + slot], fb, tmax);
                     }
                 }
-                const SceneHit h = finish_hit(sc, o, d, sb, fb);
+                const SceneHit h = finish_hit<SHAPES>(sc, o, d, sb, fb);
                 const int r = shade_hit(sc, h, o, d, T, L, rng, pd);
                 --left;
                 if (r == kPathEnd) {
@@ -148,12 +149,17 @@ __global__ void __launch_bounds__(128) k_wf_shade(DScene sc, WfBuf b, int cur_li
             }
         }
         if (alive) {                                    // hand the ray to the trace kernel
-            const ShapeBest sb = shapes_closest(sc, o, d, c);
-            b.sh_id[slot] = sb.has ? (((uint32_t)sb.kind << 28) | sb.prim) : kNoShape;
-            b.sh_t[slot] = sb.t;
+            if (SHAPES) {
+                const ShapeBest sb = shapes_closest(sc, o, d, c);
+                b.sh_id[slot] = sb.has ? (((uint32_t)sb.kind << 28) | sb.prim) : kNoShape;
+                b.sh_t[slot] = sb.t;
+            } else {
+                b.sh_id[slot] = kNoShape;
+                b.sh_t[slot] = 0.0;
+            }
             if (pend_light) {
                 ++c.lray;
-                b.pimp[slot] = light_shapes_impact(sc, o, d, c);
+                b.pimp[slot] = SHAPES ? light_shapes_impact(sc, o, d, c) : 0.0;
                 st_soa(b.pv, N, slot, pd.v);
                 b.pcos[slot] = pd.cos_pdf;
             }
@@ -428,12 +434,15 @@ cudaError_t launch_render_wavefront(cudaStream_t st, const DScene &sc, uint32_t 
     const uint64_t max_iters = (uint64_t)sample_count * (sc.ray_depth ? sc.ray_depth : 1) + 2;
     int cur = 0;
     bool poll_pending = false;
+    // scenes without planes / boxes / ellipsoids (every glTF scene) run the kernel compiled without them
+    const bool shapes = sc.n_planes || sc.boxes.n_prims || sc.ellipsoids.n_prims || sc.lboxes.n_prims || sc.lellipsoids.n_prims;
     const uint32_t tail_threshold = b.n / 16 + 1;       // below this many live slots, finish in one kernel
     for (uint64_t it = 0; it < max_iters; ++it) {
         // next list starts empty, trace cursor at 0
         cudaMemsetAsync(&b.n_live[cur ^ 1], 0, sizeof(uint32_t), st);
         cudaMemsetAsync(b.cursor, 0, sizeof(uint32_t), st);
-        k_wf_shade<<<blocks, 128, 0, st>>>(sc, b, cur, sample_begin, sample_count, seed, accum, ctr);
+        if (shapes) k_wf_shade<true><<<blocks, 128, 0, st>>>(sc, b, cur, sample_begin, sample_count, seed, accum, ctr);
+        else k_wf_shade<false><<<blocks, 128, 0, st>>>(sc, b, cur, sample_begin, sample_count, seed, accum, ctr);
         k_wf_trace<<<trace_blocks, 128, 0, st>>>(sc, b, cur ^ 1, ctr);
         *launches += 2;
         cur ^= 1;
