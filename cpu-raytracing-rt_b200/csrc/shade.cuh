@@ -107,14 +107,16 @@ RT_D d3 uniform_on_box(d3 s, Rng &rng) {                    // :142-157
     else p = mk3(u1, u2, sign);
     return mul3(p, s);
 }
+// SHAPES = false: the caller guarantees there are no box / ellipsoid lights (their code is dropped)
+template <bool SHAPES = true>
 RT_D d3 light_sample(const DScene &sc, d3 pos, Rng &rng) {  // :101-130
     const uint32_t index = (uint32_t)rng.range_usize(sc.n_lights);
-    const uint32_t nb = sc.lboxes.n_prims, ne = sc.lellipsoids.n_prims;
+    const uint32_t nb = SHAPES ? sc.lboxes.n_prims : 0u, ne = SHAPES ? sc.lellipsoids.n_prims : 0u;
     d3 world;
-    if (index < nb) {
+    if (SHAPES && index < nb) {
         const ShapeRec l = load_shape(sc.lbox_prims + index);
         world = add(qrot(l.rot, uniform_on_box(l.param, rng)), l.position);
-    } else if (index < nb + ne) {
+    } else if (SHAPES && index < nb + ne) {
         const ShapeRec l = load_shape(sc.lell_prims + (index - nb));
         world = add(qrot(l.rot, mul3(uniform_on_sphere(rng), l.param)), l.position);
     } else {
@@ -155,6 +157,7 @@ struct Pending {
     double cos_pdf;     // Cosine::pdf
 };
 enum { kPathEnd = 0, kPathContinue = 1, kPathPendingPdf = 2 };
+template <bool SHAPES = true>
 RT_D int shade_hit(const DScene &sc, const SceneHit &h, d3 &o, d3 &d, d3 &T, d3 &L, Rng &rng, Pending &pd) {
     if (h.kind < 0) { L = add(L, mul3(T, sc.bg)); return kPathEnd; }         // :14
     const double2 *mp = reinterpret_cast<const double2 *>(sc.materials + h.material);
@@ -167,7 +170,7 @@ RT_D int shade_hit(const DScene &sc, const SceneHit &h, d3 &o, d3 &d, d3 &T, d3 
     if (kind == 0) {                                                        // Diffuse :16-34
         const bool mix = sc.n_lights != 0;
         d3 dir;
-        if (mix && !rng.gen_bool(0.5)) dir = light_sample(sc, pos, rng);    // Mix::sample :87-93
+        if (mix && !rng.gen_bool(0.5)) dir = light_sample<SHAPES>(sc, pos, rng);    // Mix::sample :87-93
         else dir = cosine_sample(h.ns, rng);
         const double cosv = dot3(dir, h.ns);
         if (cosv <= 0.0) return kPathEnd;                                   // :23-25

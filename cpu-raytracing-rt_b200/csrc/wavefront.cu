@@ -59,6 +59,14 @@ __global__ void k_wf_init(WfBuf b) {
 }
 
 // ---- shade -------------------------------------------------------------------------------------
+// Candidate-list overflow is rare (never on the bench scene): its full searches are kept out of
+// line so that they do not sit in the instruction stream of the hot path.
+static __device__ __noinline__ void closest_fast_cold(const FBvh f, const DTriI *tri_i, d3 o, d3 d, float tmax, FBest &best) {
+    closest_fast(f, tri_i, o, d, tmax, best);
+}
+static __device__ __noinline__ void light_hits_fast_cold(const FBvh f, const DTriI *tri_i, const DTriS *tri_s, d3 o, d3 d, double &impact) {
+    light_hits_fast(f, tri_i, tri_s, o, d, impact);
+}
 template <bool SHAPES>
 __global__ void __launch_bounds__(128) k_wf_shade(DScene sc, WfBuf b, int cur_list, uint32_t sample_begin, uint32_t sample_count,
                                                   unsigned long long seed, double *__restrict__ accum, DCounters *ctr) {
@@ -88,7 +96,7 @@ __global__ void __launch_bounds__(128) k_wf_shade(DScene sc, WfBuf b, int cur_li
             if (flags & kFlagPendLight) {               // finish the previous diffuse bounce: Light::pdf of THIS ray
                 double impact = b.pimp[slot];
                 if (nc_all & kOverflowLight) {
-                    light_hits_fast(sc.fltris, sc.ltri_i, sc.ltri_s, o, d, impact);
+                    light_hits_fast_cold(sc.fltris, sc.ltri_i, sc.ltri_s, o, d, impact);
                 } else {
                     const uint32_t nl = (nc_all >> 8) & 0xFFu;
                     for (uint32_t k = 0; k < nl; ++k) light_confirm(sc.ltri_i, sc.ltri_s, o, d, b.lcand[k * N + slot], impact);
@@ -108,7 +116,7 @@ __global__ void __launch_bounds__(128) k_wf_shade(DScene sc, WfBuf b, int cur_li
                 float tmax = shapes_tmax(sb, skip);
                 if (!skip) {
                     if (nc_all & kOverflowClosest) {
-                        closest_fast(sc.ftris, sc.tri_i, o, d, tmax, fb);
+                        closest_fast_cold(sc.ftris, sc.tri_i, o, d, tmax, fb);
                     } else {
                         const uint32_t nc = nc_all & 0xFFu;
                         for (uint32_t k = 0; k < nc; ++k)
@@ -116,7 +124,7 @@ __global__ void __launch_bounds__(128) k_wf_shade(DScene sc, WfBuf b, int cur_li
                     }
                 }
                 const SceneHit h = finish_hit<SHAPES>(sc, o, d, sb, fb);
-                const int r = shade_hit(sc, h, o, d, T, L, rng, pd);
+                const int r = shade_hit<SHAPES>(sc, h, o, d, T, L, rng, pd);
                 --left;
                 if (r == kPathEnd) {
                     ended = true;
