@@ -494,6 +494,7 @@ int rt_upload_scene(rt_ctx *ctx, const rt_scene *scene) {
             CK(ctx, upload(ctx, im.tris[k].fh.tris, &fb[k]->tris));
             fb[k]->root = im.tris[k].fh.root;
             fb[k]->depth = im.tris[k].fh.depth;
+            fb[k]->top = im.tris[k].fh.top;
         }
         CK(ctx, upload(ctx, im.mats, &d.materials));
         d.n_lights = (uint32_t)(s.light_boxes.prims.size() + s.light_ellipsoids.prims.size() + s.light_tris.prims.size());

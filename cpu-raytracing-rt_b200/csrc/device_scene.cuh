@@ -76,6 +76,7 @@ struct __align__(16) FTri {
 static_assert(sizeof(FTri) == 48, "FTri must be 48 bytes");
 
 constexpr int32_t kFastEmpty = INT32_MIN;   // FBvh::root of a hierarchy without primitives
+constexpr uint32_t kFastTopNodes = 85;      // 1 + 4 + 16 + 64: the levels staged in shared memory (10.6 KB)
 
 struct DBvh {
     const DNode *nodes;
@@ -87,6 +88,7 @@ struct FBvh {
     const FTri *tris;
     int32_t root;                       // >= 0 inner node, < 0 leaf code, kFastEmpty: no primitives
     uint32_t depth;                     // max number of simultaneously deferred children
+    uint32_t top, _pad;                 // nodes [0, top) = top levels, breadth-first (shared-memory staging)
 };
 
 struct DCamera {                        // camera.rs:6-15

@@ -67,12 +67,22 @@ struct Visit4 {
     float key[4];
     int32_t child[4];
 };
+// GENERIC = true loads through a generic pointer (the node may live in shared memory).
+template <bool GENERIC = false>
 RT_D Visit4 visit4(const FNode *node, const FRay &r, float tmax) {
     const float4 *p = reinterpret_cast<const float4 *>(node);
     // vectors 0..2 = lo.x lo.y lo.z, 3..5 = hi.x hi.y hi.z of the four children
-    const float4 ax = __ldg(p + 0 + 3 * r.sx), ay = __ldg(p + 1 + 3 * r.sy), az = __ldg(p + 2 + 3 * r.sz);
-    const float4 bx = __ldg(p + 3 - 3 * r.sx), by = __ldg(p + 4 - 3 * r.sy), bz = __ldg(p + 5 - 3 * r.sz);
-    const int4 lk = __ldg(reinterpret_cast<const int4 *>(p) + 6);
+    float4 ax, ay, az, bx, by, bz;
+    int4 lk;
+    if (GENERIC) {
+        ax = p[0 + 3 * r.sx]; ay = p[1 + 3 * r.sy]; az = p[2 + 3 * r.sz];
+        bx = p[3 - 3 * r.sx]; by = p[4 - 3 * r.sy]; bz = p[5 - 3 * r.sz];
+        lk = reinterpret_cast<const int4 *>(p)[6];
+    } else {
+        ax = __ldg(p + 0 + 3 * r.sx); ay = __ldg(p + 1 + 3 * r.sy); az = __ldg(p + 2 + 3 * r.sz);
+        bx = __ldg(p + 3 - 3 * r.sx); by = __ldg(p + 4 - 3 * r.sy); bz = __ldg(p + 5 - 3 * r.sz);
+        lk = __ldg(reinterpret_cast<const int4 *>(p) + 6);
+    }
     const float inf = __int_as_float(0x7F800000);
     Visit4 v;
 #define RT_SLAB(K, C)                                                                                          \

@@ -144,6 +144,35 @@ void build_fast_hierarchy(const HostBvh<HostTri> &bvh, FastHierarchy &out) {
         out.root = ~(int32_t)((root.first << 3) | (root.count - 1));
     }
     out.depth = b.max_stack;
+    // Put the top of the tree first, in breadth-first order, so that a kernel can stage nodes
+    // [0, top) in shared memory with one contiguous copy.  The rest keeps its depth-first order.
+    if (out.root >= 0) {
+        const size_t n = out.nodes.size();
+        const size_t want = std::min<size_t>(n, kFastTopNodes);
+        std::vector<int32_t> bfs;
+        bfs.reserve(want);
+        bfs.push_back(out.root);
+        for (size_t head = 0; head < bfs.size() && bfs.size() < want; ++head)
+            for (int k = 0; k < 4 && bfs.size() < want; ++k) {
+                const int32_t c = out.nodes[bfs[head]].child[k];
+                if (c >= 0) bfs.push_back(c);
+            }
+        std::vector<int32_t> new_index(n, -1);
+        for (size_t i = 0; i < bfs.size(); ++i) new_index[bfs[i]] = (int32_t)i;
+        int32_t next = (int32_t)bfs.size();
+        for (size_t i = 0; i < n; ++i)
+            if (new_index[i] < 0) new_index[i] = next++;
+        std::vector<FNode> moved(n);
+        for (size_t i = 0; i < n; ++i) {
+            FNode nd = out.nodes[i];
+            for (int k = 0; k < 4; ++k)
+                if (nd.child[k] >= 0) nd.child[k] = new_index[nd.child[k]];
+            moved[new_index[i]] = nd;
+        }
+        out.nodes.swap(moved);
+        out.root = new_index[out.root];
+        out.top = (uint32_t)bfs.size();
+    }
 }
 
 }  // namespace rt

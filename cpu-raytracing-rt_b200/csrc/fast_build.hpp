@@ -12,6 +12,7 @@ struct FastHierarchy {
     std::vector<FTri> tris;
     int32_t root = kFastEmpty;
     uint32_t depth = 0;
+    uint32_t top = 0;                   // nodes [0, top) are the top levels in breadth-first order
 };
 void build_fast_hierarchy(const HostBvh<HostTri> &bvh, FastHierarchy &out);
 

@@ -203,6 +203,9 @@ __global__ void __launch_bounds__(128) k_wf_shade(DScene sc, WfBuf b, int cur_li
 // finished lane is refilled from the live list as soon as enough lanes are idle — no lane waits
 // for the slowest ray of its warp.  The closest-hit search of the scene hierarchy and the all-hits
 // search of the light hierarchy use the same two steps with per-lane node / triangle pointers.
+#ifndef WF_SMEM_TOP
+#define WF_SMEM_TOP 0      // measured on B200 (C3): 947 Mseg/s with staging vs 1015 without — L1 hits cost the same as shared memory
+#endif
 #ifndef WF_REFILL
 #define WF_REFILL 8
 #endif
@@ -216,6 +219,14 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
     const uint32_t *__restrict__ live = b.live[list];
     const int lane = threadIdx.x & 31;
     const float inf = __int_as_float(0x7F800000);
+#if WF_SMEM_TOP
+    // shared-memory staging of the top levels of the scene hierarchy (every ray starts there):
+    // nodes [0, top) are its first levels in breadth-first order, one contiguous copy per block
+    __shared__ float4 s_top[kFastTopNodes * 8];
+    const uint32_t top_n = sc.ftris.root >= 0 ? (sc.ftris.top < kFastTopNodes ? sc.ftris.top : kFastTopNodes) : 0u;
+    for (uint32_t k = threadIdx.x; k < top_n * 8; k += blockDim.x) s_top[k] = __ldg(reinterpret_cast<const float4 *>(sc.ftris.nodes) + k);
+    __syncthreads();
+#endif
     bool has = false, drained = false, closest = true, want_light = false;
     uint32_t slot = 0, nc = 0, nl = 0, over = 0, tri_i = 0, tri_end = 0;
     uint32_t n_inner = 0, n_tri = 0, n_cand = 0, n_over = 0;
@@ -304,7 +315,12 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
         if (ni >= nt) {
             if (wi) {                                           // INNER step: one 4-wide node
                 ++n_inner;
+#if WF_SMEM_TOP
+                const FNode *np = (closest && (uint32_t)cur < top_n) ? reinterpret_cast<const FNode *>(s_top) + cur : nodes + cur;
+                Visit4 v = visit4<true>(np, r, tmax);
+#else
                 Visit4 v = visit4(nodes + cur, r, tmax);
+#endif
                 if (closest) {
                     sort4(v);                                   // nearest child first
                 } else {
