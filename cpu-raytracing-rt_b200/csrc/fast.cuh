@@ -14,8 +14,9 @@
 //   * every surviving candidate runs tri_exact (the reference's own arithmetic) and only its
 //     f64 (t, u, v) are ever used.  Results are therefore the EXACT-mode ones (ids, t, normals,
 //     light PDFs), which tests/test_gpu_parity.py::test_fast_mode_equals_exact_mode asserts bitwise.
-// Differences from EXACT by construction: equal-t ties between two triangles keep the first one
-// in FAST visit order, and rays whose hits lie beyond t ~ 1e9 are out of range of the fp32 slabs.
+// Differences from EXACT by construction: equal-t ties between triangles of DIFFERENT leaves go to
+// the lowest primitive index (the reference keeps the first one in its visit order), and rays whose
+// hits lie beyond t ~ 1e9 are out of range of the fp32 slabs.
 #pragma once
 #include "shade.cuh"
 
@@ -201,7 +202,10 @@ struct FBest {
 RT_D void confirm(const DTriI *tri_i, d3 o, d3 d, uint32_t prim, FBest &best, float &tmax) {
     double t, u, v;
     if (!tri_exact(tri_i + prim, o, d, t, u, v)) return;
-    if (!best.has || t < best.t) {
+    // equal distances: the lowest primitive index wins, whatever order the candidates were found
+    // in.  That is the reference's answer whenever the tied triangles share a leaf (it keeps the
+    // first one tested, bvh.rs:213-222) and it makes the result independent of the traversal order.
+    if (!best.has || t < best.t || (t == best.t && prim < best.prim)) {
         best.has = true; best.t = t; best.u = u; best.v = v; best.prim = prim;
         tmax = fminf(tmax, up_f32(t));
     }

@@ -1,0 +1,114 @@
+"""Edge cases of the hot path on the GPU, each against the oracle: empty scenes, no lights,
+depth 0/1, odd image sizes, background colour, planes hit edge-on (t = inf / NaN), a leaf far
+longer than 4 primitives (SameNode, src/bvh.rs:93-96), degenerate triangles."""
+import numpy as np
+import pytest
+
+import rtb200
+import rtb200.ctypes_types as T
+from rtb200.scene_desc import RawScene
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = rtb200.Context(0)
+    yield c
+    c.close()
+
+
+def _check(orc, ctx, raw, spp, wavefront=True):
+    prod, oracle = rtb200.Scene.from_raw(raw), orc.OracleScene(raw)
+    ctx.upload(prod)
+    want, oc = oracle.render_accum(0, spp, 99)
+    ctx.reset_counters()
+    ctx.render_accum(0, spp, 99, T.MODE_EXACT, clear=True)
+    exact, ec = ctx.accum(), ctx.counters()
+    for k in ("segments", "light_pdf_rays", "paths", "aabb_tests", "prim_tests"):
+        assert ec[k] == oc[k], k
+    ok = np.isfinite(want)
+    assert np.array_equal(np.isfinite(exact), ok)
+    err = np.abs(exact[ok] - want[ok]) / np.maximum(np.abs(want[ok]), 1e-300)
+    err[exact[ok] == want[ok]] = 0
+    assert err.size == 0 or err.max() <= 1e-9
+    ctx.render_accum(0, spp, 99, T.MODE_FAST, clear=True)
+    assert ctx.accum().tobytes() == exact.tobytes()
+    if wavefront:
+        ctx.render_accum(0, spp, 99, T.MODE_FAST, T.SCHED_WAVEFRONT, clear=True)
+        assert ctx.accum().tobytes() == exact.tobytes()
+    g_hits, _ = ctx.trace_primary(0.5, 0.5, T.MODE_FAST)
+    c_hits, _, _ = oracle.trace_primary(0.5, 0.5)
+    assert np.array_equal(g_hits["kind"], c_hits["kind"]) and np.array_equal(g_hits["prim"], c_hits["prim"])
+    return want
+
+
+def test_empty_scene_returns_background(orc, ctx):
+    raw = RawScene(width=13, height=7, samples=2, ray_depth=3, bg_color=(0.25, 0.5, 0.75))
+    want = _check(orc, ctx, raw, 2)
+    assert np.allclose(want, np.array([0.5, 1.0, 1.5]))
+
+
+def test_depth_zero_and_one(orc, ctx):
+    for depth in (0, 1):
+        raw = RawScene(width=9, height=5, samples=3, ray_depth=depth, bg_color=(1.0, 1.0, 1.0), tri_mode=T.TRI_MODEL)
+        raw.materials = [{"kind": T.MAT_DIFFUSE, "color": (0.5, 0.5, 0.5), "emission": (2.0, 0.0, 0.0)}]
+        raw.shapes = [{"type": T.SHAPE_ELLIPSOID, "material": 0, "param": (0.5, 0.4, 0.3), "position": (0.0, 0.0, 2.0)}]
+        want = _check(orc, ctx, raw, 3)
+        if depth == 0:
+            assert want.sum() == 0.0
+
+
+def test_no_lights_uses_cosine_sampler_only(orc, ctx):
+    rng = np.random.default_rng(3)
+    raw = RawScene(width=24, height=16, samples=3, ray_depth=5, bg_color=(0.6, 0.7, 0.9), cam_position=(0.0, 0.5, -3.0))
+    raw.materials = [{"kind": T.MAT_DIFFUSE, "color": (0.8, 0.4, 0.2)}, {"kind": T.MAT_METALLIC, "color": (0.9, 0.9, 0.9)},
+                     {"kind": T.MAT_DIELECTRIC, "ior": 1.33, "color": (0.9, 1.0, 0.9)}]
+    c = rng.uniform(-1.5, 1.5, (300, 1, 3)) + np.array([0.0, 0.0, 2.0])
+    raw.tri_pos = (c + rng.normal(scale=0.35, size=(300, 3, 3))).reshape(300, 9)
+    raw.tri_mat = rng.integers(0, 3, 300).astype(np.uint32)
+    raw.shapes = [{"type": T.SHAPE_PLANE, "material": 0, "param": (0.0, 2.0, 0.0), "position": (0.0, -1.0, 0.0)}]
+    _check(orc, ctx, raw, 3)
+
+
+def test_plane_seen_edge_on_and_axis_parallel_rays(orc, ctx):
+    """Camera in the plane of a PLANE looking along it: n.d = 0 gives t = NaN / +-inf, which the
+    reference reports as a hit candidate and then drops (plane.rs:12-14, intersections.rs:56)."""
+    raw = RawScene(width=8, height=8, samples=2, ray_depth=4, bg_color=(0.1, 0.2, 0.3), cam_position=(0.0, 0.0, 0.0),
+                   fov=0.5, tri_mode=T.TRI_MODEL)
+    raw.materials = [{"kind": T.MAT_DIFFUSE, "color": (0.7, 0.7, 0.7)}, {"kind": T.MAT_DIFFUSE, "emission": (3.0, 3.0, 3.0), "color": (0.5, 0.5, 0.5)}]
+    raw.shapes = [{"type": T.SHAPE_PLANE, "material": 0, "param": (0.0, 1.0, 0.0), "position": (0.0, 0.0, 0.0)},
+                  {"type": T.SHAPE_BOX, "material": 1, "param": (0.5, 0.5, 0.5), "position": (0.0, 0.0, 4.0)},
+                  {"type": T.SHAPE_BOX, "material": 0, "param": (0.3, 0.3, 0.3), "position": (1.5, 0.3, 4.0), "rotation": (0.0, 0.3826834323650898, 0.0, 0.9238795325112867)}]
+    prod, oracle = rtb200.Scene.from_raw(raw), orc.OracleScene(raw)
+    ctx.upload(prod)
+    o = np.zeros((6, 3))
+    d = np.array([[0, 0, 1.0], [1.0, 0, 0], [0, 1.0, 0], [0, -1.0, 0], [0, 0, -1.0], [1.0, 0, 1.0]])
+    for mode in (T.MODE_EXACT, T.MODE_FAST):
+        g = ctx.trace_rays(o, d, mode)
+        c, _ = oracle.trace_rays(o, d)
+        assert np.array_equal(g["kind"], c["kind"]) and np.array_equal(g["prim"], c["prim"])
+        hit = c["kind"] >= 0
+        assert g["t"][hit].tobytes() == c["t"][hit].tobytes()
+    _check(orc, ctx, raw, 2)
+
+
+def test_long_leaf_and_degenerate_triangles(orc, ctx):
+    """40 coincident triangles cannot be split by SAH -> one reference leaf of 40 primitives
+    (src/bvh.rs:93-96), which the fp32 hierarchy must split into <= 8-triangle runs; plus zero-area
+    and needle triangles (|det| < 1e-11 rejects, triangle.rs:51)."""
+    base = np.array([-1.0, -1.0, 3.0, 1.0, -1.0, 3.0, 0.0, 1.0, 3.0])
+    tris = [base] * 40
+    tris.append(np.array([0.0, 0.0, 2.0, 0.0, 0.0, 2.0, 0.0, 0.0, 2.0]))            # a point
+    tris.append(np.array([-2.0, 0.0, 2.5, 2.0, 0.0, 2.5, 0.0, 1e-13, 2.5]))          # a needle
+    rng = np.random.default_rng(5)
+    c = rng.uniform(-2, 2, (30, 1, 3)) + np.array([0.0, 0.0, 5.0])
+    tris += list((c + rng.normal(scale=0.5, size=(30, 3, 3))).reshape(30, 9))
+    raw = RawScene(width=20, height=12, samples=2, ray_depth=4, bg_color=(0.2, 0.2, 0.2))
+    raw.materials = [{"kind": T.MAT_DIFFUSE, "color": (0.6, 0.6, 0.6)}, {"kind": T.MAT_DIFFUSE, "color": (0.5, 0.5, 0.5), "emission": (4.0, 4.0, 4.0)}]
+    raw.tri_pos = np.array(tris)
+    raw.tri_mat = np.array([0] * 42 + [1] * 5 + [0] * 25, np.uint32)
+    prod = rtb200.Scene.from_raw(raw)
+    counts = prod.bvh(T.BVH_TRIANGLES)["count"]
+    assert counts.max() >= 40
+    _check(orc, ctx, raw, 2)
