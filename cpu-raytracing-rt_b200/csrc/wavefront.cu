@@ -238,8 +238,7 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
     const DTriI *xtris = sc.tri_i;
     int32_t cur = kFastEmpty;
     int sp = 0;
-    int32_t stk_n[kFastStack];
-    float stk_t[kFastStack];
+    uint2 stk[kFastStack];                  // (child code, entry distance bits): one 8-byte local access per push / pop
 #define WF_ENTER_LEAF()                                                                     \
     if (cur < 0 && cur != kFastEmpty) {                                                     \
         const uint32_t code_ = (uint32_t)~cur;                                              \
@@ -251,7 +250,8 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
         cur = kFastEmpty;                                                                   \
         while (sp > 0) {                                                                    \
             --sp;                                                                           \
-            if (stk_t[sp] <= tmax) { cur = stk_n[sp]; cur_t = stk_t[sp]; break; } \
+            const uint2 e_ = stk[sp];                                                       \
+            if (__uint_as_float(e_.y) <= tmax) { cur = (int32_t)e_.x; cur_t = __uint_as_float(e_.y); break; } \
         }                                                                                   \
         WF_ENTER_LEAF()                                                                     \
     }
@@ -321,22 +321,27 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
 #else
                 Visit4 v = visit4(nodes + cur, r, tmax);
 #endif
-                if (closest) {
-                    sort4(v);                                   // nearest child first
-                } else {
-                    // light search (all hits): children in the reference's left-to-right order
-                    // (bvh.rs:188-210), which fixes the order of the pdf sum; entry distance 0
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) v.key[k] = v.key[k] < inf ? (float)k : inf;
-                    sort4(v);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) v.key[k] = v.key[k] < inf ? 0.0f : inf;
-                }
-                if (v.key[3] < inf) { stk_n[sp] = v.child[3]; stk_t[sp] = v.key[3]; ++sp; }
-                if (v.key[2] < inf) { stk_n[sp] = v.child[2]; stk_t[sp] = v.key[2]; ++sp; }
-                if (v.key[1] < inf) { stk_n[sp] = v.child[1]; stk_t[sp] = v.key[1]; ++sp; }
-                if (v.key[0] < inf) {
-                    cur = v.child[0]; cur_t = v.key[0];
+                // Nearest hit child becomes `cur`; the other hit children are deferred in child
+                // order.  The child index rides in the two low mantissa bits of the (positive) entry
+                // distance — cleared bits round it DOWN, so it stays a lower bound — and an integer
+                // min picks the nearest.  The light search (all hits) uses the index alone as the
+                // key: children left to right, the reference's visit order (bvh.rs:188-210), which
+                // fixes the order of the pdf sum.
+                const uint32_t none = 0xFFFFFFFFu;
+                const uint32_t k0 = v.key[0] < inf ? ((closest ? (__float_as_uint(v.key[0]) & ~3u) : 0u) | 0u) : none;
+                const uint32_t k1 = v.key[1] < inf ? ((closest ? (__float_as_uint(v.key[1]) & ~3u) : 0u) | 1u) : none;
+                const uint32_t k2 = v.key[2] < inf ? ((closest ? (__float_as_uint(v.key[2]) & ~3u) : 0u) | 2u) : none;
+                const uint32_t k3 = v.key[3] < inf ? ((closest ? (__float_as_uint(v.key[3]) & ~3u) : 0u) | 3u) : none;
+                const uint32_t kmin = min(min(k0, k1), min(k2, k3));
+                if (kmin != none) {
+                    // deferred children are pushed right to left, so they pop left to right
+                    if (k3 != none && k3 != kmin) { stk[sp] = make_uint2((uint32_t)v.child[3], k3 & ~3u); ++sp; }
+                    if (k2 != none && k2 != kmin) { stk[sp] = make_uint2((uint32_t)v.child[2], k2 & ~3u); ++sp; }
+                    if (k1 != none && k1 != kmin) { stk[sp] = make_uint2((uint32_t)v.child[1], k1 & ~3u); ++sp; }
+                    if (k0 != none && k0 != kmin) { stk[sp] = make_uint2((uint32_t)v.child[0], k0 & ~3u); ++sp; }
+                    const uint32_t sel = kmin & 3u;
+                    cur = sel == 0u ? v.child[0] : (sel == 1u ? v.child[1] : (sel == 2u ? v.child[2] : v.child[3]));
+                    cur_t = __uint_as_float(kmin & ~3u);
                     WF_ENTER_LEAF()
                 } else {
                     WF_POP()
