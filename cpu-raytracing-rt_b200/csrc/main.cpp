@@ -2,7 +2,8 @@
 //   cpu-raytracing-rt custom <out.ppm> < scene.txt
 //   cpu-raytracing-rt glTF <in.gltf> <W> <H> <spp> <out.ppm>
 // Scene loading and the BVH build run on the host; generate_image (src/main.rs:85) runs on the GPU.
-// Extra, optional environment knobs (not in the reference): RT_SEED, RT_MODE=exact|fast, RT_DEVICE.
+// Extra, optional environment knobs (not in the reference): RT_SEED, RT_MODE=exact|fast (fast =
+// wavefront scheduler, exact = megakernel parity anchor), RT_DEVICE.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -48,7 +49,8 @@ int main(int argc, char **argv) {
     std::vector<double> rgb((size_t)info.width * info.height * 3);
     // progress lines of the reference (src/main.rs:105-110) at 5% granularity of the SAMPLE range
     rt_render_params p{};
-    p.seed = seed; p.mode = mode; p.sched = RT_SCHED_MEGAKERNEL; p.clear = 1;
+    p.seed = seed; p.mode = mode; p.clear = 1;
+    p.sched = mode == RT_MODE_FAST ? RT_SCHED_WAVEFRONT : RT_SCHED_MEGAKERNEL;
     uint32_t done = 0;
     for (int step = 1; step <= 20; ++step) {
         const uint32_t upto = (uint32_t)((uint64_t)info.samples * step / 20);
