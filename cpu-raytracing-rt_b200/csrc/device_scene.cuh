@@ -3,8 +3,8 @@
 // EXACT mode reads the reference's own hierarchy (reference src/bvh.rs:49-54) flattened to
 // 64-byte nodes: pre-order, left child = self + 1 (src/bvh.rs:104-108), so only `right` is
 // stored.  Every record is a multiple of 16 bytes and is fetched with 16-byte vector loads.
-// FAST mode reads a derived fp32 structure (two child boxes per 64-byte node, rounded outward)
-// and confirms candidates against the same f64 triangle records.
+// FAST mode reads a derived fp32 structure (4-wide nodes of 128 bytes, child boxes rounded
+// outward) and confirms candidates against the same f64 triangle records.
 #pragma once
 #include <vector_types.h>
 

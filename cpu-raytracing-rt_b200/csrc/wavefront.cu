@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(128) k_wf_shade(DScene sc, WfBuf b, int cur_li
 
 // ---- trace -------------------------------------------------------------------------------------
 // Warp-synchronous state machine.  A lane with a ray is in one of two states: at an INNER node
-// (one step = fetch a 128-byte 4-wide node, four slab tests, sort, descend / push / pop) or at a LEAF with
+// (one step = fetch a 128-byte 4-wide node, four slab tests, pick the nearest child, push the others) or at a LEAF with
 // triangles left (one step = one fp32 pre-test).  Every iteration the warp votes and runs the
 // step kind more lanes are waiting for, so the 32 lanes always execute the same code and a
 // finished lane is refilled from the live list as soon as enough lanes are idle — no lane waits
