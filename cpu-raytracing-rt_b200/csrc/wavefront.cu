@@ -206,11 +206,18 @@ __global__ void __launch_bounds__(128) k_wf_shade(DScene sc, WfBuf b, int cur_li
 #ifndef WF_SMEM_TOP
 #define WF_SMEM_TOP 0      // measured on B200 (C3): 947 Mseg/s with staging vs 1015 without — L1 hits cost the same as shared memory
 #endif
+#ifndef WF_COUNT
+#define WF_COUNT 0           // 1: count fp32 node visits / pre-tests / candidates / overflows (diagnostics)
+#endif
+#ifndef WF_VOTE_I
+#define WF_VOTE_I 1            // the INNER step runs when WF_VOTE_I * (#lanes at a node) >= WF_VOTE_T * (#lanes at a leaf)
+#define WF_VOTE_T 1
+#endif
 #ifndef WF_REFILL
 #define WF_REFILL 8
 #endif
 #ifndef WF_TRACE_BLOCKS
-#define WF_TRACE_BLOCKS 6
+#define WF_TRACE_BLOCKS 7
 #endif
 constexpr int kRefillLanes = WF_REFILL;  // refill once this many lanes are idle
 
@@ -229,13 +236,18 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
 #endif
     bool has = false, drained = false, closest = true, want_light = false;
     uint32_t slot = 0, nc = 0, nl = 0, over = 0, tri_i = 0, tri_end = 0;
+#if WF_COUNT
     uint32_t n_inner = 0, n_tri = 0, n_cand = 0, n_over = 0;
+#define WF_INC(X) ++X;
+#else
+#define WF_INC(X)
+#endif
     FRay r = {};
-    d3 o = mk3(0.0, 0.0, 0.0), dd = o;
+    // the f64 origin and direction are only needed by the triangle pre-test: they live in shared
+    // memory (48 B per thread) instead of 12 registers, which buys one more resident block per SM
+    __shared__ double s_ray[6][128];
+    double *const my_ray = &s_ray[0][threadIdx.x];
     float dl1g = 0.0f, tmax = inf, cur_t = 0.0f;     // cur_t: conservative entry distance of `cur`
-    const FNode *nodes = sc.ftris.nodes;
-    const FTri *tris = sc.ftris.tris;
-    const DTriI *xtris = sc.tri_i;
     int32_t cur = kFastEmpty;
     int sp = 0;
     uint2 stk[kFastStack];                  // (child code, entry distance bits): one 8-byte local access per push / pop
@@ -266,7 +278,6 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
             if (has && cur == kFastEmpty) {
                 if (closest && want_light && sc.fltris.root != kFastEmpty) {       // start the light search
                     closest = false;
-                    nodes = sc.fltris.nodes; tris = sc.fltris.tris; xtris = sc.ltri_i;
                     tmax = inf; sp = 0;
                     cur = sc.fltris.root; cur_t = 0.0f;
                     WF_ENTER_LEAF()
@@ -286,8 +297,9 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
                     const uint32_t idx = base + __popc(idle & ((1u << lane) - 1u));
                     if (idx < n) {
                         slot = live[idx];
-                        o = ld_soa(b.ro, N, slot);
-                        dd = ld_soa(b.rd, N, slot);
+                        const d3 o = ld_soa(b.ro, N, slot), dd = ld_soa(b.rd, N, slot);
+                        my_ray[0] = o.x; my_ray[128] = o.y; my_ray[256] = o.z;
+                        my_ray[384] = dd.x; my_ray[512] = dd.y; my_ray[640] = dd.z;
                         r = make_fray(o, dd);
                         dl1g = kGamma * (fabsf(r.dx) + fabsf(r.dy) + fabsf(r.dz));
                         const uint32_t sid = b.sh_id[slot];
@@ -297,7 +309,6 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
                         want_light = (b.flags[slot] & kFlagPendLight) != 0;
                         nc = 0; nl = 0; over = 0; sp = 0;
                         closest = true;
-                        nodes = sc.ftris.nodes; tris = sc.ftris.tris; xtris = sc.tri_i;
                         cur = skip ? kFastEmpty : sc.ftris.root; cur_t = 0.0f;
                         WF_ENTER_LEAF()
                         has = true;
@@ -312,14 +323,14 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
             mt = __ballot_sync(kFull, wt);
         }
         const int ni = __popc(mi), nt = __popc(mt);
-        if (ni >= nt) {
+        if (WF_VOTE_I * ni >= WF_VOTE_T * nt) {
             if (wi) {                                           // INNER step: one 4-wide node
-                ++n_inner;
+                WF_INC(n_inner)
 #if WF_SMEM_TOP
-                const FNode *np = (closest && (uint32_t)cur < top_n) ? reinterpret_cast<const FNode *>(s_top) + cur : nodes + cur;
+                const FNode *np = (closest && (uint32_t)cur < top_n) ? reinterpret_cast<const FNode *>(s_top) + cur : (closest ? sc.ftris.nodes : sc.fltris.nodes) + cur;
                 Visit4 v = visit4<true>(np, r, tmax);
 #else
-                Visit4 v = visit4(nodes + cur, r, tmax);
+                Visit4 v = visit4((closest ? sc.ftris.nodes : sc.fltris.nodes) + cur, r, tmax);
 #endif
                 // Nearest hit child becomes `cur`; the other hit children are deferred in child
                 // order.  The child index rides in the two low mantissa bits of the (positive) entry
@@ -348,12 +359,15 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
                 }
             }
         } else if (wt) {                                        // TRIANGLE step: the whole (<= 2 triangle) leaf
+            const FTri *tris = closest ? sc.ftris.tris : sc.fltris.tris;
+            const DTriI *xtris = closest ? sc.tri_i : sc.ltri_i;
+            const d3 o = mk3(my_ray[0], my_ray[128], my_ray[256]), dd = mk3(my_ray[384], my_ray[512], my_ray[640]);
             do {
-                ++n_tri;
+                WF_INC(n_tri)
                 float tlo, thi;
                 const int cls = tri_classify(tris + tri_i, xtris + tri_i, r, o, dd, cur_t, dl1g, tmax, tlo, thi);
                 if (cls != 0) {
-                    ++n_cand;
+                    WF_INC(n_cand)
                     if (closest) {
                         if (cls == 2) tmax = fminf(tmax, thi);
                         if (nc < (uint32_t)kWfCand) {
@@ -362,11 +376,11 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
                             ++nc;
                         } else {
                             over |= kOverflowClosest;           // rare: the shade kernel redoes this search
-                            ++n_over;
+                            WF_INC(n_over)
                         }
                     } else {
                         if (nl < (uint32_t)kWfCand) { b.lcand[nl * N + slot] = tri_i; ++nl; }
-                        else { over |= kOverflowLight; ++n_over; }
+                        else { over |= kOverflowLight; WF_INC(n_over) }
                     }
                 }
             } while (++tri_i != tri_end);
@@ -375,6 +389,8 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
     }
 #undef WF_ENTER_LEAF
 #undef WF_POP
+#undef WF_INC
+#if WF_COUNT
     // diagnostics: fp32 node visits / pre-tests / candidates / overflows of this launch
     unsigned long long v[4] = {n_inner, n_tri, n_cand, n_over};
     unsigned long long *dst[4] = {&ctr->aabb_tests, &ctr->prim_tests, &ctr->light_aabb_tests, &ctr->light_prim_tests};
@@ -384,6 +400,9 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
         for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(kFull, s, off);
         if (lane == 0 && s) atomicAdd(dst[k], s);
     }
+#else
+    (void)ctr;
+#endif
 }
 
 // ---- tail ----------------------------------------------------------------------------------------
