@@ -186,3 +186,28 @@ def test_wavefront_scheduler_equals_megakernel(orc, ctx, tmp_path, kind):
     assert wc["segments"] == oc["segments"] and wc["light_pdf_rays"] == oc["light_pdf_rays"]
     with pytest.raises(rtb200.RtError):
         ctx.render_accum(0, 1, 1, T.MODE_EXACT, T.SCHED_WAVEFRONT, clear=True)
+
+
+def test_converged_image_statistical_parity(orc, ctx, tmp_path):
+    """SURVEY §8d image tolerance on C1 (Cornell box, text format): with DIFFERENT seeds on the two
+    sides (the reference itself is seeded by the OS) the converged images must agree statistically:
+    relative mean-luminance difference <= 1 % and RMSE of the tonemapped 8-bit images <= 2 x the RMSE
+    between two independent oracle runs (the noise floor)."""
+    from oracle import loaders
+    spp = 64
+    path = helpers.cornell(tmp_path, 96, 96, spp, 6, extra=False)
+    prod = rtb200.Scene.load_text(path)
+    oracle = orc.OracleScene(loaders.parse_text_scene(open(path).read()))
+    ctx.upload(prod)
+    ctx.render_accum(0, spp, 0xA11CE, T.MODE_FAST, T.SCHED_WAVEFRONT, clear=True)
+    gpu = ctx.accum()
+    cpu_b, _ = oracle.render_accum(0, spp, 0xB0B)
+    cpu_c, _ = oracle.render_accum(0, spp, 0xCAFE)
+    lum = lambda a: float((a @ np.array([0.2126, 0.7152, 0.0722])).mean())
+    assert abs(lum(gpu) - lum(cpu_b)) / lum(cpu_b) <= 0.01
+    img = lambda a: orc.to_bytes(orc.postprocess(a, spp)).astype(np.float64)
+    rmse = lambda a, b: float(np.sqrt(((img(a) - img(b)) ** 2).mean()))
+    floor = rmse(cpu_b, cpu_c)
+    assert floor > 0 and rmse(gpu, cpu_b) <= 2.0 * floor, (rmse(gpu, cpu_b), floor)
+    # and the device tonemap of the GPU image equals the oracle's tonemap of the same sums
+    np.testing.assert_allclose(ctx.postprocess(spp), orc.postprocess(gpu, spp), rtol=1e-13, atol=1e-15)
