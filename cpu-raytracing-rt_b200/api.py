@@ -17,7 +17,7 @@ _LIB = None
 
 # every symbol include/rt_b200.h declares (tests check that the library exports each of them)
 SYMBOLS = [
-    "rt_scene_build", "rt_scene_free", "rt_scene_load_text", "rt_scene_load_gltf", "rt_scene_get_info",
+    "rt_scene_build", "rt_scene_from_built", "rt_scene_free", "rt_scene_load_text", "rt_scene_load_gltf", "rt_scene_get_info",
     "rt_scene_get_bvh", "rt_scene_get_triangle", "rt_scene_get_shape", "rt_scene_get_material", "rt_save_ppm",
     "rt_device_count", "rt_create", "rt_destroy", "rt_last_error", "rt_upload_scene", "rt_scene_device_bytes", "rt_trace_rays",
     "rt_trace_primary", "rt_light_pdf", "rt_render_accum", "rt_accum_device_ptr", "rt_get_accum", "rt_set_accum",
@@ -49,6 +49,7 @@ def lib():
         L = C.CDLL(_LIB_PATH)
         vp, u32, u64, i32, dbl = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_double
         L.rt_scene_build.argtypes = [C.POINTER(T.RawScene), C.POINTER(vp)]
+        L.rt_scene_from_built.argtypes = [C.POINTER(T.BuiltScene), C.POINTER(vp)]
         L.rt_scene_free.argtypes = [vp]
         L.rt_scene_free.restype = None
         L.rt_scene_load_text.argtypes = [C.c_char_p, C.POINTER(vp)]
@@ -137,6 +138,54 @@ class Scene:
         """gltf::parse + gltf::build_scene (src/main.rs:47-66)."""
         h = C.c_void_p()
         _check(lib().rt_scene_load_gltf(os.fsencode(path), width, height, samples, C.byref(h)))
+        return cls(h)
+
+    def export_built(self):
+        """This scene as an rt_built_scene (already-built hierarchies as flat arrays) + keepalive."""
+        keep = []
+        b = T.BuiltScene()
+        i = self.info
+        b.width, b.height, b.samples, b.ray_depth = i.width, i.height, i.samples, i.ray_depth
+        for name in ("bg_color", "cam_position", "cam_right", "cam_up", "cam_forward"):
+            getattr(b, name)[:] = list(getattr(i, name))
+        b.tan_half_fov_x, b.tan_half_fov_y = i.tan_half_fov_x, i.tan_half_fov_y
+        mats = (T.Material * max(1, i.n_materials))()
+        for k in range(i.n_materials):
+            mats[k] = self.material(k)
+        planes = (T.Shape * max(1, i.n_planes))()
+        for k in range(i.n_planes):
+            planes[k] = self.shape(-1, k)[0]
+        keep += [mats, planes]
+        b.n_materials, b.n_planes, b.materials, b.planes = i.n_materials, i.n_planes, mats, planes
+        for w in range(6):
+            d = self.bvh(w)
+            keep.append(d)
+            bb = b.bvh[w]
+            bb.n_nodes, bb.n_prims = len(d["left"]), len(d["prim_order"])
+            bb.bounds = d["bounds"].ctypes.data_as(T.c_double_p)
+            for name in ("left", "right", "first", "count"):
+                setattr(bb, name, d[name].ctypes.data_as(T.c_u32_p))
+            if w in (T.BVH_TRIANGLES, T.BVH_LIGHT_TRIANGLES):
+                tri = np.zeros((max(1, bb.n_prims), 28))
+                mat = np.zeros(max(1, bb.n_prims), np.uint32)
+                for k in range(bb.n_prims):
+                    tri[k], mat[k] = self.triangle(w, k)
+                keep += [tri, mat]
+                bb.tri28, bb.tri_material = tri.ctypes.data_as(T.c_double_p), mat.ctypes.data_as(T.c_u32_p)
+            else:
+                sh = (T.Shape * max(1, bb.n_prims))()
+                boxes = np.zeros((max(1, bb.n_prims), 6))
+                for k in range(bb.n_prims):
+                    sh[k], boxes[k] = self.shape(w, k)
+                keep += [sh, boxes]
+                bb.shapes, bb.shape_aabb = sh, boxes.ctypes.data_as(T.c_double_p)
+        return b, keep
+
+    @classmethod
+    def from_built(cls, built):
+        """A scene whose hierarchies the caller built (rt_scene_from_built)."""
+        h = C.c_void_p()
+        _check(lib().rt_scene_from_built(C.byref(built), C.byref(h)))
         return cls(h)
 
     def __del__(self):

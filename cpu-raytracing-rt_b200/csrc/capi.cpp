@@ -276,6 +276,35 @@ static void export_bvh(const HostBvh<P> &b, double *bounds, uint32_t *left, uint
     }
     if (order) for (size_t i = 0; i < b.prims.size(); ++i) order[i] = b.prims[i].orig;
 }
+namespace {
+template <class P>
+void import_nodes(const rt_built_bvh &b, HostBvh<P> &out) {
+    if (b.n_nodes && (!b.bounds || !b.left || !b.right || !b.first || !b.count)) throw std::runtime_error("null node array");
+    if (b.n_nodes >= RT_NO_CHILD || b.n_prims >= RT_NO_CHILD) throw std::runtime_error("hierarchy too large for 32-bit indices");
+    out.nodes.resize(b.n_nodes);
+    std::vector<uint32_t> depth(b.n_nodes, 0);
+    if (b.n_nodes) depth[0] = 1;
+    out.depth = 0;
+    for (uint64_t i = 0; i < b.n_nodes; ++i) {
+        HostNode n{};
+        for (int k = 0; k < 3; ++k) { n.box.lo[k] = b.bounds[i * 6 + k]; n.box.hi[k] = b.bounds[i * 6 + 3 + k]; }
+        n.left = b.left[i]; n.right = b.right[i]; n.first = b.first[i]; n.count = b.count[i];
+        const bool leaf = n.left == RT_NO_CHILD;
+        if (leaf != (n.right == RT_NO_CHILD)) throw std::runtime_error("node with exactly one child");
+        if (leaf) {
+            if ((uint64_t)n.first + n.count > b.n_prims) throw std::runtime_error("leaf range outside the primitive array");
+        } else {
+            // the reference numbers nodes in pre-order (src/bvh.rs:104-108): left child = node + 1
+            if (n.left != i + 1 || n.right <= n.left || n.right >= b.n_nodes) throw std::runtime_error("nodes are not in the reference's pre-order numbering");
+            depth[n.left] = depth[i] + 1;
+            depth[n.right] = depth[i] + 1;
+        }
+        out.depth = std::max(out.depth, depth[i]);
+        out.nodes[i] = n;
+    }
+}
+}  // namespace
+
 // ---- host side -----------------------------------------------------------------------------------
 extern "C" {
 
@@ -318,6 +347,64 @@ int rt_scene_load_gltf(const char *path, uint32_t width, uint32_t height, uint32
         std::unique_ptr<rt_scene> s(new rt_scene());
         build_scene(st.raw, s->s);
         *out = s.release();
+        return (int)RT_OK;
+    });
+}
+
+int rt_scene_from_built(const rt_built_scene *built, rt_scene **out) {
+    if (!built || !out) return set_err(nullptr, RT_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    return guarded(nullptr, RT_ERR_INVALID_ARG, [&]() {
+        const rt_built_scene &b = *built;
+        if (b.width == 0 || b.height == 0) throw std::runtime_error("zero image dimensions");
+        if (b.ray_depth > 255) throw std::runtime_error("ray_depth is a u8 in the reference");
+        if ((b.n_materials && !b.materials) || (b.n_planes && !b.planes)) throw std::runtime_error("null array");
+        std::unique_ptr<rt_scene> sc(new rt_scene());
+        HostScene &s = sc->s;
+        s.width = b.width; s.height = b.height; s.samples = b.samples; s.ray_depth = b.ray_depth;
+        auto v3 = [](const double *p) { return mk3(p[0], p[1], p[2]); };
+        s.bg_color = v3(b.bg_color);
+        s.cam_position = v3(b.cam_position); s.cam_right = v3(b.cam_right); s.cam_up = v3(b.cam_up); s.cam_forward = v3(b.cam_forward);
+        s.tan_half_fov_x = b.tan_half_fov_x; s.tan_half_fov_y = b.tan_half_fov_y;
+        s.materials.assign(b.materials, b.materials + b.n_materials);
+        auto shape_of = [&](const rt_shape &r, uint32_t orig, const double *box) {
+            if (r.material >= b.n_materials) throw std::runtime_error("material index out of range");
+            HostShape h{};
+            h.type = r.type; h.material = r.material;
+            h.param = v3(r.param); h.position = v3(r.position);
+            h.rotation = mkq_xyzw(r.rotation[0], r.rotation[1], r.rotation[2], r.rotation[3]);
+            h.orig = orig;
+            if (box) for (int k = 0; k < 3; ++k) { h.box.lo[k] = box[k]; h.box.hi[k] = box[3 + k]; }
+            return h;
+        };
+        for (uint32_t i = 0; i < b.n_planes; ++i) s.planes.push_back(shape_of(b.planes[i], i, nullptr));
+        HostBvh<HostShape> *shape_sets[6] = {&s.boxes, &s.ellipsoids, nullptr, &s.light_boxes, &s.light_ellipsoids, nullptr};
+        HostBvh<HostTri> *tri_sets[6] = {nullptr, nullptr, &s.tris, nullptr, nullptr, &s.light_tris};
+        for (int w = 0; w < 6; ++w) {
+            const rt_built_bvh &bb = b.bvh[w];
+            if (shape_sets[w]) {
+                if (bb.n_prims && !bb.shapes) throw std::runtime_error("null shape array");
+                import_nodes(bb, *shape_sets[w]);
+                for (uint64_t i = 0; i < bb.n_prims; ++i) shape_sets[w]->prims.push_back(shape_of(bb.shapes[i], (uint32_t)i, bb.shape_aabb ? bb.shape_aabb + i * 6 : nullptr));
+            } else {
+                if (bb.n_prims && (!bb.tri28 || !bb.tri_material)) throw std::runtime_error("null triangle array");
+                import_nodes(bb, *tri_sets[w]);
+                tri_sets[w]->prims.resize(bb.n_prims);
+                for (uint64_t i = 0; i < bb.n_prims; ++i) {
+                    const double *t = bb.tri28 + i * 28;
+                    HostTri h{};
+                    h.a = v3(t); h.ba = v3(t + 3); h.ca = v3(t + 6); h.ng = v3(t + 9);
+                    h.na = v3(t + 12); h.nb = v3(t + 15); h.nc = v3(t + 18);
+                    h.inv_area = t[21];
+                    for (int k = 0; k < 3; ++k) { h.box.lo[k] = t[22 + k]; h.box.hi[k] = t[25 + k]; }
+                    h.material = bb.tri_material[i];
+                    if (h.material >= b.n_materials) throw std::runtime_error("material index out of range");
+                    h.orig = (uint32_t)i;
+                    tri_sets[w]->prims[i] = h;
+                }
+            }
+        }
+        *out = sc.release();
         return (int)RT_OK;
     });
 }

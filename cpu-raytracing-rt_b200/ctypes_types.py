@@ -38,6 +38,21 @@ class SceneInfo(C.Structure):
                 ("bvh_depth", C.c_uint32 * 6)]
 
 
+class BuiltBvh(C.Structure):
+    _fields_ = [("n_nodes", C.c_uint64), ("n_prims", C.c_uint64), ("bounds", c_double_p), ("left", c_u32_p),
+                ("right", c_u32_p), ("first", c_u32_p), ("count", c_u32_p), ("shapes", C.POINTER(Shape)),
+                ("shape_aabb", c_double_p), ("tri28", c_double_p), ("tri_material", c_u32_p)]
+
+
+class BuiltScene(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("samples", C.c_uint32), ("ray_depth", C.c_uint32),
+                ("bg_color", C.c_double * 3), ("cam_position", C.c_double * 3), ("cam_right", C.c_double * 3),
+                ("cam_up", C.c_double * 3), ("cam_forward", C.c_double * 3),
+                ("tan_half_fov_x", C.c_double), ("tan_half_fov_y", C.c_double),
+                ("n_materials", C.c_uint32), ("n_planes", C.c_uint32),
+                ("materials", C.POINTER(Material)), ("planes", C.POINTER(Shape)), ("bvh", BuiltBvh * 6)]
+
+
 class Hit(C.Structure):
     _fields_ = [("t", C.c_double), ("geometry_normal", C.c_double * 3),
                 ("shading_normal", C.c_double * 3), ("kind", C.c_int32), ("prim", C.c_uint32),

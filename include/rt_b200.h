@@ -139,6 +139,34 @@ RT_API int rt_scene_get_shape(const rt_scene *scene, int which, uint64_t i, rt_s
                               double *aabb6);
 RT_API int rt_scene_get_material(const rt_scene *scene, uint32_t i, rt_material *out);
 
+/* A scene whose hierarchies were ALREADY built by the caller — the reference's own `Scene`
+ * (src/scene.rs:82-90) handed over as flat arrays, for a host that keeps its BVH::new
+ * (src/bvh.rs:12-17) and only wants the render path replaced.  Layouts are exactly what
+ * rt_scene_get_bvh / rt_scene_get_triangle / rt_scene_get_shape return: node arrays in the
+ * reference's pre-order numbering (left child = node + 1), primitives in post-build order.
+ * Everything is copied; nothing is retained. */
+typedef struct rt_built_bvh {
+    uint64_t n_nodes, n_prims;
+    const double   *bounds;         /* n_nodes * 6: min xyz, max xyz                       */
+    const uint32_t *left, *right;   /* RT_NO_CHILD for leaves                              */
+    const uint32_t *first, *count;  /* primitive_indices range                             */
+    const rt_shape *shapes;         /* RT_BVH_(LIGHT_)BOXES / ELLIPSOIDS: n_prims shapes   */
+    const double   *shape_aabb;     /* optional, n_prims * 6: world AABB of each shape     */
+    const double   *tri28;          /* RT_BVH_(LIGHT_)TRIANGLES: n_prims * 28 doubles      */
+    const uint32_t *tri_material;   /* n_prims                                             */
+} rt_built_bvh;
+typedef struct rt_built_scene {
+    uint32_t width, height, samples, ray_depth;
+    double   bg_color[3];
+    double   cam_position[3], cam_right[3], cam_up[3], cam_forward[3];
+    double   tan_half_fov_x, tan_half_fov_y;        /* Camera::new, src/camera.rs:18-46 */
+    uint32_t n_materials, n_planes;
+    const rt_material *materials;
+    const rt_shape    *planes;
+    rt_built_bvh bvh[6];            /* indexed by RT_BVH_*                                 */
+} rt_built_scene;
+RT_API int rt_scene_from_built(const rt_built_scene *built, rt_scene **out);
+
 /* ppm::save_to_ppm (src/ppm.rs:4-19): binary P6 of post-gamma rgb (width*height*3 doubles). */
 RT_API int rt_save_ppm(const char *path, uint32_t width, uint32_t height, const double *rgb);
 

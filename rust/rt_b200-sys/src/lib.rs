@@ -77,11 +77,47 @@ pub struct rt_render_params {
     pub _pad: i32,
 }
 
+#[repr(C)]
+pub struct rt_built_bvh {
+    pub n_nodes: u64,
+    pub n_prims: u64,
+    pub bounds: *const f64,
+    pub left: *const u32,
+    pub right: *const u32,
+    pub first: *const u32,
+    pub count: *const u32,
+    pub shapes: *const rt_shape,
+    pub shape_aabb: *const f64,
+    pub tri28: *const f64,
+    pub tri_material: *const u32,
+}
+
+#[repr(C)]
+pub struct rt_built_scene {
+    pub width: u32,
+    pub height: u32,
+    pub samples: u32,
+    pub ray_depth: u32,
+    pub bg_color: [f64; 3],
+    pub cam_position: [f64; 3],
+    pub cam_right: [f64; 3],
+    pub cam_up: [f64; 3],
+    pub cam_forward: [f64; 3],
+    pub tan_half_fov_x: f64,
+    pub tan_half_fov_y: f64,
+    pub n_materials: u32,
+    pub n_planes: u32,
+    pub materials: *const rt_material,
+    pub planes: *const rt_shape,
+    pub bvh: [rt_built_bvh; 6],
+}
+
 pub enum rt_scene {}
 pub enum rt_ctx {}
 
 extern "C" {
     pub fn rt_scene_build(raw: *const rt_raw_scene, out: *mut *mut rt_scene) -> c_int;
+    pub fn rt_scene_from_built(built: *const rt_built_scene, out: *mut *mut rt_scene) -> c_int;
     pub fn rt_scene_free(scene: *mut rt_scene);
     pub fn rt_scene_load_text(path: *const c_char, out: *mut *mut rt_scene) -> c_int;
     pub fn rt_scene_load_gltf(path: *const c_char, width: u32, height: u32, samples: u32, out: *mut *mut rt_scene) -> c_int;

@@ -112,3 +112,18 @@ def test_long_leaf_and_degenerate_triangles(orc, ctx):
     counts = prod.bvh(T.BVH_TRIANGLES)["count"]
     assert counts.max() >= 40
     _check(orc, ctx, raw, 2)
+
+
+def test_prebuilt_scene_renders_identically(orc, ctx, tmp_path):
+    """rt_scene_from_built (the caller's own hierarchies as flat arrays) renders bit for bit like
+    the scene it was exported from."""
+    from tests import helpers
+    path = helpers.cornell(tmp_path, 40, 32, 3, 5)
+    prod = rtb200.Scene.load_text(path)
+    ctx.upload(prod)
+    ctx.render_accum(0, 3, 17, T.MODE_FAST, T.SCHED_WAVEFRONT, clear=True)
+    want = ctx.accum()
+    built, keep = prod.export_built()
+    ctx.upload(rtb200.Scene.from_built(built))
+    ctx.render_accum(0, 3, 17, T.MODE_FAST, T.SCHED_WAVEFRONT, clear=True)
+    assert ctx.accum().tobytes() == want.tobytes() and want.sum() > 0

@@ -192,3 +192,29 @@ def test_ppm_bytes(orc, tmp_path):
     body = np.frombuffer(data[len(b"P6\n7 5\n255\n"):], np.uint8).reshape(5, 7, 3)
     assert np.array_equal(body, orc.to_bytes(img))
     assert tuple(body[0, 0]) == (1, 2, 3) and tuple(body[0, 1]) == (0, 255, 0)
+
+
+def test_prebuilt_scene_round_trip(orc, tmp_path):
+    """rt_scene_from_built: a host that keeps its own BVH::new hands the hierarchies over as flat
+    arrays.  Exporting a built scene and importing it again must give the same scene bit for bit;
+    malformed hierarchies are rejected."""
+    from oracle import loaders
+    path = helpers.cornell(tmp_path, 32, 24, 2, 5)
+    prod = rtb200.Scene.load_text(path)
+    built, keep = prod.export_built()
+    again = rtb200.Scene.from_built(built)
+    helpers.assert_scene_equal(again, orc.OracleScene(loaders.parse_text_scene(open(path).read())), prim_order=False)
+    assert list(again.info.bvh_depth) == list(prod.info.bvh_depth)
+    gltf, _ = helpers.heightfield(tmp_path, 12, 20)
+    prod2 = rtb200.Scene.load_gltf(gltf, 16, 9, 1)
+    built2, keep2 = prod2.export_built()
+    helpers.assert_scene_equal(rtb200.Scene.from_built(built2), orc.OracleScene(loaders.load_gltf(gltf, 16, 9, 1)), prim_order=False)
+    # not in pre-order: swap the children of the root
+    d = keep2[2 + T.BVH_TRIANGLES]
+    d["left"][0], d["right"][0] = d["right"][0], d["left"][0]
+    with pytest.raises(rtb200.RtError):
+        rtb200.Scene.from_built(built2)
+    d["left"][0], d["right"][0] = d["right"][0], d["left"][0]
+    d["count"][-1] += 5                                              # leaf range past the primitive array
+    with pytest.raises(rtb200.RtError):
+        rtb200.Scene.from_built(built2)
