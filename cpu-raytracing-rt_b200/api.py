@@ -142,7 +142,7 @@ class Scene:
 
     def export_built(self):
         """This scene as an rt_built_scene (already-built hierarchies as flat arrays) + keepalive."""
-        keep = []
+        keep = {"bvh": [], "other": []}     # owns every array the struct points to; keep["bvh"][w] = node arrays
         b = T.BuiltScene()
         i = self.info
         b.width, b.height, b.samples, b.ray_depth = i.width, i.height, i.samples, i.ray_depth
@@ -155,11 +155,11 @@ class Scene:
         planes = (T.Shape * max(1, i.n_planes))()
         for k in range(i.n_planes):
             planes[k] = self.shape(-1, k)[0]
-        keep += [mats, planes]
+        keep["other"] += [mats, planes]
         b.n_materials, b.n_planes, b.materials, b.planes = i.n_materials, i.n_planes, mats, planes
         for w in range(6):
             d = self.bvh(w)
-            keep.append(d)
+            keep["bvh"].append(d)
             bb = b.bvh[w]
             bb.n_nodes, bb.n_prims = len(d["left"]), len(d["prim_order"])
             bb.bounds = d["bounds"].ctypes.data_as(T.c_double_p)
@@ -170,14 +170,14 @@ class Scene:
                 mat = np.zeros(max(1, bb.n_prims), np.uint32)
                 for k in range(bb.n_prims):
                     tri[k], mat[k] = self.triangle(w, k)
-                keep += [tri, mat]
+                keep["other"] += [tri, mat]
                 bb.tri28, bb.tri_material = tri.ctypes.data_as(T.c_double_p), mat.ctypes.data_as(T.c_u32_p)
             else:
                 sh = (T.Shape * max(1, bb.n_prims))()
                 boxes = np.zeros((max(1, bb.n_prims), 6))
                 for k in range(bb.n_prims):
                     sh[k], boxes[k] = self.shape(w, k)
-                keep += [sh, boxes]
+                keep["other"] += [sh, boxes]
                 bb.shapes, bb.shape_aabb = sh, boxes.ctypes.data_as(T.c_double_p)
         return b, keep
 

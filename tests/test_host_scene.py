@@ -210,7 +210,7 @@ def test_prebuilt_scene_round_trip(orc, tmp_path):
     built2, keep2 = prod2.export_built()
     helpers.assert_scene_equal(rtb200.Scene.from_built(built2), orc.OracleScene(loaders.load_gltf(gltf, 16, 9, 1)), prim_order=False)
     # not in pre-order: swap the children of the root
-    d = keep2[2 + T.BVH_TRIANGLES]
+    d = keep2["bvh"][T.BVH_TRIANGLES]
     d["left"][0], d["right"][0] = d["right"][0], d["left"][0]
     with pytest.raises(rtb200.RtError):
         rtb200.Scene.from_built(built2)
