@@ -480,37 +480,57 @@ cudaError_t launch_render_wavefront(cudaStream_t st, const DScene &sc, uint32_t 
     k_wf_init<<<blocks, 128, 0, st>>>(b);
     ++*launches;
     const uint64_t max_iters = (uint64_t)sample_count * (sc.ray_depth ? sc.ray_depth : 1) + 2;
-    int cur = 0;
     bool poll_pending = false;
     // scenes without planes / boxes / ellipsoids (every glTF scene) run the kernel compiled without them
     const bool shapes = sc.n_planes || sc.boxes.n_prims || sc.ellipsoids.n_prims || sc.lboxes.n_prims || sc.lellipsoids.n_prims;
     const uint32_t tail_threshold = b.n / 16 + 1;       // below this many live slots, finish in one kernel
-    for (uint64_t it = 0; it < max_iters; ++it) {
-        // next list starts empty, trace cursor at 0
-        cudaMemsetAsync(&b.n_live[cur ^ 1], 0, sizeof(uint32_t), st);
-        cudaMemsetAsync(b.cursor, 0, sizeof(uint32_t), st);
-        if (shapes) k_wf_shade<true><<<blocks, 128, 0, st>>>(sc, b, cur, sample_begin, sample_count, seed, accum, ctr);
-        else k_wf_shade<false><<<blocks, 128, 0, st>>>(sc, b, cur, sample_begin, sample_count, seed, accum, ctr);
-        k_wf_trace<<<trace_blocks, 128, 0, st>>>(sc, b, cur ^ 1, ctr);
-        *launches += 2;
-        cur ^= 1;
-        if ((it & 3) == 3) {                    // poll the live count without stalling the stream
-            if (poll_pending) {
-                cudaError_t e = cudaEventSynchronize(ev);
-                if (e != cudaSuccess) return e;
-                if (*host_live == 0) break;
-                if (*host_live < tail_threshold) {
-                    // few slots left: finish them in one kernel (the count can only have shrunk since)
-                    k_wf_finish<<<(tail_threshold + 127) / 128, 128, 0, st>>>(sc, b, cur, sample_begin, sample_count, seed, accum, ctr);
-                    ++*launches;
-                    break;
-                }
-            }
-            cudaMemcpyAsync((void *)host_live, &b.n_live[cur], sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
-            cudaEventRecord(ev, st);
-            poll_pending = true;
-        }
+    // One iteration = 2 memset nodes + shade + trace; four iterations (ending on the list they
+    // started from) are captured ONCE into a CUDA graph and replayed, so the host issues one launch
+    // per four iterations instead of sixteen — the inner loop is launch-bound on small images and
+    // in the last iterations of every render.
+    auto issue_iteration = [&](int from) {
+        cudaMemsetAsync(&b.n_live[from ^ 1], 0, sizeof(uint32_t), st);      // next list starts empty
+        cudaMemsetAsync(b.cursor, 0, sizeof(uint32_t), st);                  // trace fetch position
+        if (shapes) k_wf_shade<true><<<blocks, 128, 0, st>>>(sc, b, from, sample_begin, sample_count, seed, accum, ctr);
+        else k_wf_shade<false><<<blocks, 128, 0, st>>>(sc, b, from, sample_begin, sample_count, seed, accum, ctr);
+        k_wf_trace<<<trace_blocks, 128, 0, st>>>(sc, b, from ^ 1, ctr);
+    };
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    bool use_graph = false;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        for (int k = 0; k < 4; ++k) issue_iteration(k & 1);
+        if (cudaStreamEndCapture(st, &graph) == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) use_graph = true;
     }
+    if (!use_graph) cudaGetLastError();             // fall back to plain launches (same kernels, same order)
+    cudaError_t result = cudaSuccess;
+    for (uint64_t it = 0; it < max_iters; it += 4) {
+        if (use_graph) {
+            result = cudaGraphLaunch(exec, st);
+            if (result != cudaSuccess) break;
+        } else {
+            for (int k = 0; k < 4; ++k) issue_iteration(k & 1);
+        }
+        *launches += 8;
+        // four iterations end on list 0 again; poll its live count without stalling the stream
+        if (poll_pending) {
+            result = cudaEventSynchronize(ev);
+            if (result != cudaSuccess) break;
+            if (*host_live == 0) break;
+            if (*host_live < tail_threshold) {
+                // few slots left: finish them in one kernel (the count can only have shrunk since)
+                k_wf_finish<<<(tail_threshold + 127) / 128, 128, 0, st>>>(sc, b, 0, sample_begin, sample_count, seed, accum, ctr);
+                ++*launches;
+                break;
+            }
+        }
+        cudaMemcpyAsync((void *)host_live, &b.n_live[0], sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+        cudaEventRecord(ev, st);
+        poll_pending = true;
+    }
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    if (result != cudaSuccess) return result;
     return cudaGetLastError();
 }
 
