@@ -304,6 +304,16 @@ def main():
                          "aabb_tests_per_segment": exact_c["aabb_tests"] / max(1, exact_c["segments"]),
                          "prim_tests_per_segment": exact_c["prim_tests"] / max(1, exact_c["segments"])},
         }
+        # issue-side view of the same kernels (static, from the tracked ncu summaries): the path is
+        # latency / issue bound, not HBM bound, so lanes per instruction and issue activity say more
+        # about kernel quality than the HBM fraction
+        ncu_path = os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")
+        if args.sched == "wavefront" and os.path.exists(ncu_path):
+            ns = json.load(open(ncu_path))
+            out["issue"] = {k: {"lanes_per_instruction": v["smsp__thread_inst_executed_per_inst_executed.ratio"][0],
+                                "issue_active_pct": v["smsp__issue_active.avg.pct_of_peak_sustained_active"][0],
+                                "registers": v["launch__registers_per_thread"][0],
+                                "source": "profiles/r01_ncu_full_summary.json (ncu --set full, one launch)"} for k, v in ns.items()}
         if world == 1 and not args.no_cpu_baseline:
             from oracle import loaders, orc
             orc.build()

@@ -259,7 +259,9 @@ class Context:
         _check(lib().rt_light_pdf(self._h, mode, pos.shape[0], _p(pos), _p(dirs), _p(out)), self._h)
         return out
 
-    def render_accum(self, sample_begin, sample_count, seed, mode=T.MODE_FAST, sched=T.SCHED_MEGAKERNEL, clear=False):
+    def render_accum(self, sample_begin, sample_count, seed, mode=T.MODE_FAST, sched=None, clear=False):
+        if sched is None:       # FAST renders with the wavefront scheduler, EXACT is the megakernel parity anchor
+            sched = T.SCHED_WAVEFRONT if mode == T.MODE_FAST else T.SCHED_MEGAKERNEL
         p = T.RenderParams(sample_begin, sample_count, seed, mode, sched, 1 if clear else 0, 0)
         _check(lib().rt_render_accum(self._h, C.byref(p)), self._h)
 
@@ -296,7 +298,9 @@ class Context:
         _check(lib().rt_scene_device_bytes(self._h, C.byref(n)), self._h)
         return n.value
 
-    def render(self, seed=0xC0FFEE, mode=T.MODE_FAST, sched=T.SCHED_MEGAKERNEL):
+    def render(self, seed=0xC0FFEE, mode=T.MODE_FAST, sched=None):
+        if sched is None:
+            sched = T.SCHED_WAVEFRONT if mode == T.MODE_FAST else T.SCHED_MEGAKERNEL
         out = np.zeros((self.scene.height, self.scene.width, 3))
         _check(lib().rt_render(self._h, seed, mode, sched, _p(out)), self._h)
         return out
