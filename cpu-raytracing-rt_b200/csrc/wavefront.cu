@@ -251,8 +251,9 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
     int32_t cur = kFastEmpty;
     int sp = 0;
     uint2 stk[kFastStack];                  // (child code, entry distance bits): one 8-byte local access per push / pop
+// decoded unconditionally (three integer ops, meaningful only when `cur` is a leaf code): no branch
 #define WF_ENTER_LEAF()                                                                     \
-    if (cur < 0 && cur != kFastEmpty) {                                                     \
+    {                                                                                       \
         const uint32_t code_ = (uint32_t)~cur;                                              \
         tri_i = code_ >> 3;                                                                 \
         tri_end = tri_i + (code_ & 7u) + 1u;                                                \
@@ -339,10 +340,11 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
                 // key: children left to right, the reference's visit order (bvh.rs:188-210), which
                 // fixes the order of the pdf sum.
                 const uint32_t none = 0xFFFFFFFFu;
-                const uint32_t k0 = v.key[0] < inf ? ((closest ? (__float_as_uint(v.key[0]) & ~3u) : 0u) | 0u) : none;
-                const uint32_t k1 = v.key[1] < inf ? ((closest ? (__float_as_uint(v.key[1]) & ~3u) : 0u) | 1u) : none;
-                const uint32_t k2 = v.key[2] < inf ? ((closest ? (__float_as_uint(v.key[2]) & ~3u) : 0u) | 2u) : none;
-                const uint32_t k3 = v.key[3] < inf ? ((closest ? (__float_as_uint(v.key[3]) & ~3u) : 0u) | 3u) : none;
+                const uint32_t cmask = closest ? ~3u : 0u;          // branch-free: selects, no divergent paths
+                const uint32_t b0 = (__float_as_uint(v.key[0]) & cmask) | 0u, b1 = (__float_as_uint(v.key[1]) & cmask) | 1u;
+                const uint32_t b2 = (__float_as_uint(v.key[2]) & cmask) | 2u, b3 = (__float_as_uint(v.key[3]) & cmask) | 3u;
+                const uint32_t k0 = v.key[0] < inf ? b0 : none, k1 = v.key[1] < inf ? b1 : none;
+                const uint32_t k2 = v.key[2] < inf ? b2 : none, k3 = v.key[3] < inf ? b3 : none;
                 const uint32_t kmin = min(min(k0, k1), min(k2, k3));
                 if (kmin != none) {
                     // deferred children are pushed right to left, so they pop left to right
@@ -351,7 +353,8 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
                     if (k1 != none && k1 != kmin) { stk[sp] = make_uint2((uint32_t)v.child[1], k1 & ~3u); ++sp; }
                     if (k0 != none && k0 != kmin) { stk[sp] = make_uint2((uint32_t)v.child[0], k0 & ~3u); ++sp; }
                     const uint32_t sel = kmin & 3u;
-                    cur = sel == 0u ? v.child[0] : (sel == 1u ? v.child[1] : (sel == 2u ? v.child[2] : v.child[3]));
+                    const int32_t c01 = (sel & 1u) ? v.child[1] : v.child[0], c23 = (sel & 1u) ? v.child[3] : v.child[2];
+                    cur = (sel & 2u) ? c23 : c01;
                     cur_t = __uint_as_float(kmin & ~3u);
                     WF_ENTER_LEAF()
                 } else {
