@@ -17,7 +17,7 @@ _LIB = None
 
 # every symbol include/rt_b200.h declares (tests check that the library exports each of them)
 SYMBOLS = [
-    "rt_scene_build", "rt_scene_from_built", "rt_scene_free", "rt_scene_load_text", "rt_scene_load_gltf", "rt_scene_get_info",
+    "rt_scene_build", "rt_scene_build_cached", "rt_scene_load_gltf_cached", "rt_scene_from_built", "rt_scene_free", "rt_scene_load_text", "rt_scene_load_gltf", "rt_scene_get_info",
     "rt_scene_get_bvh", "rt_scene_get_triangle", "rt_scene_get_shape", "rt_scene_get_material", "rt_save_ppm",
     "rt_device_count", "rt_create", "rt_destroy", "rt_last_error", "rt_upload_scene", "rt_scene_device_bytes", "rt_trace_rays",
     "rt_trace_primary", "rt_light_pdf", "rt_render_accum", "rt_accum_device_ptr", "rt_get_accum", "rt_set_accum",
@@ -54,6 +54,8 @@ def lib():
         L.rt_scene_free.restype = None
         L.rt_scene_load_text.argtypes = [C.c_char_p, C.POINTER(vp)]
         L.rt_scene_load_gltf.argtypes = [C.c_char_p, u32, u32, u32, C.POINTER(vp)]
+        L.rt_scene_build_cached.argtypes = [C.POINTER(T.RawScene), C.c_char_p, C.POINTER(vp), C.POINTER(i32)]
+        L.rt_scene_load_gltf_cached.argtypes = [C.c_char_p, u32, u32, u32, C.c_char_p, C.POINTER(vp), C.POINTER(i32)]
         L.rt_scene_get_info.argtypes = [vp, C.POINTER(T.SceneInfo)]
         L.rt_scene_get_bvh.argtypes = [vp, i32] + [vp] * 6
         L.rt_scene_get_triangle.argtypes = [vp, i32, u64, vp, C.POINTER(u32)]
@@ -118,13 +120,22 @@ class Scene:
         self.width, self.height, self.samples, self.ray_depth = info.width, info.height, info.samples, info.ray_depth
 
     @classmethod
-    def from_raw(cls, raw_scene):
-        """Scene::new (src/scene.rs:180) / build_scene on an in-memory description."""
+    def from_raw(cls, raw_scene, cache_dir=None):
+        """Scene::new (src/scene.rs:180) / build_scene on an in-memory description.
+
+        cache_dir: keep the built hierarchies on disk, keyed by a hash of the geometry; the next
+        call with the same mesh reads them back instead of rebuilding (`scene.cache_hit`)."""
         raw, keep = raw_scene.as_ctypes()
         h = C.c_void_p()
-        _check(lib().rt_scene_build(C.byref(raw), C.byref(h)))
+        hit = C.c_int32(0)
+        if cache_dir is None:
+            _check(lib().rt_scene_build(C.byref(raw), C.byref(h)))
+        else:
+            _check(lib().rt_scene_build_cached(C.byref(raw), os.fsencode(cache_dir), C.byref(h), C.byref(hit)))
         del keep
-        return cls(h)
+        sc = cls(h)
+        sc.cache_hit = bool(hit.value)
+        return sc
 
     @classmethod
     def load_text(cls, path):
@@ -134,11 +145,18 @@ class Scene:
         return cls(h)
 
     @classmethod
-    def load_gltf(cls, path, width, height, samples):
-        """gltf::parse + gltf::build_scene (src/main.rs:47-66)."""
+    def load_gltf(cls, path, width, height, samples, cache_dir=None):
+        """gltf::parse + gltf::build_scene (src/main.rs:47-66); cache_dir as in from_raw."""
         h = C.c_void_p()
-        _check(lib().rt_scene_load_gltf(os.fsencode(path), width, height, samples, C.byref(h)))
-        return cls(h)
+        hit = C.c_int32(0)
+        if cache_dir is None:
+            _check(lib().rt_scene_load_gltf(os.fsencode(path), width, height, samples, C.byref(h)))
+        else:
+            _check(lib().rt_scene_load_gltf_cached(os.fsencode(path), width, height, samples, os.fsencode(cache_dir),
+                                                   C.byref(h), C.byref(hit)))
+        sc = cls(h)
+        sc.cache_hit = bool(hit.value)
+        return sc
 
     def export_built(self):
         """This scene as an rt_built_scene (already-built hierarchies as flat arrays) + keepalive."""

@@ -351,6 +351,32 @@ int rt_scene_load_gltf(const char *path, uint32_t width, uint32_t height, uint32
     });
 }
 
+int rt_scene_build_cached(const rt_raw_scene *raw, const char *cache_dir, rt_scene **out, int *cache_hit) {
+    if (!raw || !out || !cache_dir) return set_err(nullptr, RT_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    if (cache_hit) *cache_hit = 0;
+    return guarded(nullptr, RT_ERR_IO, [&]() {
+        std::unique_ptr<rt_scene> s(new rt_scene());
+        const bool hit = build_scene_cached(*raw, cache_dir, s->s);
+        if (cache_hit) *cache_hit = hit ? 1 : 0;
+        *out = s.release();
+        return (int)RT_OK;
+    });
+}
+int rt_scene_load_gltf_cached(const char *path, uint32_t width, uint32_t height, uint32_t samples, const char *cache_dir,
+                              rt_scene **out, int *cache_hit) {
+    if (!out || !path || !cache_dir) return set_err(nullptr, RT_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    if (cache_hit) *cache_hit = 0;
+    RawSceneStorage st;
+    const int rc = guarded(nullptr, RT_ERR_PARSE, [&]() {
+        load_gltf_scene(path, width, height, samples, st);
+        return (int)RT_OK;
+    });
+    if (rc != RT_OK) return rc;
+    return rt_scene_build_cached(&st.raw, cache_dir, out, cache_hit);
+}
+
 int rt_scene_from_built(const rt_built_scene *built, rt_scene **out) {
     if (!built || !out) return set_err(nullptr, RT_ERR_INVALID_ARG, "null argument");
     *out = nullptr;

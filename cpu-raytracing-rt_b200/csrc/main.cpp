@@ -31,7 +31,11 @@ int main(int argc, char **argv) {
         char *e1 = nullptr, *e2 = nullptr, *e3 = nullptr;
         const unsigned long w = std::strtoul(argv[3], &e1, 10), h = std::strtoul(argv[4], &e2, 10), spp = std::strtoul(argv[5], &e3, 10);
         if (*e1 || *e2 || *e3) { std::fprintf(stderr, "width, height and samples must be base-10 integers\n"); return 101; }
-        if (rt_scene_load_gltf(argv[2], (uint32_t)w, (uint32_t)h, (uint32_t)spp, &scene)) return die("glTF", nullptr);
+        // RT_BVH_CACHE=<dir>: keep the built hierarchies on disk, keyed by a hash of the mesh
+        const char *cache = std::getenv("RT_BVH_CACHE");
+        const int rc = cache && *cache ? rt_scene_load_gltf_cached(argv[2], (uint32_t)w, (uint32_t)h, (uint32_t)spp, cache, &scene, nullptr)
+                                       : rt_scene_load_gltf(argv[2], (uint32_t)w, (uint32_t)h, (uint32_t)spp, &scene);
+        if (rc) return die("glTF", nullptr);
     } else {
         if (rt_scene_load_text(nullptr, &scene)) return die("scene", nullptr);
     }

@@ -304,12 +304,12 @@ inline bool emits(const rt_material &m) {                   // is_light, src/sce
 
 }  // namespace
 
-void build_scene(const rt_raw_scene &raw, HostScene &s) {
+// Everything of the Scene that is not geometry: image size, sample count, depth, background and
+// Camera::new (src/camera.rs:18-46).  Separate so that cached hierarchies (scene_cache.cpp) can be
+// paired with the view of the current run.
+void apply_view(const rt_raw_scene &raw, HostScene &s) {
     if (raw.width == 0 || raw.height == 0) throw std::runtime_error("zero image dimensions");
     if (raw.ray_depth > 255) throw std::runtime_error("ray_depth is a u8 in the reference");
-    if ((raw.n_materials && !raw.materials) || (raw.n_shapes && !raw.shapes) || (raw.n_triangles && !raw.tri_pos))
-        throw std::runtime_error("null array in rt_raw_scene");
-    s = HostScene{};
     s.width = raw.width; s.height = raw.height; s.samples = raw.samples; s.ray_depth = raw.ray_depth;
     s.bg_color = ld3(raw.bg_color);
     s.cam_position = ld3(raw.cam_position); s.cam_right = ld3(raw.cam_right);
@@ -322,6 +322,13 @@ void build_scene(const rt_raw_scene &raw, HostScene &s) {
         s.tan_half_fov_x = tan(raw.fov / 2.0);
         s.tan_half_fov_y = s.tan_half_fov_x / (fw / fh);
     }
+}
+
+void build_scene(const rt_raw_scene &raw, HostScene &s) {
+    if ((raw.n_materials && !raw.materials) || (raw.n_shapes && !raw.shapes) || (raw.n_triangles && !raw.tri_pos))
+        throw std::runtime_error("null array in rt_raw_scene");
+    s = HostScene{};
+    apply_view(raw, s);
     s.materials.assign(raw.materials, raw.materials + raw.n_materials);
     auto check_mat = [&](uint32_t m) { if (m >= raw.n_materials) throw std::runtime_error("material index out of range"); };
 

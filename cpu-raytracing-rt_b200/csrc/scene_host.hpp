@@ -68,6 +68,15 @@ void build_bvh(const Box6 *boxes, size_t n, std::vector<HostNode> &nodes, std::v
 // Throws std::runtime_error on invalid input.
 void build_scene(const rt_raw_scene &raw, HostScene &out);
 
+void apply_view(const rt_raw_scene &raw, HostScene &s);     // image size, samples, depth, background, camera
+
+// On-disk cache of the built hierarchies (scene_cache.cpp), keyed by a hash of the geometry.
+uint64_t geometry_hash(const rt_raw_scene &raw);
+std::string scene_cache_path(const std::string &dir, uint64_t hash);
+void save_scene_cache(const std::string &path, uint64_t hash, const HostScene &s);
+bool load_scene_cache(const std::string &path, uint64_t hash, HostScene &s);       // false: absent or another mesh
+bool build_scene_cached(const rt_raw_scene &raw, const std::string &cache_dir, HostScene &out);   // true: cache hit
+
 // Loaders (throw std::runtime_error where the reference would panic).
 struct RawSceneStorage {            // owns the arrays an rt_raw_scene points to
     rt_raw_scene raw{};

@@ -182,6 +182,30 @@ __global__ void __launch_bounds__(128) k_wf_shade(DScene sc, WfBuf b, int cur_li
             b.sample[slot] = s;
         }
     }
+#if WF_OCTANT_BIN
+    // stream compaction of the live slots, grouped by direction octant inside the block: rays that
+    // a trace warp picks up together then choose the same near / far planes at every node
+    __shared__ uint32_t s_cnt[8][4];
+    __shared__ uint32_t s_base;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t oct = keep ? ((b.rd[slot] < 0.0 ? 1u : 0u) | (b.rd[N + slot] < 0.0 ? 2u : 0u) | (b.rd[2u * N + slot] < 0.0 ? 4u : 0u)) : 8u;
+    uint32_t rank = 0;
+#pragma unroll
+    for (uint32_t q = 0; q < 8; ++q) {
+        const unsigned mq = __ballot_sync(kFull, oct == q);
+        if (lane == 0) s_cnt[q][wid] = __popc(mq);
+        if (oct == q) rank = __popc(mq & ((1u << lane) - 1u));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int q = 0; q < 8; ++q)
+            for (int w = 0; w < 4; ++w) { const uint32_t v = s_cnt[q][w]; s_cnt[q][w] = tot; tot += v; }
+        s_base = tot ? atomicAdd(&b.n_live[cur_list ^ 1], tot) : 0u;
+    }
+    __syncthreads();
+    if (keep) next_live[s_base + s_cnt[oct][wid] + rank] = slot;
+#else
     // stream compaction of the live slots: ballot + prefix sum inside the warp, one atomic per warp
     __syncwarp();
     const unsigned m = __ballot_sync(kFull, keep);
@@ -192,6 +216,7 @@ __global__ void __launch_bounds__(128) k_wf_shade(DScene sc, WfBuf b, int cur_li
         base = __shfl_sync(kFull, base, leader);
         if (keep) next_live[base + __popc(m & ((1u << lane) - 1u))] = slot;
     }
+#endif
     flush_counters_wf(c, ctr);
 }
 
@@ -212,6 +237,9 @@ __global__ void __launch_bounds__(128) k_wf_shade(DScene sc, WfBuf b, int cur_li
 #ifndef WF_VOTE_I
 #define WF_VOTE_I 1            // the INNER step runs when WF_VOTE_I * (#lanes at a node) >= WF_VOTE_T * (#lanes at a leaf)
 #define WF_VOTE_T 1
+#endif
+#ifndef WF_OCTANT_BIN
+#define WF_OCTANT_BIN 0          // measured on B200 (C3): 1096.5 Mseg/s with the grouping, 1096-1099 without
 #endif
 #ifndef WF_REFILL
 #define WF_REFILL 8

@@ -105,6 +105,19 @@ RT_API int  rt_scene_load_text(const char *path, rt_scene **out);
 RT_API int  rt_scene_load_gltf(const char *path, uint32_t width, uint32_t height, uint32_t samples,
                                rt_scene **out);
 
+/* The same two calls with an on-disk cache of the BUILT scene (the
+ * reference rebuilds src/bvh.rs:12-17 on every run).  The file <cache_dir>/<hash>.rtbvh is keyed by
+ * a 64-bit hash of the geometry (materials, shapes, triangle arrays); image size, samples, depth,
+ * background and camera always come from the arguments, so one cached mesh serves any view.
+ * On a miss the scene is built and the file written (atomically: temporary name + rename).
+ * *cache_hit (may be NULL) reports which happened.  A damaged file is an error (RT_ERR_IO), never
+ * silently rebuilt; the loaded hierarchies pass the same checks as rt_scene_from_built. */
+RT_API int  rt_scene_build_cached(const rt_raw_scene *raw, const char *cache_dir, rt_scene **out,
+                                  int *cache_hit);
+RT_API int  rt_scene_load_gltf_cached(const char *path, uint32_t width, uint32_t height,
+                                      uint32_t samples, const char *cache_dir, rt_scene **out,
+                                      int *cache_hit);
+
 /* Which of the six hierarchies (src/scene.rs:57-69). Build order in the reference is lights
  * first (src/scene.rs:209-220); the numbering here is only a name. */
 enum { RT_BVH_BOXES = 0, RT_BVH_ELLIPSOIDS = 1, RT_BVH_TRIANGLES = 2,

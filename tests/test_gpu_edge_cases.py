@@ -127,3 +127,22 @@ def test_prebuilt_scene_renders_identically(orc, ctx, tmp_path):
     ctx.upload(rtb200.Scene.from_built(built))
     ctx.render_accum(0, 3, 17, T.MODE_FAST, T.SCHED_WAVEFRONT, clear=True)
     assert ctx.accum().tobytes() == want.tobytes() and want.sum() > 0
+
+
+def test_cached_scene_renders_identically(orc, ctx, tmp_path):
+    """A scene read back from the on-disk hierarchy cache renders bit for bit like a fresh build."""
+    from tests import helpers
+    path, _ = helpers.heightfield(tmp_path, 24, 32, lights=True, spheres=True)
+    cache = tmp_path / "cache"
+    cache.mkdir()
+    images = []
+    for expect_hit in (False, True):
+        sc = rtb200.Scene.load_gltf(path, 48, 32, 3, cache_dir=str(cache))
+        assert sc.cache_hit == expect_hit
+        ctx.upload(sc)
+        ctx.render_accum(0, 3, 23, T.MODE_FAST, T.SCHED_WAVEFRONT, clear=True)
+        images.append(ctx.accum())
+    ctx.upload(rtb200.Scene.load_gltf(path, 48, 32, 3))
+    ctx.render_accum(0, 3, 23, T.MODE_FAST, T.SCHED_WAVEFRONT, clear=True)
+    want = ctx.accum()
+    assert images[0].tobytes() == want.tobytes() == images[1].tobytes() and want.sum() > 0

@@ -218,3 +218,61 @@ def test_prebuilt_scene_round_trip(orc, tmp_path):
     d["count"][-1] += 5                                              # leaf range past the primitive array
     with pytest.raises(rtb200.RtError):
         rtb200.Scene.from_built(built2)
+
+
+def test_scene_cache_round_trip(orc, tmp_path):
+    """the built hierarchies are stored on disk keyed by a hash of the geometry.
+    A hit must give the bits a fresh build gives (== the oracle's), with the VIEW of the current
+    call (image size, samples, camera), and another mesh must not hit."""
+    from oracle import loaders
+    cache = tmp_path / "cache"
+    cache.mkdir()
+    path, _ = helpers.heightfield(tmp_path, 30, 40, lights=True, spheres=True)
+    first = rtb200.Scene.load_gltf(path, 64, 36, 2, cache_dir=str(cache))
+    assert not first.cache_hit and len(list(cache.glob("*.rtbvh"))) == 1
+    again = rtb200.Scene.load_gltf(path, 96, 54, 7, cache_dir=str(cache))      # same mesh, other view
+    assert again.cache_hit and len(list(cache.glob("*"))) == 1                 # no temporary left behind
+    assert (again.info.width, again.info.height, again.info.samples) == (96, 54, 7)
+    helpers.assert_scene_equal(again, orc.OracleScene(loaders.load_gltf(path, 96, 54, 7)))
+    helpers.assert_scene_equal(first, orc.OracleScene(loaders.load_gltf(path, 64, 36, 2)))
+    # text-format scene through the in-memory entry point: shapes + planes + model-space triangles
+    raw = loaders.parse_text_scene(open(helpers.cornell(tmp_path)).read())
+    a = rtb200.Scene.from_raw(raw, cache_dir=str(cache))
+    b = rtb200.Scene.from_raw(raw, cache_dir=str(cache))
+    assert not a.cache_hit and b.cache_hit and len(list(cache.glob("*.rtbvh"))) == 2
+    helpers.assert_scene_equal(b, orc.OracleScene(raw))
+    # one changed coordinate is another mesh
+    raw.shapes[0]["position"] = tuple(np.add(raw.shapes[0]["position"], (0.0, 1e-9, 0.0)))
+    c = rtb200.Scene.from_raw(raw, cache_dir=str(cache))
+    assert not c.cache_hit and len(list(cache.glob("*.rtbvh"))) == 3
+
+
+def test_scene_cache_rejects_damaged_files(tmp_path):
+    """A truncated or corrupted cache file is an error (RT_ERR_IO = 4), not a silent rebuild and
+    not an out-of-range index later on the device."""
+    cache = tmp_path / "cache"
+    cache.mkdir()
+    path, _ = helpers.heightfield(tmp_path, 12, 12, lights=True, spheres=False)
+    rtb200.Scene.load_gltf(path, 16, 16, 1, cache_dir=str(cache))
+    (f,) = list(cache.glob("*.rtbvh"))
+    blob = f.read_bytes()
+    f.write_bytes(blob[:-40])
+    with pytest.raises(rtb200.RtError) as e:
+        rtb200.Scene.load_gltf(path, 16, 16, 1, cache_dir=str(cache))
+    assert e.value.code == 4 and "size" in str(e.value)
+    # same size, a child link pointing outside the node array
+    import struct
+    n_mat = struct.unpack_from("<I", blob, 28)[0]
+    n_planes = struct.unpack_from("<Q", blob, 40)[0]
+    assert n_planes == 0
+    first_node = 48 + 8 * 12 + n_mat * C.sizeof(T.Material)        # header, materials, (no planes / shapes)
+    bad = bytearray(blob)
+    n_nodes = struct.unpack_from("<6Q", blob, 48)
+    assert n_nodes[T.BVH_TRIANGLES] > 1 and n_nodes[T.BVH_BOXES] == 0
+    struct.pack_into("<I", bad, first_node + 48 + 4, 0x7FFFFFFF)    # root.right of the triangle hierarchy
+    f.write_bytes(bytes(bad))
+    with pytest.raises(rtb200.RtError) as e:
+        rtb200.Scene.load_gltf(path, 16, 16, 1, cache_dir=str(cache))
+    assert e.value.code == 4 and "pre-order" in str(e.value)
+    with pytest.raises(rtb200.RtError):                             # unwritable cache directory
+        rtb200.Scene.load_gltf(path, 16, 16, 1, cache_dir=str(tmp_path / "missing" / "dir"))
