@@ -44,6 +44,9 @@ def parse_args():
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
     ap.add_argument("--sched", default="wavefront", choices=["megakernel", "wavefront"])
     ap.add_argument("--seed", type=lambda s: int(s, 0), default=0xC0FFEE)
+    ap.add_argument("--shard", default="samples", choices=["samples", "rows"],
+                    help="N>1: every rank renders its own sample range of the whole image (default), or all the "
+                         "samples of its own band of rows (tile sharding; same total work, shows the load imbalance)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-spp", type=int, default=1, help="samples per step of the CPU reference arm")
     return ap.parse_args()
@@ -189,9 +192,20 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def render_shard(k):
+        """this rank's share of pass k: S samples of every pixel, or S*world samples of its rows"""
+        if args.shard == "rows" and world > 1:
+            band = sharding.row_band(rank, world, args.width, args.height)
+            if band is None:
+                ctx.render_accum(k * world * S, 0, args.seed, mode, sched, clear=True)
+            else:
+                ctx.render_accum(k * world * S, S * world, args.seed, mode, sched, clear=True, region=band)
+        else:
+            ctx.render_accum(*sharding.step_sample_range(rank, world, k, S), args.seed, mode, sched, clear=True)
+
     def step(k):
         """one pass: S spp per GPU on a disjoint global sample range, reduce, tonemap"""
-        ctx.render_accum((k * world + rank) * S, S, args.seed, mode, sched, clear=True)
+        render_shard(k)
         if world > 1:
             with torch.cuda.stream(stream):
                 dist.reduce(accum_t, dst=0, op=dist.ReduceOp.SUM)
@@ -218,7 +232,7 @@ def main():
     ev[0].record(stream)
     for k in range(args.steps):
         k_ev[k][0].record(stream)
-        ctx.render_accum(*sharding.step_sample_range(rank, world, k, S), args.seed, mode, sched, clear=True)
+        render_shard(k)
         k_ev[k][1].record(stream)
         if world > 1:
             with torch.cuda.stream(stream):
@@ -245,14 +259,14 @@ def main():
     img = np.zeros((args.height, args.width, 3))
     for w in range(2):
         ctx.upload(scene)
-        ctx.render_accum(20_000 + w, S, args.seed, mode, sched, clear=True)
+        render_shard(20_000 + w)
         ctx.postprocess_into(S, img)
     barrier()
     ctx.reset_counters()
     t0 = time.perf_counter()
     for k in range(args.steps):
         ctx.upload(scene)                                                   # H2D: the flattened scene
-        ctx.render_accum((k * world + rank) * S, S, args.seed, mode, sched, clear=True)
+        render_shard(k)
         if world > 1:
             dptr2, _ = ctx.accum_device_ptr()
             assert dptr2 == dptr, "accumulation buffer moved"
@@ -290,7 +304,7 @@ def main():
             "ms_per_step": ms / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args, n_tris), "spp_per_step_per_gpu": S, "mode": args.mode,
-                       "scheduler": args.sched, "l2": f"inputs larger than L2: {scene_bytes / 1e6:.0f} MB of scene records per GPU, no flush",
+                       "scheduler": args.sched, "shard": args.shard if world > 1 else "none", "l2": f"inputs larger than L2: {scene_bytes / 1e6:.0f} MB of scene records per GPU, no flush",
                        "segments_per_path": segments / max(1.0, paths), "light_pdf_rays_per_segment": lrays / max(1.0, segments)},
             "time_to_1024spp_s": (ms * 1e-3) / max(1, args.steps) / (S * world) * 1024,
             "gpu_launches": int(counters["kernel_launches"]),

@@ -21,7 +21,7 @@ SYMBOLS = [
     "rt_scene_get_bvh", "rt_scene_get_triangle", "rt_scene_get_shape", "rt_scene_get_material", "rt_save_ppm",
     "rt_device_count", "rt_create", "rt_destroy", "rt_last_error", "rt_upload_scene", "rt_scene_device_bytes", "rt_trace_rays",
     "rt_trace_primary", "rt_light_pdf", "rt_render_accum", "rt_accum_device_ptr", "rt_get_accum", "rt_set_accum",
-    "rt_postprocess", "rt_render", "rt_sync", "rt_stream", "rt_get_counters", "rt_reset_counters", "rt_debug_rng", "rt_debug_wavefront",
+    "rt_postprocess", "rt_render", "rt_render_progressive", "rt_sync", "rt_stream", "rt_get_counters", "rt_reset_counters", "rt_debug_rng", "rt_debug_wavefront",
 ]
 
 
@@ -79,6 +79,7 @@ def lib():
         L.rt_set_accum.argtypes = [vp, vp]
         L.rt_postprocess.argtypes = [vp, u32, vp]
         L.rt_render.argtypes = [vp, u64, i32, i32, vp]
+        L.rt_render_progressive.argtypes = [vp, u64, i32, i32, u32, T.ProgressFn, vp, vp, C.POINTER(u32)]
         L.rt_sync.argtypes = [vp]
         L.rt_stream.argtypes = [vp, C.POINTER(vp)]
         L.rt_get_counters.argtypes = [vp, C.POINTER(T.Counters)]
@@ -277,10 +278,14 @@ class Context:
         _check(lib().rt_light_pdf(self._h, mode, pos.shape[0], _p(pos), _p(dirs), _p(out)), self._h)
         return out
 
-    def render_accum(self, sample_begin, sample_count, seed, mode=T.MODE_FAST, sched=None, clear=False):
+    def render_accum(self, sample_begin, sample_count, seed, mode=T.MODE_FAST, sched=None, clear=False, region=None):
+        """accum += sum of `sample_count` samples per pixel (src/main.rs:94-103 without :104).
+        region = (x0, y0, w, h): only those pixels (same values as the full render has there)."""
         if sched is None:       # FAST renders with the wavefront scheduler, EXACT is the megakernel parity anchor
             sched = T.SCHED_WAVEFRONT if mode == T.MODE_FAST else T.SCHED_MEGAKERNEL
         p = T.RenderParams(sample_begin, sample_count, seed, mode, sched, 1 if clear else 0, 0)
+        if region is not None:
+            p.region[:] = [int(v) for v in region]
         _check(lib().rt_render_accum(self._h, C.byref(p)), self._h)
 
     def accum(self):
@@ -322,6 +327,34 @@ class Context:
         out = np.zeros((self.scene.height, self.scene.width, 3))
         _check(lib().rt_render(self._h, seed, mode, sched, _p(out)), self._h)
         return out
+
+    def render_progressive(self, chunk_samples, callback=None, seed=0xC0FFEE, mode=T.MODE_FAST, sched=None):
+        """generate_image in chunks with the image so far after each chunk (rt_render_progressive).
+        callback(samples_done, samples_total, rgb) -> truthy stops the render; rgb is a view that
+        is only valid during the call.  Returns (rgb, samples_done); run to the end, rgb is bit
+        for bit what render() returns."""
+        if sched is None:
+            sched = T.SCHED_WAVEFRONT if mode == T.MODE_FAST else T.SCHED_MEGAKERNEL
+        h, w = self.scene.height, self.scene.width
+        out = np.zeros((h, w, 3))
+        raised = []
+
+        @T.ProgressFn
+        def trampoline(_user, done, total, rgb):
+            if callback is None:
+                return 0
+            try:
+                view = np.ctypeslib.as_array(rgb, shape=(h, w, 3))
+                return 1 if callback(int(done), int(total), view) else 0
+            except BaseException as e:        # an exception must not unwind through the C frames
+                raised.append(e)
+                return 1
+
+        done = C.c_uint32(0)
+        _check(lib().rt_render_progressive(self._h, seed, mode, sched, chunk_samples, trampoline, None, _p(out), C.byref(done)), self._h)
+        if raised:
+            raise raised[0]
+        return out, done.value
 
     def sync(self):
         _check(lib().rt_sync(self._h), self._h)

@@ -686,16 +686,22 @@ int rt_render_accum(rt_ctx *ctx, const rt_render_params *p) {
     if (int r = check_mode(ctx, p->mode)) return r;
     if (p->sched != RT_SCHED_MEGAKERNEL && p->sched != RT_SCHED_WAVEFRONT) return set_err(ctx, RT_ERR_INVALID_ARG, "unknown scheduler");
     if ((uint64_t)p->sample_begin + p->sample_count > 0xFFFFFFFFull) return set_err(ctx, RT_ERR_INVALID_ARG, "sample range overflows u32");
+    DRegion rg{0u, 0u, ctx->dsc.width, ctx->dsc.height};
+    if (p->region[2] != 0 && p->region[3] != 0) {
+        rg = DRegion{p->region[0], p->region[1], p->region[2], p->region[3]};
+        if ((uint64_t)rg.x0 + rg.w > ctx->dsc.width || (uint64_t)rg.y0 + rg.h > ctx->dsc.height)
+            return set_err(ctx, RT_ERR_INVALID_ARG, "render region reaches outside the image");
+    }
     if (p->clear) CK(ctx, cudaMemsetAsync(ctx->d_accum, 0, ctx->n_px * 3 * sizeof(double), ctx->stream));
     if (p->sample_count == 0) return RT_OK;
     if (p->sched == RT_SCHED_WAVEFRONT && ctx->dsc.ray_depth > 0) {
         if (p->mode != RT_MODE_FAST) return set_err(ctx, RT_ERR_INVALID_ARG, "the wavefront scheduler runs FAST mode only (EXACT is the megakernel parity anchor)");
         CK(ctx, ensure_wavefront(ctx));
         CK(ctx, launch_render_wavefront(ctx->stream, ctx->dsc, p->sample_begin, p->sample_count, p->seed, ctx->d_accum, ctx->d_ctr,
-                                        ctx->wf, ctx->wf_host_live, ctx->wf_event, ctx->wf_blocks, &ctx->launches));
+                                        ctx->wf, ctx->wf_host_live, ctx->wf_event, ctx->wf_blocks, &ctx->launches, rg));
         return RT_OK;
     }
-    CK(ctx, launch_render_mega(ctx->stream, ctx->dsc, p->mode, p->sample_begin, p->sample_count, p->seed, ctx->d_accum, ctx->d_ctr));
+    CK(ctx, launch_render_mega(ctx->stream, ctx->dsc, p->mode, p->sample_begin, p->sample_count, p->seed, ctx->d_accum, ctx->d_ctr, rg));
     ++ctx->launches;
     return RT_OK;
 }
@@ -736,6 +742,28 @@ int rt_render(rt_ctx *ctx, uint64_t seed, int mode, int sched, double *rgb_out) 
     p.seed = seed; p.mode = mode; p.sched = sched; p.clear = 1;
     if (int r = rt_render_accum(ctx, &p)) return r;
     return rt_postprocess(ctx, ctx->samples, rgb_out);
+}
+int rt_render_progressive(rt_ctx *ctx, uint64_t seed, int mode, int sched, uint32_t chunk_samples, rt_progress_fn progress,
+                          void *user, double *rgb_out, uint32_t *samples_done) {
+    if (int r = need_scene(ctx)) return r;
+    if (!rgb_out) return set_err(ctx, RT_ERR_INVALID_ARG, "null argument");
+    if (chunk_samples == 0) return set_err(ctx, RT_ERR_INVALID_ARG, "chunk_samples must be positive");
+    const uint32_t total = ctx->samples;
+    uint32_t done = 0;
+    if (samples_done) *samples_done = 0;
+    do {                                            // samples == 0 still clears and tonemaps once, like rt_render
+        rt_render_params p{};
+        p.sample_begin = done;
+        p.sample_count = total - done < chunk_samples ? total - done : chunk_samples;
+        p.seed = seed; p.mode = mode; p.sched = sched; p.clear = done == 0 ? 1 : 0;
+        if (int r = rt_render_accum(ctx, &p)) return r;
+        done += p.sample_count;
+        // the last line of generate_image (src/main.rs:104) divides by the samples taken SO FAR
+        if (int r = rt_postprocess(ctx, done ? done : total, rgb_out)) return r;
+        if (samples_done) *samples_done = done;
+        if (progress && progress(user, done, total, rgb_out) != 0) break;
+    } while (done < total);
+    return RT_OK;
 }
 int rt_debug_rng(rt_ctx *ctx, uint64_t seed, uint32_t pixel, uint32_t sample, uint64_t n, uint64_t *u64_out, double *probe8) {
     if (!ctx || !u64_out || !probe8) return set_err(ctx, RT_ERR_INVALID_ARG, "null argument");

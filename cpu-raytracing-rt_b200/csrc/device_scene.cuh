@@ -109,6 +109,13 @@ struct DScene {
     d3 bg;
 };
 
+// Rectangle of the image one render call covers (tile sharding, previews of a region).  Paths are
+// keyed by the pixel's index in the WHOLE image, so a region renders exactly the values the full
+// image has there.
+struct DRegion {
+    uint32_t x0, y0, w, h;
+};
+
 struct DCounters {                      // mirrors rt_counters (kernel_launches is host-side)
     unsigned long long segments, light_pdf_rays, paths, aabb_tests, prim_tests, light_aabb_tests, light_prim_tests;
 };

@@ -104,10 +104,11 @@ __global__ void __launch_bounds__(128) k_light_pdf(DScene sc, unsigned long long
 // independent of how sample ranges are split across launches or GPUs.
 template <class POLICY>
 __global__ void __launch_bounds__(128) k_render_mega(DScene sc, uint32_t sample_begin, uint32_t sample_count,
-                                                     unsigned long long seed, double *__restrict__ accum, DCounters *ctr) {
+                                                     unsigned long long seed, double *__restrict__ accum, DCounters *ctr, DRegion rg) {
     uint32_t x, y;
     Cnt c;
-    if (tile_pixel(sc.width, sc.height, x, y)) {
+    if (tile_pixel(rg.w, rg.h, x, y)) {
+        x += rg.x0; y += rg.y0;
         const uint32_t p = y * sc.width + x;
         d3 sum = mk3(accum[(size_t)p * 3], accum[(size_t)p * 3 + 1], accum[(size_t)p * 3 + 2]);
         Rng rng;
@@ -196,10 +197,10 @@ cudaError_t launch_light_pdf(cudaStream_t st, const DScene &sc, int mode, uint64
     return cudaGetLastError();
 }
 cudaError_t launch_render_mega(cudaStream_t st, const DScene &sc, int mode, uint32_t sample_begin, uint32_t sample_count,
-                               uint64_t seed, double *accum, DCounters *ctr) {
-    const unsigned n = tile_grid_threads(sc.width, sc.height);
-    if (mode == RT_MODE_FAST) k_render_mega<FastPolicy><<<blocks_for(n, 128), 128, 0, st>>>(sc, sample_begin, sample_count, seed, accum, ctr);
-    else k_render_mega<ExactPolicy><<<blocks_for(n, 128), 128, 0, st>>>(sc, sample_begin, sample_count, seed, accum, ctr);
+                               uint64_t seed, double *accum, DCounters *ctr, DRegion rg) {
+    const unsigned n = tile_grid_threads(rg.w, rg.h);
+    if (mode == RT_MODE_FAST) k_render_mega<FastPolicy><<<blocks_for(n, 128), 128, 0, st>>>(sc, sample_begin, sample_count, seed, accum, ctr, rg);
+    else k_render_mega<ExactPolicy><<<blocks_for(n, 128), 128, 0, st>>>(sc, sample_begin, sample_count, seed, accum, ctr, rg);
     return cudaGetLastError();
 }
 cudaError_t launch_postprocess(cudaStream_t st, uint64_t n, const double *accum, uint32_t samples, double *rgb) {

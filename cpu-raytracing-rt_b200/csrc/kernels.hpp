@@ -15,7 +15,7 @@ cudaError_t launch_trace_primary(cudaStream_t st, const DScene &sc, int mode, do
 cudaError_t launch_light_pdf(cudaStream_t st, const DScene &sc, int mode, uint64_t n, const double *pos, const double *dir,
                              double *pdf, DCounters *ctr);
 cudaError_t launch_render_mega(cudaStream_t st, const DScene &sc, int mode, uint32_t sample_begin, uint32_t sample_count,
-                               uint64_t seed, double *accum, DCounters *ctr);
+                               uint64_t seed, double *accum, DCounters *ctr, DRegion rg);
 // ---- wavefront scheduler (wavefront.cu) ----------------------------------------------------------
 constexpr int kWfCand = 6;              // deferred candidates kept per ray and per search
 struct WfBuf {                          // per-pixel path slots, structure of arrays; n = width * height
@@ -33,7 +33,7 @@ size_t wf_bytes_per_slot();
 int wf_trace_blocks(int device);
 cudaError_t launch_render_wavefront(cudaStream_t st, const DScene &sc, uint32_t sample_begin, uint32_t sample_count,
                                     uint64_t seed, double *accum, DCounters *ctr, const WfBuf &b, volatile uint32_t *host_live,
-                                    cudaEvent_t ev, int trace_blocks, uint64_t *launches);
+                                    cudaEvent_t ev, int trace_blocks, uint64_t *launches, DRegion rg);
 
 cudaError_t launch_postprocess(cudaStream_t st, uint64_t n, const double *accum, uint32_t samples, double *rgb);
 cudaError_t launch_rng_probe(cudaStream_t st, uint64_t seed, uint32_t pixel, uint32_t sample, uint64_t n,

@@ -3,7 +3,8 @@
 //   cpu-raytracing-rt glTF <in.gltf> <W> <H> <spp> <out.ppm>
 // Scene loading and the BVH build run on the host; generate_image (src/main.rs:85) runs on the GPU.
 // Extra, optional environment knobs (not in the reference): RT_SEED, RT_MODE=exact|fast (fast =
-// wavefront scheduler, exact = megakernel parity anchor), RT_DEVICE.
+// wavefront scheduler, exact = megakernel parity anchor), RT_DEVICE, RT_BVH_CACHE=<dir> (on-disk cache
+// of the built hierarchies), RT_PREVIEW=1 (rewrite the output after every chunk of samples).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -16,6 +17,24 @@ static int die(const char *what, rt_ctx *ctx) {
     std::fprintf(stderr, "%s: %s\n", what, rt_last_error(ctx));
     return 101;     // a Rust panic exits with 101
 }
+
+namespace {
+struct Progress {
+    const char *output;
+    uint32_t width, height;
+    bool preview;
+    int last_percent;
+};
+int on_progress(void *user, uint32_t done, uint32_t total, const double *rgb) {
+    Progress *pg = static_cast<Progress *>(user);
+    const int percent = total ? (int)((uint64_t)done * 100 / total) : 100;
+    if (percent != pg->last_percent) std::printf("%d%%\n", percent);
+    pg->last_percent = percent;
+    std::fflush(stdout);
+    if (pg->preview && done < total) rt_save_ppm(pg->output, pg->width, pg->height, rgb);   // best effort
+    return 0;
+}
+}  // namespace
 
 int main(int argc, char **argv) {
     if (argc < 2) { std::puts("You must specify the input format"); return 0; }
@@ -51,23 +70,15 @@ int main(int argc, char **argv) {
     const uint64_t seed = seed_s ? std::strtoull(seed_s, nullptr, 0) : 0xC0FFEEull;
     const int mode = (mode_s && !std::strcmp(mode_s, "exact")) ? RT_MODE_EXACT : RT_MODE_FAST;
     std::vector<double> rgb((size_t)info.width * info.height * 3);
-    // progress lines of the reference (src/main.rs:105-110) at 5% granularity of the SAMPLE range
-    rt_render_params p{};
-    p.seed = seed; p.mode = mode; p.clear = 1;
-    p.sched = mode == RT_MODE_FAST ? RT_SCHED_WAVEFRONT : RT_SCHED_MEGAKERNEL;
-    uint32_t done = 0;
-    for (int step = 1; step <= 20; ++step) {
-        const uint32_t upto = (uint32_t)((uint64_t)info.samples * step / 20);
-        if (upto > done) {
-            p.sample_begin = done; p.sample_count = upto - done;
-            if (rt_render_accum(ctx, &p)) return die("render", ctx);
-            if (rt_sync(ctx)) return die("render", ctx);
-            p.clear = 0;
-            done = upto;
-        }
-        std::printf("%d%%\n", step * 5);
-    }
-    if (rt_postprocess(ctx, info.samples, rgb.data())) return die("postprocess", ctx);
+    // The reference prints "N%" lines while it renders (src/main.rs:105-110) and writes the image
+    // once at the end.  Here the samples are rendered in 20 chunks: one line per chunk, and with
+    // RT_PREVIEW=1 the output file is rewritten after every chunk with the image so far.
+    const char *preview_s = std::getenv("RT_PREVIEW");
+    Progress pg{output, info.width, info.height, preview_s && *preview_s && std::strcmp(preview_s, "0") != 0, 0};
+    const uint32_t chunk = info.samples >= 20 ? (info.samples + 19) / 20 : 1;
+    const int sched = mode == RT_MODE_FAST ? RT_SCHED_WAVEFRONT : RT_SCHED_MEGAKERNEL;
+    if (rt_render_progressive(ctx, seed, mode, sched, chunk, on_progress, &pg, rgb.data(), nullptr)) return die("render", ctx);
+    if (pg.last_percent < 100) std::puts("100%");
     if (rt_save_ppm(output, info.width, info.height, rgb.data())) return die("Cannot create output file", nullptr);
     rt_destroy(ctx);
     rt_scene_free(scene);

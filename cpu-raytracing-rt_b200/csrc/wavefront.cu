@@ -48,14 +48,18 @@ __device__ __forceinline__ void flush_counters_wf(const Cnt &c, DCounters *out) 
     }
 }
 
-__global__ void k_wf_init(WfBuf b) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < b.n) {
-        b.flags[i] = 0;
-        b.sample[i] = 0;
-        b.live[0][i] = i;
+// A slot IS a pixel of the whole image (state arrays, RNG key and accumulation index all use it);
+// a render call restricted to a region simply starts with a live list that holds the region's
+// pixels only, so the other kernels do not know about regions at all.
+__global__ void k_wf_init(WfBuf b, DRegion rg, uint32_t width) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, n = rg.w * rg.h;
+    if (i < n) {
+        const uint32_t ly = i / rg.w, slot = (rg.y0 + ly) * width + rg.x0 + (i - ly * rg.w);
+        b.flags[slot] = 0;
+        b.sample[slot] = 0;
+        b.live[0][i] = slot;
     }
-    if (i == 0) { b.n_live[0] = b.n; b.n_live[1] = 0; *b.cursor = 0; }
+    if (i == 0) { b.n_live[0] = n; b.n_live[1] = 0; *b.cursor = 0; }
 }
 
 // ---- shade -------------------------------------------------------------------------------------
@@ -506,15 +510,16 @@ int wf_trace_blocks(int device) {
 }
 cudaError_t launch_render_wavefront(cudaStream_t st, const DScene &sc, uint32_t sample_begin, uint32_t sample_count,
                                     uint64_t seed, double *accum, DCounters *ctr, const WfBuf &b, volatile uint32_t *host_live,
-                                    cudaEvent_t ev, int trace_blocks, uint64_t *launches) {
-    const unsigned blocks = (b.n + 127) / 128;
-    k_wf_init<<<blocks, 128, 0, st>>>(b);
+                                    cudaEvent_t ev, int trace_blocks, uint64_t *launches, DRegion rg) {
+    const uint32_t n_region = rg.w * rg.h;
+    const unsigned blocks = (n_region + 127) / 128;
+    k_wf_init<<<blocks, 128, 0, st>>>(b, rg, sc.width);
     ++*launches;
     const uint64_t max_iters = (uint64_t)sample_count * (sc.ray_depth ? sc.ray_depth : 1) + 2;
     bool poll_pending = false;
     // scenes without planes / boxes / ellipsoids (every glTF scene) run the kernel compiled without them
     const bool shapes = sc.n_planes || sc.boxes.n_prims || sc.ellipsoids.n_prims || sc.lboxes.n_prims || sc.lellipsoids.n_prims;
-    const uint32_t tail_threshold = b.n / 16 + 1;       // below this many live slots, finish in one kernel
+    const uint32_t tail_threshold = n_region / 16 + 1;       // below this many live slots, finish in one kernel
     // One iteration = 2 memset nodes + shade + trace; four iterations (ending on the list they
     // started from) are captured ONCE into a CUDA graph and replayed, so the host issues one launch
     // per four iterations instead of sixteen — the inner loop is launch-bound on small images and

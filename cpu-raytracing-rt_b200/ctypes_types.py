@@ -62,7 +62,10 @@ class Hit(C.Structure):
 class RenderParams(C.Structure):
     _fields_ = [("sample_begin", C.c_uint32), ("sample_count", C.c_uint32), ("seed", C.c_uint64),
                 ("mode", C.c_int32), ("sched", C.c_int32), ("clear", C.c_int32),
-                ("_pad", C.c_int32)]
+                ("_pad", C.c_int32), ("region", C.c_uint32 * 4)]
+
+
+ProgressFn = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_double))
 
 
 class Counters(C.Structure):

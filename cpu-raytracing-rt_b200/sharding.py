@@ -25,6 +25,24 @@ def step_sample_range(rank, world, step, spp_per_step):
     return (step * world + rank) * spp_per_step, spp_per_step
 
 
+def row_band(rank, world, width, height, align=4):
+    """Tile sharding (the other partition north_star names): rank r renders a band of whole rows at
+    the full sample count.  Returns the region (x0, y0, w, h) for Context.render_accum, or None
+    when there are more ranks than row groups.  Bands are `align` rows granular (a warp of the
+    megakernel covers 8x4 pixels).  The bands are disjoint and every rank's buffer is zero outside
+    its band, so the same sum-reduce assembles the image — bit for bit the single-GPU one, since no
+    pixel receives two contributions.  Load balance is what it costs: a band of sky finishes long
+    before a band of terrain, which is why samples are the default partition."""
+    if not 0 <= rank < world:
+        raise ValueError("rank out of range")
+    groups = (height + align - 1) // align
+    g0, gn = sample_range(rank, world, groups)
+    if gn == 0:
+        return None
+    y0 = g0 * align
+    return 0, y0, width, min(height, (g0 + gn) * align) - y0
+
+
 def reduce_accum(accum, dst=0, group=None):
     """Sum-reduce the accumulation buffers onto `dst` (in place on dst).  `accum` is a torch tensor
     viewing the library's device buffer (NCCL) or any CPU tensor (gloo in the tests).  Must run

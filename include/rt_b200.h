@@ -238,6 +238,12 @@ typedef struct rt_render_params {
     int32_t  sched;                 /* RT_SCHED_*                                          */
     int32_t  clear;                 /* 1: zero the accumulation buffer first               */
     int32_t  _pad;
+    uint32_t region[4];             /* x0, y0, w, h of the pixels to render (tile sharding,
+                                       region previews); w == 0 or h == 0: the whole image.
+                                       Paths stay keyed by the pixel's index in the whole image:
+                                       a region gets bit for bit the values the full render
+                                       has there, the rest of the accumulation buffer is left
+                                       untouched                                            */
 } rt_render_params;
 
 /* The pixel loop of generate_image without its last line: accum[p] += Σ_samples raytrace(...)
@@ -255,6 +261,18 @@ RT_API int rt_postprocess(rt_ctx *ctx, uint32_t total_samples, double *rgb_out);
 /* generate_image (src/main.rs:85-114) in one call: clear, accumulate scene.samples samples,
  * postprocess, copy to host. */
 RT_API int rt_render(rt_ctx *ctx, uint64_t seed, int mode, int sched, double *rgb_out);
+
+/* generate_image in chunks of `chunk_samples` samples per pixel, with the image so far after every
+ * chunk (the reference only prints "N%" lines, src/main.rs:106-110, and
+ * writes once at the end).  After each chunk the accumulation buffer is tonemapped for the samples
+ * done so far into rgb_out and `progress(user, samples_done, samples_total, rgb_out)` is called;
+ * a non-zero return stops the render there (rgb_out then holds the image of samples_done samples,
+ * RT_OK is returned).  progress may be NULL.  Sample s of a pixel is the same path whatever the
+ * chunking, and sums are taken in sample order: the final image is bit for bit rt_render's.
+ * *samples_done (may be NULL) receives the number of samples in rgb_out. */
+typedef int (*rt_progress_fn)(void *user, uint32_t samples_done, uint32_t samples_total, const double *rgb);
+RT_API int rt_render_progressive(rt_ctx *ctx, uint64_t seed, int mode, int sched, uint32_t chunk_samples,
+                                 rt_progress_fn progress, void *user, double *rgb_out, uint32_t *samples_done);
 RT_API int rt_sync(rt_ctx *ctx);
 /* CUDA stream handle (cudaStream_t) the context launches on, for event timing by the caller. */
 RT_API int rt_stream(rt_ctx *ctx, void **stream);

@@ -75,7 +75,13 @@ pub struct rt_render_params {
     pub sched: i32,
     pub clear: i32,
     pub _pad: i32,
+    /// x0, y0, w, h of the pixels to render; w == 0 or h == 0: the whole image
+    pub region: [u32; 4],
 }
+
+/// Called by `rt_render_progressive` after every chunk of samples; non-zero return stops the render.
+pub type rt_progress_fn =
+    Option<unsafe extern "C" fn(user: *mut c_void, samples_done: u32, samples_total: u32, rgb: *const f64) -> c_int>;
 
 #[repr(C)]
 pub struct rt_built_bvh {
@@ -133,5 +139,8 @@ extern "C" {
     pub fn rt_set_accum(ctx: *mut rt_ctx, sum_rgb: *const f64) -> c_int;
     pub fn rt_postprocess(ctx: *mut rt_ctx, total_samples: u32, rgb_out: *mut f64) -> c_int;
     pub fn rt_render(ctx: *mut rt_ctx, seed: u64, mode: c_int, sched: c_int, rgb_out: *mut f64) -> c_int;
+    pub fn rt_render_progressive(ctx: *mut rt_ctx, seed: u64, mode: c_int, sched: c_int, chunk_samples: u32,
+                                 progress: rt_progress_fn, user: *mut c_void, rgb_out: *mut f64, samples_done: *mut u32) -> c_int;
+    pub fn rt_scene_build_cached(raw: *const rt_raw_scene, cache_dir: *const c_char, out: *mut *mut rt_scene, cache_hit: *mut c_int) -> c_int;
     pub fn rt_sync(ctx: *mut rt_ctx) -> c_int;
 }

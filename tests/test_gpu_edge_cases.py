@@ -146,3 +146,51 @@ def test_cached_scene_renders_identically(orc, ctx, tmp_path):
     ctx.render_accum(0, 3, 23, T.MODE_FAST, T.SCHED_WAVEFRONT, clear=True)
     want = ctx.accum()
     assert images[0].tobytes() == want.tobytes() == images[1].tobytes() and want.sum() > 0
+
+
+@pytest.mark.parametrize("sched", [T.SCHED_MEGAKERNEL, T.SCHED_WAVEFRONT])
+def test_region_render_equals_the_full_render_there(ctx, tmp_path, sched):
+    """Tile sharding: a render restricted to a rectangle writes bit for bit what the full render
+    has in that rectangle and leaves the rest of the buffer alone; disjoint row bands (what
+    sharding.row_band hands to the ranks) assemble the whole image."""
+    from rtb200 import sharding
+    from tests import helpers
+    path = helpers.cornell(tmp_path, 45, 38, 3, 5)          # odd sizes: partial 8x4 tiles, w != W
+    sc = rtb200.Scene.load_text(path)
+    ctx.upload(sc)
+    ctx.render_accum(0, 3, 99, T.MODE_FAST, sched, clear=True)
+    full = ctx.accum()
+    x0, y0, w, h = 7, 5, 21, 19
+    ctx.render_accum(0, 3, 99, T.MODE_FAST, sched, clear=True, region=(x0, y0, w, h))
+    part = ctx.accum()
+    assert part[y0:y0 + h, x0:x0 + w].tobytes() == full[y0:y0 + h, x0:x0 + w].tobytes()
+    outside = part.copy()
+    outside[y0:y0 + h, x0:x0 + w] = 0
+    assert not outside.any() and part.any()
+    ctx.render_accum(0, 0, 99, T.MODE_FAST, sched, clear=True)
+    for rank in range(3):
+        ctx.render_accum(0, 3, 99, T.MODE_FAST, sched, region=sharding.row_band(rank, 3, 45, 38))
+    assert ctx.accum().tobytes() == full.tobytes()
+    with pytest.raises(rtb200.RtError):
+        ctx.render_accum(0, 1, 99, T.MODE_FAST, sched, region=(40, 0, 10, 10))
+
+
+def test_progressive_render(ctx, tmp_path):
+    """rt_render_progressive: the callback sees the image of the samples done so far (== a render
+    of that many samples), the final image is render()'s, and a truthy return stops early."""
+    from tests import helpers
+    path = helpers.cornell(tmp_path, 32, 24, 7, 4)
+    ctx.upload(rtb200.Scene.load_text(path))
+    want = ctx.render(seed=5)
+    seen = []
+    rgb, done = ctx.render_progressive(3, lambda d, t, img: seen.append((d, t, img.copy())) and False, seed=5)
+    assert done == 7 and [s[:2] for s in seen] == [(3, 7), (6, 7), (7, 7)]
+    assert rgb.tobytes() == want.tobytes() == seen[-1][2].tobytes()
+    ctx.render_accum(0, 3, 5, clear=True)
+    assert ctx.postprocess(3).tobytes() == seen[0][2].tobytes()
+    rgb2, done2 = ctx.render_progressive(3, lambda d, t, img: d >= 6, seed=5)
+    assert done2 == 6 and rgb2.tobytes() == seen[1][2].tobytes()
+    with pytest.raises(ZeroDivisionError):                   # exceptions come back out, after the C call returned
+        ctx.render_progressive(3, lambda d, t, img: 1 // 0, seed=5)
+    with pytest.raises(rtb200.RtError):
+        ctx.render_progressive(0, None, seed=5)

@@ -63,3 +63,21 @@ def test_two_rank_reduce_equals_single_rank(orc, tmp_path):
     np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-300)
     # and the tonemapped image agrees
     np.testing.assert_allclose(orc.postprocess(got, 6), orc.postprocess(want, 6), rtol=1e-12, atol=1e-15)
+
+
+def test_row_bands_partition_the_image():
+    """Tile sharding: the bands are disjoint, 4-row granular and cover every row exactly once."""
+    from rtb200 import sharding
+    for height in (1, 3, 4, 38, 1080, 2160):
+        for world in (1, 2, 3, 8):
+            rows = []
+            for rank in range(world):
+                r = sharding.row_band(rank, world, 100, height)
+                if r is None:
+                    continue
+                x0, y0, w, h = r
+                assert (x0, w) == (0, 100) and h > 0 and y0 % 4 == 0
+                rows += list(range(y0, y0 + h))
+            assert rows == list(range(height)), (height, world)
+    with pytest.raises(ValueError):
+        sharding.row_band(2, 2, 10, 10)
