@@ -25,6 +25,8 @@ struct WfBuf {                          // per-pixel path slots, structure of ar
     uint32_t *sh_id, *rng_block, *rng_s0, *rng_s1, *sample, *flags, *ncand;    // n
     uint32_t *cand, *lcand;             // kWfCand * n: triangle candidates (scene / lights)
     float *cand_t;                      // kWfCand * n: lower bound of each scene candidate's distance
+    double *res_t, *res_u, *res_v;      // kWfCand * n: k_wf_confirm's exact (t, u, v) per scene candidate; u == -1: no hit
+    double *lres;                       // kWfCand * n: exact Light::pdf term per light candidate; -1: no hit
     uint32_t *live[2];                  // n each: compacted indices of slots with work
     uint32_t *n_live;                   // [2]
     uint32_t *cursor;                   // trace kernel's fetch position in the live list

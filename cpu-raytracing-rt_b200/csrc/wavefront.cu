@@ -62,6 +62,86 @@ __global__ void k_wf_init(WfBuf b, DRegion rg, uint32_t width) {
     if (i == 0) { b.n_live[0] = n; b.n_live[1] = 0; *b.cursor = 0; }
 }
 
+// ---- confirm -----------------------------------------------------------------------------------
+// The exact f64 test of every deferred candidate (the reference's Triangle::intersection, ~400
+// instructions with its nine divisions) as a kernel of its own, one (ray, candidate) PAIR per
+// thread: a ray has 0..6 scene candidates and 0..6 light candidates, so a loop per ray runs with a
+// third of the lanes; here a block gathers the pairs of its 128 rays with a prefix sum and deals
+// them out evenly.  Results go to per-slot arrays in list order; the shade kernel only folds them
+// (minimum for the scene, ordered sum for the lights), so the values are bit for bit the same.
+#ifndef WF_SPLIT_CONFIRM
+#define WF_SPLIT_CONFIRM 1
+#endif
+#ifndef WF_CONFIRM_MINB
+#define WF_CONFIRM_MINB 8
+#endif
+__global__ void __launch_bounds__(128, WF_CONFIRM_MINB) k_wf_confirm(DScene sc, WfBuf b, int list) {
+    __shared__ uint32_t s_slot[128];
+    __shared__ uint16_t s_pair[128 * 2 * kWfCand];
+    __shared__ uint32_t s_warp[4];
+    __shared__ double s_ray[6][128];
+    const uint32_t tid = threadIdx.x, i = blockIdx.x * 128 + tid, lane = tid & 31, wid = tid >> 5;
+    const uint32_t n_live = b.n_live[list], N = b.n;
+    uint32_t slot = 0, nc = 0, nl = 0;
+    if (i < n_live) {
+        slot = b.live[list][i];
+        const uint32_t flags = b.flags[slot];
+        if (flags & kFlagAlive) {                       // not alive: nothing was traced for this slot
+            const uint32_t nc_all = b.ncand[slot];
+            nc = (nc_all & kOverflowClosest) ? 0u : (nc_all & 0xFFu);       // overflowed lists: the shade kernel redoes the search
+            nl = ((nc_all & kOverflowLight) || !(flags & kFlagPendLight)) ? 0u : ((nc_all >> 8) & 0xFFu);
+            if (nc + nl) {
+                const d3 o = ld_soa(b.ro, N, slot), d = ld_soa(b.rd, N, slot);
+                s_ray[0][tid] = o.x; s_ray[1][tid] = o.y; s_ray[2][tid] = o.z;
+                s_ray[3][tid] = d.x; s_ray[4][tid] = d.y; s_ray[5][tid] = d.z;
+            }
+        }
+    }
+    s_slot[tid] = slot;
+    // exclusive prefix sum of the pair counts over the block
+    uint32_t incl = nc + nl;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t v = __shfl_up_sync(kFull, incl, off);
+        if ((int)lane >= off) incl += v;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    uint32_t base = incl - (nc + nl), total = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < 4; ++w) {
+        const uint32_t v = s_warp[w];
+        if (w < wid) base += v;
+        total += v;
+    }
+    for (uint32_t k = 0; k < nl; ++k) s_pair[base + k] = (uint16_t)(tid | (k << 7) | 0x400u);
+    for (uint32_t k = 0; k < nc; ++k) s_pair[base + nl + k] = (uint16_t)(tid | (k << 7));
+    __syncthreads();
+    for (uint32_t e = tid; e < total; e += 128) {
+        const uint32_t pr = s_pair[e], owner = pr & 127u, k = (pr >> 7) & 7u;
+        const bool light = (pr & 0x400u) != 0;
+        const size_t at = (size_t)k * N + s_slot[owner];
+        const d3 o = mk3(s_ray[0][owner], s_ray[1][owner], s_ray[2][owner]);
+        const d3 d = mk3(s_ray[3][owner], s_ray[4][owner], s_ray[5][owner]);
+        const uint32_t prim = light ? b.lcand[at] : b.cand[at];
+        double t, u, v;
+        const bool hit = tri_exact((light ? sc.ltri_i : sc.tri_i) + prim, o, d, t, u, v);
+        if (light) {
+            double term = -1.0;
+            if (hit) {                                  // the term of light_confirm (ray_sampler.rs:135-137)
+                const double2 *p = reinterpret_cast<const double2 *>(sc.ltri_s + prim);
+                const double2 q0 = __ldg(p), q1 = __ldg(p + 1);
+                const double inv_area = __ldg(&sc.ltri_s[prim].inv_area);
+                term = inv_area * (t * t / fabs(dot3(d, mk3(q0.x, q0.y, q1.x))));
+            }
+            b.lres[at] = term;
+        } else {
+            b.res_u[at] = hit ? u : -1.0;
+            if (hit) { b.res_t[at] = t; b.res_v[at] = v; }
+        }
+    }
+}
+
 // ---- shade -------------------------------------------------------------------------------------
 // Candidate-list overflow is rare (never on the bench scene): its full searches are kept out of
 // line so that they do not sit in the instruction stream of the hot path.
@@ -71,8 +151,11 @@ static __device__ __noinline__ void closest_fast_cold(const FBvh f, const DTriI 
 static __device__ __noinline__ void light_hits_fast_cold(const FBvh f, const DTriI *tri_i, const DTriS *tri_s, d3 o, d3 d, double &impact) {
     light_hits_fast(f, tri_i, tri_s, o, d, impact);
 }
+#ifndef WF_SHADE_MINB
+#define WF_SHADE_MINB 4
+#endif
 template <bool SHAPES>
-__global__ void __launch_bounds__(128) k_wf_shade(DScene sc, WfBuf b, int cur_list, uint32_t sample_begin, uint32_t sample_count,
+__global__ void __launch_bounds__(128, WF_SHADE_MINB) k_wf_shade(DScene sc, WfBuf b, int cur_list, uint32_t sample_begin, uint32_t sample_count,
                                                   unsigned long long seed, double *__restrict__ accum, DCounters *ctr) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_live = b.n_live[cur_list], N = b.n;
@@ -103,7 +186,16 @@ __global__ void __launch_bounds__(128) k_wf_shade(DScene sc, WfBuf b, int cur_li
                     light_hits_fast_cold(sc.fltris, sc.ltri_i, sc.ltri_s, o, d, impact);
                 } else {
                     const uint32_t nl = (nc_all >> 8) & 0xFFu;
+#if WF_SPLIT_CONFIRM
+                    // k_wf_confirm has evaluated the terms; they are summed here in list order
+                    // (= the reference's DFS order, bvh.rs:188-210)
+                    for (uint32_t k = 0; k < nl; ++k) {
+                        const double term = b.lres[k * N + slot];
+                        if (term != -1.0) impact += term;
+                    }
+#else
                     for (uint32_t k = 0; k < nl; ++k) light_confirm(sc.ltri_i, sc.ltri_s, o, d, b.lcand[k * N + slot], impact);
+#endif
                 }
                 pd.v = ld_soa(b.pv, N, slot);
                 pd.cos_pdf = b.pcos[slot];
@@ -123,8 +215,22 @@ __global__ void __launch_bounds__(128) k_wf_shade(DScene sc, WfBuf b, int cur_li
                         closest_fast_cold(sc.ftris, sc.tri_i, o, d, tmax, fb);
                     } else {
                         const uint32_t nc = nc_all & 0xFFu;
+#if WF_SPLIT_CONFIRM
+                        for (uint32_t k = 0; k < nc; ++k) {
+                            const double u = b.res_u[k * N + slot];
+                            if (u != -1.0) {                // same rule as confirm(): nearest, then lowest primitive index
+                                const double t = b.res_t[k * N + slot];
+                                const uint32_t prim = b.cand[k * N + slot];
+                                if (!fb.has || t < fb.t || (t == fb.t && prim < fb.prim)) {
+                                    fb.has = true; fb.t = t; fb.u = u; fb.v = b.res_v[k * N + slot]; fb.prim = prim;
+                                }
+                            }
+                        }
+                        (void)tmax;
+#else
                         for (uint32_t k = 0; k < nc; ++k)
                             if (b.cand_t[k * N + slot] <= tmax) confirm(sc.tri_i, o, d, b.cand[k * N + slot], fb, tmax);
+#endif
                     }
                 }
                 const SceneHit h = finish_hit<SHAPES>(sc, o, d, sb, fb);
@@ -501,7 +607,7 @@ __global__ void __launch_bounds__(128) k_wf_finish(DScene sc, WfBuf b, int list,
 }
 
 // ---- host loop -----------------------------------------------------------------------------------
-size_t wf_bytes_per_slot() { return 15 * 8 + 3 * 8 + 7 * 4 + kWfCand * 12 + 2 * 4; }
+size_t wf_bytes_per_slot() { return 15 * 8 + 3 * 8 + 7 * 4 + kWfCand * 12 + kWfCand * 32 + 2 * 4; }
 int wf_trace_blocks(int device) {
     int sms = 148, per_sm = 4;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -527,6 +633,9 @@ cudaError_t launch_render_wavefront(cudaStream_t st, const DScene &sc, uint32_t 
     auto issue_iteration = [&](int from) {
         cudaMemsetAsync(&b.n_live[from ^ 1], 0, sizeof(uint32_t), st);      // next list starts empty
         cudaMemsetAsync(b.cursor, 0, sizeof(uint32_t), st);                  // trace fetch position
+#if WF_SPLIT_CONFIRM
+        k_wf_confirm<<<blocks, 128, 0, st>>>(sc, b, from);
+#endif
         if (shapes) k_wf_shade<true><<<blocks, 128, 0, st>>>(sc, b, from, sample_begin, sample_count, seed, accum, ctr);
         else k_wf_shade<false><<<blocks, 128, 0, st>>>(sc, b, from, sample_begin, sample_count, seed, accum, ctr);
         k_wf_trace<<<trace_blocks, 128, 0, st>>>(sc, b, from ^ 1, ctr);
@@ -547,7 +656,7 @@ cudaError_t launch_render_wavefront(cudaStream_t st, const DScene &sc, uint32_t 
         } else {
             for (int k = 0; k < 4; ++k) issue_iteration(k & 1);
         }
-        *launches += 8;
+        *launches += WF_SPLIT_CONFIRM ? 12 : 8;
         // four iterations end on list 0 again; poll its live count without stalling the stream
         if (poll_pending) {
             result = cudaEventSynchronize(ev);

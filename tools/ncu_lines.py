@@ -41,3 +41,6 @@ for f, v in sorted(ftot.items(), key=lambda kv: -kv[1][0]):
 print("top lines by issued instructions:")
 for (f, line), v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
     print(f"  {f}:{line:<4d} {100*v[0]/tot:5.2f}% lanes {v[1]/max(1,v[0]):5.1f} smp {100*v[2]/tots:5.2f}%  {v[3]}")
+print("top lines by stall samples:")
+for (f, line), v in sorted(agg.items(), key=lambda kv: -kv[1][2])[:top]:
+    print(f"  {f}:{line:<4d} smp {100*v[2]/tots:5.2f}% inst {100*v[0]/tot:5.2f}% lanes {v[1]/max(1,v[0]):5.1f}  {v[3]}")
