@@ -99,11 +99,11 @@ cudaError_t ensure_wavefront(rt_ctx *ctx) {
     for (double **q : res) *q = (double *)take((size_t)n * 8 * kWfCand);
     b.live[0] = (uint32_t *)take((size_t)n * 4);
     b.live[1] = (uint32_t *)take((size_t)n * 4);
-    b.n_live = (uint32_t *)take(8);
+    b.n_live = (uint32_t *)take(16);
     b.cursor = (uint32_t *)take(4);
     if ((size_t)(p - ctx->wf_arena) > total) return cudaErrorMemoryAllocation;
     if (!ctx->wf_host_live) {
-        e = cudaHostAlloc((void **)&ctx->wf_host_live, sizeof(uint32_t), cudaHostAllocDefault);
+        e = cudaHostAlloc((void **)&ctx->wf_host_live, 2 * sizeof(uint32_t), cudaHostAllocDefault);
         if (e != cudaSuccess) return e;
         e = cudaEventCreateWithFlags(&ctx->wf_event, cudaEventDisableTiming);
         if (e != cudaSuccess) return e;

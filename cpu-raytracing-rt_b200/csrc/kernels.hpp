@@ -28,7 +28,7 @@ struct WfBuf {                          // per-pixel path slots, structure of ar
     double *res_t, *res_u, *res_v;      // kWfCand * n: k_wf_confirm's exact (t, u, v) per scene candidate; u == -1: no hit
     double *lres;                       // kWfCand * n: exact Light::pdf term per light candidate; -1: no hit
     uint32_t *live[2];                  // n each: compacted indices of slots with work
-    uint32_t *n_live;                   // [2]
+    uint32_t *n_live;                   // [4]: per list, entries filled from the front / from the back (8-byte aligned pairs)
     uint32_t *cursor;                   // trace kernel's fetch position in the live list
 };
 size_t wf_bytes_per_slot();

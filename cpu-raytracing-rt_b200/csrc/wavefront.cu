@@ -51,6 +51,25 @@ __device__ __forceinline__ void flush_counters_wf(const Cnt &c, DCounters *out) 
 // A slot IS a pixel of the whole image (state arrays, RNG key and accumulation index all use it);
 // a render call restricted to a region simply starts with a live list that holds the region's
 // pixels only, so the other kernels do not know about regions at all.
+// A live list is filled from BOTH ends: slots whose ray is a fresh camera ray go to the front,
+// slots in the middle of a path to the back.  Consumers walk front then back, so the warps of
+// the trace kernel get runs of neighbouring primary rays (which visit the same nodes) instead of
+// a mixture of primary and bounced rays, and the shade kernel's warps see similar hits.
+// n_live[2 * list] = entries at the front, n_live[2 * list + 1] = entries at the back.
+struct LiveList {
+    const uint32_t *p;
+    uint32_t nf, n, last;
+    RT_D uint32_t at(uint32_t i) const { return p[i < nf ? i : last - (i - nf)]; }
+};
+RT_D LiveList live_list(const WfBuf &b, int list) {
+    LiveList l;
+    l.p = b.live[list];
+    l.nf = b.n_live[2 * list];
+    l.n = l.nf + b.n_live[2 * list + 1];
+    l.last = b.n - 1u;
+    return l;
+}
+
 __global__ void k_wf_init(WfBuf b, DRegion rg, uint32_t width) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, n = rg.w * rg.h;
     if (i < n) {
@@ -59,7 +78,7 @@ __global__ void k_wf_init(WfBuf b, DRegion rg, uint32_t width) {
         b.sample[slot] = 0;
         b.live[0][i] = slot;
     }
-    if (i == 0) { b.n_live[0] = n; b.n_live[1] = 0; *b.cursor = 0; }
+    if (i == 0) { b.n_live[0] = n; b.n_live[1] = 0; b.n_live[2] = 0; b.n_live[3] = 0; *b.cursor = 0; }
 }
 
 // ---- confirm -----------------------------------------------------------------------------------
@@ -81,10 +100,11 @@ __global__ void __launch_bounds__(128, WF_CONFIRM_MINB) k_wf_confirm(DScene sc, 
     __shared__ uint32_t s_warp[4];
     __shared__ double s_ray[6][128];
     const uint32_t tid = threadIdx.x, i = blockIdx.x * 128 + tid, lane = tid & 31, wid = tid >> 5;
-    const uint32_t n_live = b.n_live[list], N = b.n;
+    const LiveList ll = live_list(b, list);
+    const uint32_t N = b.n;
     uint32_t slot = 0, nc = 0, nl = 0;
-    if (i < n_live) {
-        slot = b.live[list][i];
+    if (i < ll.n) {
+        slot = ll.at(i);
         const uint32_t flags = b.flags[slot];
         if (flags & kFlagAlive) {                       // not alive: nothing was traced for this slot
             const uint32_t nc_all = b.ncand[slot];
@@ -158,14 +178,14 @@ template <bool SHAPES>
 __global__ void __launch_bounds__(128, WF_SHADE_MINB) k_wf_shade(DScene sc, WfBuf b, int cur_list, uint32_t sample_begin, uint32_t sample_count,
                                                   unsigned long long seed, double *__restrict__ accum, DCounters *ctr) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t n_live = b.n_live[cur_list], N = b.n;
-    const uint32_t *__restrict__ live = b.live[cur_list];
+    const LiveList ll = live_list(b, cur_list);
+    const uint32_t N = b.n;
     uint32_t *__restrict__ next_live = b.live[cur_list ^ 1];
     Cnt c;
-    bool keep = false;
+    bool keep = false, fresh = false;
     uint32_t slot = 0;
-    if (i < n_live) {
-        slot = live[i];
+    if (i < ll.n) {
+        slot = ll.at(i);
         uint32_t flags = b.flags[slot], s = b.sample[slot];
         Rng rng;
         rng.init(seed, slot, sample_begin + s);
@@ -264,6 +284,7 @@ __global__ void __launch_bounds__(128, WF_SHADE_MINB) k_wf_shade(DScene sc, WfBu
                 L = mk3(0.0, 0.0, 0.0);
                 left = sc.ray_depth;
                 pend_light = false;
+                fresh = true;
             }
         }
         if (alive) {                                    // hand the ray to the trace kernel
@@ -292,41 +313,23 @@ __global__ void __launch_bounds__(128, WF_SHADE_MINB) k_wf_shade(DScene sc, WfBu
             b.sample[slot] = s;
         }
     }
-#if WF_OCTANT_BIN
-    // stream compaction of the live slots, grouped by direction octant inside the block: rays that
-    // a trace warp picks up together then choose the same near / far planes at every node
-    __shared__ uint32_t s_cnt[8][4];
-    __shared__ uint32_t s_base;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const uint32_t oct = keep ? ((b.rd[slot] < 0.0 ? 1u : 0u) | (b.rd[N + slot] < 0.0 ? 2u : 0u) | (b.rd[2u * N + slot] < 0.0 ? 4u : 0u)) : 8u;
-    uint32_t rank = 0;
-#pragma unroll
-    for (uint32_t q = 0; q < 8; ++q) {
-        const unsigned mq = __ballot_sync(kFull, oct == q);
-        if (lane == 0) s_cnt[q][wid] = __popc(mq);
-        if (oct == q) rank = __popc(mq & ((1u << lane) - 1u));
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t tot = 0;
-        for (int q = 0; q < 8; ++q)
-            for (int w = 0; w < 4; ++w) { const uint32_t v = s_cnt[q][w]; s_cnt[q][w] = tot; tot += v; }
-        s_base = tot ? atomicAdd(&b.n_live[cur_list ^ 1], tot) : 0u;
-    }
-    __syncthreads();
-    if (keep) next_live[s_base + s_cnt[oct][wid] + rank] = slot;
-#else
-    // stream compaction of the live slots: ballot + prefix sum inside the warp, one atomic per warp
+    // stream compaction of the live slots: ballot + prefix sum inside the warp, one 64-bit atomic
+    // per warp reserves room at both ends of the next list (front: fresh camera rays, back: the rest)
     __syncwarp();
-    const unsigned m = __ballot_sync(kFull, keep);
-    if (m) {
-        const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-        uint32_t base = 0;
-        if (lane == leader) base = atomicAdd(&b.n_live[cur_list ^ 1], (uint32_t)__popc(m));
-        base = __shfl_sync(kFull, base, leader);
-        if (keep) next_live[base + __popc(m & ((1u << lane) - 1u))] = slot;
+    const unsigned mf = __ballot_sync(kFull, keep && fresh), mb = __ballot_sync(kFull, keep && !fresh);
+    if (mf | mb) {
+        const int lane = threadIdx.x & 31;
+        unsigned long long base = 0;
+        if (lane == 0)
+            base = atomicAdd(reinterpret_cast<unsigned long long *>(b.n_live + 2 * (cur_list ^ 1)),
+                             (unsigned long long)__popc(mf) | ((unsigned long long)__popc(mb) << 32));
+        base = __shfl_sync(kFull, base, 0);
+        const unsigned below = (1u << lane) - 1u;
+        if (keep) {
+            if (fresh) next_live[(uint32_t)base + __popc(mf & below)] = slot;
+            else next_live[N - 1u - ((uint32_t)(base >> 32) + __popc(mb & below))] = slot;
+        }
     }
-#endif
     flush_counters_wf(c, ctr);
 }
 
@@ -348,9 +351,6 @@ __global__ void __launch_bounds__(128, WF_SHADE_MINB) k_wf_shade(DScene sc, WfBu
 #define WF_VOTE_I 1            // the INNER step runs when WF_VOTE_I * (#lanes at a node) >= WF_VOTE_T * (#lanes at a leaf)
 #define WF_VOTE_T 1
 #endif
-#ifndef WF_OCTANT_BIN
-#define WF_OCTANT_BIN 0          // measured on B200 (C3): 1096.5 Mseg/s with the grouping, 1096-1099 without
-#endif
 #ifndef WF_REFILL
 #define WF_REFILL 8
 #endif
@@ -360,8 +360,8 @@ __global__ void __launch_bounds__(128, WF_SHADE_MINB) k_wf_shade(DScene sc, WfBu
 constexpr int kRefillLanes = WF_REFILL;  // refill once this many lanes are idle
 
 __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, WfBuf b, int list, DCounters *ctr) {
-    const uint32_t n = b.n_live[list], N = b.n;
-    const uint32_t *__restrict__ live = b.live[list];
+    const LiveList ll = live_list(b, list);
+    const uint32_t n = ll.n, N = b.n;
     const int lane = threadIdx.x & 31;
     const float inf = __int_as_float(0x7F800000);
 #if WF_SMEM_TOP
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
                 if (!has) {
                     const uint32_t idx = base + __popc(idle & ((1u << lane) - 1u));
                     if (idx < n) {
-                        slot = live[idx];
+                        slot = ll.at(idx);
                         const d3 o = ld_soa(b.ro, N, slot), dd = ld_soa(b.rd, N, slot);
                         my_ray[0] = o.x; my_ray[128] = o.y; my_ray[256] = o.z;
                         my_ray[384] = dd.x; my_ray[512] = dd.y; my_ray[640] = dd.z;
@@ -554,10 +554,11 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
 __global__ void __launch_bounds__(128) k_wf_finish(DScene sc, WfBuf b, int list, uint32_t sample_begin, uint32_t sample_count,
                                                    unsigned long long seed, double *__restrict__ accum, DCounters *ctr) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t n_live = b.n_live[list], N = b.n;
+    const LiveList ll = live_list(b, list);
+    const uint32_t N = b.n;
     Cnt c;
-    if (i < n_live) {
-        const uint32_t slot = b.live[list][i];
+    if (i < ll.n) {
+        const uint32_t slot = ll.at(i);
         const uint32_t flags = b.flags[slot];
         uint32_t s = b.sample[slot], left = (flags >> 8) & 0xFFu;
         Rng rng;
@@ -631,7 +632,7 @@ cudaError_t launch_render_wavefront(cudaStream_t st, const DScene &sc, uint32_t 
     // per four iterations instead of sixteen — the inner loop is launch-bound on small images and
     // in the last iterations of every render.
     auto issue_iteration = [&](int from) {
-        cudaMemsetAsync(&b.n_live[from ^ 1], 0, sizeof(uint32_t), st);      // next list starts empty
+        cudaMemsetAsync(&b.n_live[2 * (from ^ 1)], 0, 2 * sizeof(uint32_t), st);   // next list starts empty
         cudaMemsetAsync(b.cursor, 0, sizeof(uint32_t), st);                  // trace fetch position
 #if WF_SPLIT_CONFIRM
         k_wf_confirm<<<blocks, 128, 0, st>>>(sc, b, from);
@@ -644,7 +645,7 @@ cudaError_t launch_render_wavefront(cudaStream_t st, const DScene &sc, uint32_t 
     cudaGraphExec_t exec = nullptr;
     bool use_graph = false;
     if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-        for (int k = 0; k < 4; ++k) issue_iteration(k & 1);
+        for (int k = 0; k < 4; ++k) issue_iteration(0);
         if (cudaStreamEndCapture(st, &graph) == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) use_graph = true;
     }
     if (!use_graph) cudaGetLastError();             // fall back to plain launches (same kernels, same order)
@@ -654,22 +655,23 @@ cudaError_t launch_render_wavefront(cudaStream_t st, const DScene &sc, uint32_t 
             result = cudaGraphLaunch(exec, st);
             if (result != cudaSuccess) break;
         } else {
-            for (int k = 0; k < 4; ++k) issue_iteration(k & 1);
+            for (int k = 0; k < 4; ++k) issue_iteration(0);
         }
         *launches += WF_SPLIT_CONFIRM ? 12 : 8;
         // four iterations end on list 0 again; poll its live count without stalling the stream
         if (poll_pending) {
             result = cudaEventSynchronize(ev);
             if (result != cudaSuccess) break;
-            if (*host_live == 0) break;
-            if (*host_live < tail_threshold) {
+            const uint32_t n_left = host_live[0] + host_live[1];       // front + back of list 0
+            if (n_left == 0) break;
+            if (n_left < tail_threshold) {
                 // few slots left: finish them in one kernel (the count can only have shrunk since)
-                k_wf_finish<<<(tail_threshold + 127) / 128, 128, 0, st>>>(sc, b, 0, sample_begin, sample_count, seed, accum, ctr);
+                k_wf_finish<<<(tail_threshold + 127) / 128, 128, 0, st>>>(sc, b, 1, sample_begin, sample_count, seed, accum, ctr);
                 ++*launches;
                 break;
             }
         }
-        cudaMemcpyAsync((void *)host_live, &b.n_live[0], sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync((void *)host_live, &b.n_live[2], 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
         cudaEventRecord(ev, st);
         poll_pending = true;
     }
