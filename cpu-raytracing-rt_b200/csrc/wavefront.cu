@@ -70,10 +70,22 @@ RT_D LiveList live_list(const WfBuf &b, int list) {
     return l;
 }
 
+#ifndef WF_TILE
+#define WF_TILE 1
+#endif
 __global__ void k_wf_init(WfBuf b, DRegion rg, uint32_t width) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, n = rg.w * rg.h;
     if (i < n) {
+#if WF_TILE
+        // the static list walks the region in 8x4 pixel tiles, one tile per warp (partial tiles at
+        // the right / bottom edge shrink, the map stays a bijection): the camera rays a warp
+        // regenerates together — a run in the trace list — cover a compact patch of the image
+        const uint32_t ty = i / (4u * rg.w), r = i - ty * 4u * rg.w, ht = min(4u, rg.h - 4u * ty);
+        const uint32_t tx = r / (8u * ht), l = r - tx * 8u * ht, wt = min(8u, rg.w - 8u * tx);
+        const uint32_t slot = (rg.y0 + 4u * ty + l / wt) * width + rg.x0 + 8u * tx + l % wt;
+#else
         const uint32_t ly = i / rg.w, slot = (rg.y0 + ly) * width + rg.x0 + (i - ly * rg.w);
+#endif
         b.flags[slot] = 0;
         b.sample[slot] = 0;
         b.live[0][i] = slot;
@@ -352,10 +364,10 @@ __global__ void __launch_bounds__(128, WF_SHADE_MINB) k_wf_shade(DScene sc, WfBu
 #define WF_VOTE_T 1
 #endif
 #ifndef WF_REFILL
-#define WF_REFILL 8
+#define WF_REFILL 16
 #endif
 #ifndef WF_TRACE_BLOCKS
-#define WF_TRACE_BLOCKS 7
+#define WF_TRACE_BLOCKS 8
 #endif
 constexpr int kRefillLanes = WF_REFILL;  // refill once this many lanes are idle
 
