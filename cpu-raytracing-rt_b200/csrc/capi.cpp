@@ -2,6 +2,7 @@
 // No C++ exception and no CUDA error crosses the boundary: every entry point returns rt_status.
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -100,7 +101,9 @@ cudaError_t ensure_wavefront(rt_ctx *ctx) {
     b.live[0] = (uint32_t *)take((size_t)n * 4);
     b.live[1] = (uint32_t *)take((size_t)n * 4);
     b.n_live = (uint32_t *)take(16);
-    b.cursor = (uint32_t *)take(4);
+    b.cursor = (uint32_t *)take(8);
+    b.n_x = b.cursor + 1;
+    b.xlist = (uint32_t *)take((size_t)n * 4);
     if ((size_t)(p - ctx->wf_arena) > total) return cudaErrorMemoryAllocation;
     if (!ctx->wf_host_live) {
         e = cudaHostAlloc((void **)&ctx->wf_host_live, 2 * sizeof(uint32_t), cudaHostAllocDefault);
@@ -610,6 +613,10 @@ int rt_upload_scene(rt_ctx *ctx, const rt_scene *scene) {
             fb[k]->root = im.tris[k].fh.root;
             fb[k]->depth = im.tris[k].fh.depth;
             fb[k]->top = im.tris[k].fh.top;
+            double bound = 0.0;
+            if (!im.tris[k].nodes.empty())
+                for (int a = 0; a < 3; ++a) bound = std::max(bound, std::max(std::fabs(im.tris[k].nodes[0].lo[a]), std::fabs(im.tris[k].nodes[0].hi[a])));
+            fb[k]->bound = std::nextafter((float)bound, INFINITY);
         }
         CK(ctx, upload(ctx, im.mats, &d.materials));
         d.n_lights = (uint32_t)(s.light_boxes.prims.size() + s.light_ellipsoids.prims.size() + s.light_tris.prims.size());

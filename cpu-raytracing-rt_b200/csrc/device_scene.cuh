@@ -88,7 +88,8 @@ struct FBvh {
     const FTri *tris;
     int32_t root;                       // >= 0 inner node, < 0 leaf code, kFastEmpty: no primitives
     uint32_t depth;                     // max number of simultaneously deferred children
-    uint32_t top, _pad;                 // nodes [0, top) = top levels, breadth-first (shared-memory staging)
+    uint32_t top;                       // nodes [0, top) = top levels, breadth-first (shared-memory staging)
+    float bound;                        // >= max |coordinate| of the hierarchy's root box (error scale of hit_fragile)
 };
 
 struct DCamera {                        // camera.rs:6-15

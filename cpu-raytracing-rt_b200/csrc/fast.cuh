@@ -194,21 +194,96 @@ RT_D float up_f32(double t) { return __double2float_ru(t); }
 // lanes active while the other lanes of the warp wait.  "Certain" fp32 hits still tighten tmax
 // (with the upper bound of their distance), so pruning works as if the hit were confirmed.
 constexpr int kCand = 6;
+
+// ---- when the conservative answer may not be the reference's ----------------------------------
+// FAST culling is conservative with respect to GEOMETRY: it reaches every triangle whose exact
+// test (triangle.rs:65-80) accepts the ray.  The reference is not: it reaches a triangle only if
+// its own f64 box tests (aabb.rs:51-78) let it through every ancestor node, and those tests are
+// rounded too.  A ray that clips the corner of an ancestor box — aimed at a mesh vertex, say —
+// can be rejected there by one ulp although the triangle test would accept it, and a child whose
+// computed entry distance is not `<` the current best (bvh.rs:160-176) is skipped although it holds a
+// hit that is nearer by less than the rounding error.  For a ray drawn from a continuous
+// distribution this never happens; for a ray aimed at a vertex it happens every time.
+// FAST mode therefore PROVES, per accepted hit, that the reference reaches it, and hands the
+// ray to the exact traversal when it cannot:
+//  * hit_fragile: the box of the hit triangle itself lies inside every ancestor box, so if the ray
+//    passes through it with room to spare — every cross-axis gap `exit_j - entry_i` and every exit
+//    distance larger than the worst rounding error of such a test — all ancestors pass as well;
+//  * tie_margin: two accepted hits closer together than that error (exact ties included) make the
+//    reference's strict `<` order-dependent.
+// Both are division-free; E_k = kRobust * (bound + |o_k|) over-estimates the error of one slab
+// distance times |d_k| by three orders of magnitude.
+constexpr double kRobust = 1e-13;
+RT_D bool hit_fragile(const DTriI *tp, d3 o, d3 d, double t, double bound) {
+    const double2 *p = reinterpret_cast<const double2 *>(tp);
+    const double2 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3);
+    const double q4 = __ldg(reinterpret_cast<const double *>(tp) + 8);
+    const double ax[3] = {q0.x, q0.y, q1.x}, bx[3] = {q0.x + q1.y, q0.y + q2.x, q1.x + q2.y}, cx[3] = {q0.x + q3.x, q0.y + q3.y, q1.x + q4};
+    const double oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+    double N[3], F[3], D[3], E[3];          // |d_k| * entry distance, |d_k| * exit distance, |d_k|, error of those
+    bool frag = false;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double lo = fmin(ax[k], fmin(bx[k], cx[k])), hi = fmax(ax[k], fmax(bx[k], cx[k]));
+        E[k] = kRobust * (bound + fabs(oo[k]));
+        D[k] = fabs(dd[k]);
+        if (dd[k] > 0.0) { N[k] = lo - oo[k]; F[k] = hi - oo[k]; }
+        else if (dd[k] < 0.0) { N[k] = oo[k] - hi; F[k] = oo[k] - lo; }
+        else {                              // aabb.rs:53-57: the origin has to be inside the slab, exactly
+            N[k] = 0.0; F[k] = 0.0;
+            frag = frag || !(oo[k] - lo > E[k] && hi - oo[k] > E[k]) || !(dd[k] == 0.0);     // (NaN direction: fragile)
+        }
+        if (D[k] > 0.0) {
+            frag = frag || !(F[k] > E[k]);                          // the box is left robustly after the origin
+            frag = frag || !(t * D[k] - N[k] > -E[k]);              // and the hit does not come before the box
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            if (i != j && D[i] > 0.0 && D[j] > 0.0) frag = frag || !(F[j] * D[i] - N[i] * D[j] > E[i] * D[j] + E[j] * D[i]);
+    return frag;
+}
+// distance below which two hits of one ray may be ordered differently by the reference
+RT_D double tie_margin(d3 o, d3 d, double t, double bound) {
+    double m = 0.0;
+    if (d.x != 0.0) m = fmax(m, (bound + fabs(o.x)) / fabs(d.x));
+    if (d.y != 0.0) m = fmax(m, (bound + fabs(o.y)) / fabs(d.y));
+    if (d.z != 0.0) m = fmax(m, (bound + fabs(o.z)) / fabs(d.z));
+    return kRobust * (2.0 * m + fabs(t));
+}
+
 struct FBest {
-    bool has;
+    bool has, frag;         // frag: the reference may not reach this hit (hit_fragile)
     double t, u, v;
+    double t2;              // smallest distance among the OTHER accepted candidates (lower bound for skipped ones)
     uint32_t prim;
 };
-RT_D void confirm(const DTriI *tri_i, d3 o, d3 d, uint32_t prim, FBest &best, float &tmax) {
+RT_D void fbest_clear(FBest &b) {
+    b.has = false; b.frag = false; b.t = 0.0; b.u = 0.0; b.v = 0.0; b.prim = 0;
+    b.t2 = __longlong_as_double(0x7FF0000000000000ll);
+}
+RT_D void fbest_take(FBest &best, double t, double u, double v, uint32_t prim, bool frag) {
+    // equal distances: lowest primitive index, just to have a rule — a tie is always handed to the
+    // exact traversal afterwards (fbest_needs_exact), which applies the reference's visit order
+    if (!best.has || t < best.t || (t == best.t && prim < best.prim)) {
+        if (best.has) best.t2 = fmin(best.t2, best.t);
+        best.has = true; best.frag = frag; best.t = t; best.u = u; best.v = v; best.prim = prim;
+    } else {
+        best.t2 = fmin(best.t2, t);
+    }
+}
+RT_D bool fbest_needs_exact(const FBest &b, d3 o, d3 d, double bound) {
+    if (!b.has) return false;
+    if (b.frag) return true;
+    return b.t2 < __longlong_as_double(0x7FF0000000000000ll) && !(b.t2 - b.t > tie_margin(o, d, b.t2, bound));
+}
+RT_D void confirm(const DTriI *tri_i, d3 o, d3 d, uint32_t prim, FBest &best, float &tmax, double bound) {
     double t, u, v;
     if (!tri_exact(tri_i + prim, o, d, t, u, v)) return;
-    // equal distances: the lowest primitive index wins, whatever order the candidates were found
-    // in.  That is the reference's answer whenever the tied triangles share a leaf (it keeps the
-    // first one tested, bvh.rs:213-222) and it makes the result independent of the traversal order.
-    if (!best.has || t < best.t || (t == best.t && prim < best.prim)) {
-        best.has = true; best.t = t; best.u = u; best.v = v; best.prim = prim;
-        tmax = fminf(tmax, up_f32(t));
-    }
+    fbest_take(best, t, u, v, prim, hit_fragile(tri_i + prim, o, d, t, bound));
+    tmax = fminf(tmax, up_f32(best.t));
 }
 // A ray with a NaN component can never produce a hit: every comparison of the reference's box
 // and triangle tests is false, so it walks the WHOLE hierarchy, "hits" the first triangle with
@@ -260,11 +335,13 @@ RT_D void closest_fast(const FBvh f, const DTriI *tri_i, d3 o, d3 d, float tmax,
                 if (cls == 2) tmax = fminf(tmax, thi);
                 if (nc == kCand) {                  // rare: drop entries the new bound excludes
                     int k = 0;
-                    for (int j = 0; j < kCand; ++j)
+                    for (int j = 0; j < kCand; ++j) {
                         if (cand_t[j] <= tmax) { cand_p[k] = cand_p[j]; cand_t[k] = cand_t[j]; ++k; }
+                        else best.t2 = fmin(best.t2, (double)cand_t[j]);
+                    }
                     nc = k;
                 }
-                if (nc == kCand) { confirm(tri_i, o, d, i, best, tmax); continue; }   // very rare
+                if (nc == kCand) { confirm(tri_i, o, d, i, best, tmax, (double)f.bound); continue; }   // very rare
                 cand_p[nc] = i; cand_t[nc] = tlo; ++nc;
             }
         }
@@ -274,8 +351,10 @@ RT_D void closest_fast(const FBvh f, const DTriI *tri_i, d3 o, d3 d, float tmax,
             if (stk_t[sp] <= tmax) { cur = stk_n[sp]; cur_t = stk_t[sp]; break; }
         }
     }
-    for (int j = 0; j < nc; ++j)                    // warp-converged f64 confirmation
-        if (cand_t[j] <= tmax) confirm(tri_i, o, d, cand_p[j], best, tmax);
+    for (int j = 0; j < nc; ++j) {                  // warp-converged f64 confirmation
+        if (cand_t[j] <= tmax) confirm(tri_i, o, d, cand_p[j], best, tmax, (double)f.bound);
+        else best.t2 = fmin(best.t2, (double)cand_t[j]);           // skipped: farther than the best by an fp32 ulp at least
+    }
 }
 
 // ---- intersections::intersect in FAST mode ------------------------------------------------------
@@ -339,30 +418,44 @@ RT_D SceneHit finish_hit(const DScene &sc, d3 o, d3 d, const ShapeBest &sb, cons
     }
     return h;
 }
+// the triangle hit wins against the shapes (strict <, intersections.rs:79) but the proof that the
+// reference finds the same one failed: its own traversal decides (rare, kept out of line)
+RT_D bool triangle_hit_needs_exact(const DScene &sc, d3 o, d3 d, const ShapeBest &sb, const FBest &fb) {
+    return fb.has && (!sb.has || fb.t < sb.t) && fbest_needs_exact(fb, o, d, (double)sc.ftris.bound);
+}
+static __device__ __noinline__ SceneHit intersect_exact_cold(const DScene &sc, d3 o, d3 d) {
+    Cnt scratch;
+    return intersect_exact(sc, o, d, scratch);
+}
 RT_D SceneHit intersect_fast(const DScene &sc, d3 o, d3 d, Cnt &c) {
     const ShapeBest sb = shapes_closest(sc, o, d, c);
     FBest fb;
-    fb.has = false; fb.t = 0.0; fb.u = 0.0; fb.v = 0.0; fb.prim = 0;
+    fbest_clear(fb);
     bool skip;
     const float tmax0 = shapes_tmax(sb, skip);
     if (!skip) closest_fast(sc.ftris, sc.tri_i, o, d, tmax0, fb);
+    if (triangle_hit_needs_exact(sc, o, d, sb, fb)) return intersect_exact_cold(sc, o, d);
     return finish_hit(sc, o, d, sb, fb);
 }
 
 // ---- Light::pdf in FAST mode ---------------------------------------------------------------------
 // All hits, no pruning, children visited left then right: the reference's DFS order
 // (src/bvh.rs:188-210), so the floating-point SUM is formed in the same order.
-RT_D void light_confirm(const DTriI *tri_i, const DTriS *tri_s, d3 o, d3 d, uint32_t i, double &impact) {
+// returns true when the hit is fragile (the reference's all-hits walk may not reach it)
+RT_D bool light_confirm(const DTriI *tri_i, const DTriS *tri_s, d3 o, d3 d, uint32_t i, double &impact, double bound) {
     double t, u, v;
-    if (!tri_exact(tri_i + i, o, d, t, u, v)) return;
+    if (!tri_exact(tri_i + i, o, d, t, u, v)) return false;
+    const bool frag = hit_fragile(tri_i + i, o, d, t, bound);
     const double2 *p = reinterpret_cast<const double2 *>(tri_s + i);
     const double2 q0 = __ldg(p), q1 = __ldg(p + 1);
     const double inv_area = __ldg(&tri_s[i].inv_area);
     // |d . (+-n)| is the same for the flipped normal (triangle.rs:73-77)
     impact += inv_area * (t * t / fabs(dot3(d, mk3(q0.x, q0.y, q1.x))));
+    return frag;
 }
-RT_D void light_hits_fast(const FBvh f, const DTriI *tri_i, const DTriS *tri_s, d3 o, d3 d, double &impact) {
-    if (f.root == kFastEmpty) return;
+// returns true when some hit was fragile: the caller redoes the sum with light_hits_exact
+RT_D bool light_hits_fast(const FBvh f, const DTriI *tri_i, const DTriS *tri_s, d3 o, d3 d, double &impact) {
+    if (f.root == kFastEmpty) return false;
     const FRay r = make_fray(o, d);
     const float dl1g = kGamma * (fabsf(r.dx) + fabsf(r.dy) + fabsf(r.dz));
     const float inf = __int_as_float(0x7F800000);
@@ -370,6 +463,7 @@ RT_D void light_hits_fast(const FBvh f, const DTriI *tri_i, const DTriS *tri_s, 
     float stk_t[kFastStack];
     uint32_t cand[kCand];
     int sp = 0, nc = 0;
+    bool frag = false;
     stk[sp] = f.root; stk_t[sp] = 0.0f; ++sp;
     while (sp > 0) {
         --sp;
@@ -386,14 +480,15 @@ RT_D void light_hits_fast(const FBvh f, const DTriI *tri_i, const DTriS *tri_s, 
                 float tlo, thi;
                 if (tri_classify(f.tris + i, tri_i + i, r, o, d, cur_t, dl1g, inf, tlo, thi) == 0) continue;
                 if (nc == kCand) {                  // flush in visit order, then keep collecting
-                    for (int j = 0; j < kCand; ++j) light_confirm(tri_i, tri_s, o, d, cand[j], impact);
+                    for (int j = 0; j < kCand; ++j) frag = light_confirm(tri_i, tri_s, o, d, cand[j], impact, (double)f.bound) || frag;
                     nc = 0;
                 }
                 cand[nc++] = i;
             }
         }
     }
-    for (int j = 0; j < nc; ++j) light_confirm(tri_i, tri_s, o, d, cand[j], impact);   // same order as visited
+    for (int j = 0; j < nc; ++j) frag = light_confirm(tri_i, tri_s, o, d, cand[j], impact, (double)f.bound) || frag;   // same order as visited
+    return frag;
 }
 // analytic lights (boxes, then ellipsoids: intersect_lights order, intersections.rs:88-89)
 RT_D double light_shapes_impact(const DScene &sc, d3 o, d3 dir, Cnt &c) {
@@ -402,10 +497,22 @@ RT_D double light_shapes_impact(const DScene &sc, d3 o, d3 dir, Cnt &c) {
     light_hits_exact<2>(sc.lellipsoids, sc.lell_prims, nullptr, o, dir, impact, c);
     return impact;
 }
+static __device__ __noinline__ void light_tris_exact_cold(const DScene &sc, d3 o, d3 dir, double &impact) {
+    Cnt scratch;
+    light_hits_exact<3>(sc.ltris, sc.ltri_i, sc.ltri_s, o, dir, impact, scratch);
+}
+// the emissive triangles' part of Light::pdf, added to `impact` (which holds the analytic lights' part)
+RT_D void light_tris_impact_fast(const DScene &sc, d3 o, d3 dir, double &impact) {
+    const double base = impact;
+    if (light_hits_fast(sc.fltris, sc.ltri_i, sc.ltri_s, o, dir, impact)) {
+        impact = base;
+        light_tris_exact_cold(sc, o, dir, impact);
+    }
+}
 RT_D double light_pdf_fast(const DScene &sc, d3 o, d3 dir, Cnt &c) {
     ++c.lray;
     double impact = light_shapes_impact(sc, o, dir, c);
-    light_hits_fast(sc.fltris, sc.ltri_i, sc.ltri_s, o, dir, impact);
+    light_tris_impact_fast(sc, o, dir, impact);
     return impact / (double)sc.n_lights;
 }
 

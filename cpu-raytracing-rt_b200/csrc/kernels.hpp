@@ -30,6 +30,7 @@ struct WfBuf {                          // per-pixel path slots, structure of ar
     uint32_t *live[2];                  // n each: compacted indices of slots with work
     uint32_t *n_live;                   // [4]: per list, entries filled from the front / from the back (8-byte aligned pairs)
     uint32_t *cursor;                   // trace kernel's fetch position in the live list
+    uint32_t *xlist, *n_x;              // slots deferred to k_wf_exact in this iteration (n entries), their count (= cursor + 1)
 };
 size_t wf_bytes_per_slot();
 int wf_trace_blocks(int device);

@@ -30,18 +30,29 @@ namespace rt {
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr uint32_t kFlagAlive = 1u, kFlagRngHave = 2u, kFlagPendLight = 4u;
+constexpr uint32_t kFlagExactPending = 16u;   // handed to k_wf_exact in this iteration: not shaded, not traced; cleared by the next confirm pass
 constexpr uint32_t kOverflowClosest = 0x10000u, kOverflowLight = 0x20000u;
 constexpr uint32_t kNoShape = 0xFFFFFFFFu;
 
 RT_D d3 ld_soa(const double *base, uint32_t n, uint32_t i) { return mk3(base[i], base[n + i], base[2u * n + i]); }
 RT_D void st_soa(double *base, uint32_t n, uint32_t i, d3 v) { base[i] = v.x; base[n + i] = v.y; base[2u * n + i] = v.z; }
 
+#ifndef WF_COUNT_DEFER
+#define WF_COUNT_DEFER 0
+#endif
 __device__ __forceinline__ void flush_counters_wf(const Cnt &c, DCounters *out) {
-    unsigned long long v[3] = {c.seg, c.lray, c.paths};
-    unsigned long long *dst[3] = {&out->segments, &out->light_pdf_rays, &out->paths};
+#if WF_COUNT_DEFER
+    constexpr int kN = 6;       // diagnostics: deferred slots by reason in the (otherwise unused in FAST mode) test counters
+    unsigned long long v[kN] = {c.seg, c.lray, c.paths, c.aabb, c.laabb, c.lprim};
+    unsigned long long *dst[kN] = {&out->segments, &out->light_pdf_rays, &out->paths, &out->aabb_tests, &out->light_aabb_tests, &out->light_prim_tests};
+#else
+    constexpr int kN = 3;
+    unsigned long long v[kN] = {c.seg, c.lray, c.paths};
+    unsigned long long *dst[kN] = {&out->segments, &out->light_pdf_rays, &out->paths};
+#endif
     const int lane = threadIdx.x & 31;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < kN; ++k) {
         unsigned long long s = v[k];
         for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(kFull, s, off);
         if (lane == 0 && s) atomicAdd(dst[k], s);
@@ -95,14 +106,15 @@ __global__ void k_wf_init(WfBuf b, DRegion rg, uint32_t width) {
 
 // ---- confirm -----------------------------------------------------------------------------------
 // The exact f64 test of every deferred candidate (the reference's Triangle::intersection, ~400
-// instructions with its nine divisions) as a kernel of its own, one (ray, candidate) PAIR per
-// thread: a ray has 0..6 scene candidates and 0..6 light candidates, so a loop per ray runs with a
-// third of the lanes; here a block gathers the pairs of its 128 rays with a prefix sum and deals
-// them out evenly.  Results go to per-slot arrays in list order; the shade kernel only folds them
-// (minimum for the scene, ordered sum for the lights), so the values are bit for bit the same.
-#ifndef WF_SPLIT_CONFIRM
-#define WF_SPLIT_CONFIRM 1
-#endif
+// instructions with its nine divisions) as a kernel of its own.
+// Phase 1, one (ray, candidate) PAIR per thread: a ray has 0..6 scene candidates and 0..6 light
+// candidates, so a loop per ray runs with a third of the lanes; here a block gathers the pairs of
+// its 128 rays with a prefix sum and deals them out evenly.
+// Phase 2, one ray per thread: fold the pair results into what the shade kernel needs — the
+// nearest confirmed triangle (slot entry 0 of cand / res_t / res_u / res_v, ncand = 0 or 1) and the
+// complete Light::pdf impact (lres entry 0: the analytic lights' part + the terms in list order =
+// the reference's DFS order, bvh.rs:188-210) — and decide whether the proof that the reference
+// finds the same hits holds (hit_fragile, tie_margin).  If not the slot goes to k_wf_exact.
 #ifndef WF_CONFIRM_MINB
 #define WF_CONFIRM_MINB 8
 #endif
@@ -114,12 +126,18 @@ __global__ void __launch_bounds__(128, WF_CONFIRM_MINB) k_wf_confirm(DScene sc, 
     const uint32_t tid = threadIdx.x, i = blockIdx.x * 128 + tid, lane = tid & 31, wid = tid >> 5;
     const LiveList ll = live_list(b, list);
     const uint32_t N = b.n;
-    uint32_t slot = 0, nc = 0, nl = 0;
+    uint32_t slot = 0, nc = 0, nl = 0, flags = 0, nc_all = 0;
+    bool mine = false;                                  // this thread's slot has results to fold
     if (i < ll.n) {
         slot = ll.at(i);
-        const uint32_t flags = b.flags[slot];
-        if (flags & kFlagAlive) {                       // not alive: nothing was traced for this slot
-            const uint32_t nc_all = b.ncand[slot];
+        flags = b.flags[slot];
+        if (flags & kFlagExactPending) {
+            // k_wf_exact answered this slot during the last iteration (the graph joined since):
+            // its results are final, the shade kernel takes them in this iteration
+            b.flags[slot] = flags & ~kFlagExactPending;
+        } else if (flags & kFlagAlive) {                // not alive: nothing was traced for this slot
+            mine = true;
+            nc_all = b.ncand[slot];
             nc = (nc_all & kOverflowClosest) ? 0u : (nc_all & 0xFFu);       // overflowed lists: the shade kernel redoes the search
             nl = ((nc_all & kOverflowLight) || !(flags & kFlagPendLight)) ? 0u : ((nc_all >> 8) & 0xFFu);
             if (nc + nl) {
@@ -149,6 +167,7 @@ __global__ void __launch_bounds__(128, WF_CONFIRM_MINB) k_wf_confirm(DScene sc, 
     for (uint32_t k = 0; k < nl; ++k) s_pair[base + k] = (uint16_t)(tid | (k << 7) | 0x400u);
     for (uint32_t k = 0; k < nc; ++k) s_pair[base + nl + k] = (uint16_t)(tid | (k << 7));
     __syncthreads();
+    // ---- phase 1: pairs.  res_u / lres: -1 = no hit, -2 = a hit the reference may not reach
     for (uint32_t e = tid; e < total; e += 128) {
         const uint32_t pr = s_pair[e], owner = pr & 127u, k = (pr >> 7) & 7u;
         const bool light = (pr & 0x400u) != 0;
@@ -157,10 +176,12 @@ __global__ void __launch_bounds__(128, WF_CONFIRM_MINB) k_wf_confirm(DScene sc, 
         const d3 d = mk3(s_ray[3][owner], s_ray[4][owner], s_ray[5][owner]);
         const uint32_t prim = light ? b.lcand[at] : b.cand[at];
         double t, u, v;
-        const bool hit = tri_exact((light ? sc.ltri_i : sc.tri_i) + prim, o, d, t, u, v);
+        const DTriI *tp = (light ? sc.ltri_i : sc.tri_i) + prim;
+        const bool hit = tri_exact(tp, o, d, t, u, v);
+        const bool frag = hit && hit_fragile(tp, o, d, t, (double)(light ? sc.fltris.bound : sc.ftris.bound));
         if (light) {
-            double term = -1.0;
-            if (hit) {                                  // the term of light_confirm (ray_sampler.rs:135-137)
+            double term = frag ? -2.0 : -1.0;
+            if (hit && !frag) {                         // the term of light_confirm (ray_sampler.rs:135-137)
                 const double2 *p = reinterpret_cast<const double2 *>(sc.ltri_s + prim);
                 const double2 q0 = __ldg(p), q1 = __ldg(p + 1);
                 const double inv_area = __ldg(&sc.ltri_s[prim].inv_area);
@@ -168,21 +189,49 @@ __global__ void __launch_bounds__(128, WF_CONFIRM_MINB) k_wf_confirm(DScene sc, 
             }
             b.lres[at] = term;
         } else {
-            b.res_u[at] = hit ? u : -1.0;
+            b.res_u[at] = hit ? (frag ? -2.0 : u) : -1.0;
             if (hit) { b.res_t[at] = t; b.res_v[at] = v; }
+        }
+    }
+    __syncthreads();                                    // the block's results are visible to the block
+    // ---- phase 2: one ray per thread
+    if (mine) {
+        // a candidate list that overflowed (rare: more than kWfCand survivors of the fp32 pre-test)
+        // is not worth a second fp32 search: the exact traversal answers the ray
+        bool need_exact = (nc_all & (kOverflowClosest | kOverflowLight)) != 0;
+        if ((flags & kFlagPendLight) && !(nc_all & kOverflowLight)) {
+            double impact = b.pimp[slot];
+            for (uint32_t k = 0; k < nl; ++k) {
+                const double term = b.lres[(size_t)k * N + slot];
+                if (term == -2.0) need_exact = true;
+                else if (term != -1.0) impact += term;
+            }
+            b.lres[slot] = impact;
+        }
+        if (!(nc_all & kOverflowClosest)) {
+            FBest fb;
+            fbest_clear(fb);
+            for (uint32_t k = 0; k < nc; ++k) {
+                const size_t at = (size_t)k * N + slot;
+                const double u = b.res_u[at];
+                if (u != -1.0) fbest_take(fb, b.res_t[at], u, b.res_v[at], b.cand[at], u == -2.0);
+            }
+            if (fb.has) {
+                const d3 o = mk3(s_ray[0][tid], s_ray[1][tid], s_ray[2][tid]), d = mk3(s_ray[3][tid], s_ray[4][tid], s_ray[5][tid]);
+                need_exact = need_exact || fbest_needs_exact(fb, o, d, (double)sc.ftris.bound);
+                b.cand[slot] = fb.prim;
+                b.res_t[slot] = fb.t; b.res_u[slot] = fb.u; b.res_v[slot] = fb.v;
+            }
+            b.ncand[slot] = fb.has ? 1u : 0u;
+        }
+        if (need_exact) {
+            b.flags[slot] = flags | kFlagExactPending;
+            b.xlist[atomicAdd(b.n_x, 1u)] = slot;
         }
     }
 }
 
 // ---- shade -------------------------------------------------------------------------------------
-// Candidate-list overflow is rare (never on the bench scene): its full searches are kept out of
-// line so that they do not sit in the instruction stream of the hot path.
-static __device__ __noinline__ void closest_fast_cold(const FBvh f, const DTriI *tri_i, d3 o, d3 d, float tmax, FBest &best) {
-    closest_fast(f, tri_i, o, d, tmax, best);
-}
-static __device__ __noinline__ void light_hits_fast_cold(const FBvh f, const DTriI *tri_i, const DTriS *tri_s, d3 o, d3 d, double &impact) {
-    light_hits_fast(f, tri_i, tri_s, o, d, impact);
-}
 #ifndef WF_SHADE_MINB
 #define WF_SHADE_MINB 4
 #endif
@@ -203,7 +252,8 @@ __global__ void __launch_bounds__(128, WF_SHADE_MINB) k_wf_shade(DScene sc, WfBu
         rng.init(seed, slot, sample_begin + s);
         d3 o = mk3(0.0, 0.0, 0.0), d = o, T = o, L = o;
         uint32_t left = (flags >> 8) & 0xFFu;
-        bool alive = (flags & kFlagAlive) != 0, ended = false, pend_light = false;
+        const bool defer = (flags & kFlagExactPending) != 0;
+        bool alive = (flags & kFlagAlive) != 0 && !defer, ended = false, pend_light = false;
         Pending pd;
         pd.v = o; pd.cos_pdf = 0.0;
         if (alive) {
@@ -213,58 +263,25 @@ __global__ void __launch_bounds__(128, WF_SHADE_MINB) k_wf_shade(DScene sc, WfBu
             T = ld_soa(b.T, N, slot); L = ld_soa(b.L, N, slot);
             const uint32_t nc_all = b.ncand[slot];
             if (flags & kFlagPendLight) {               // finish the previous diffuse bounce: Light::pdf of THIS ray
-                double impact = b.pimp[slot];
-                if (nc_all & kOverflowLight) {
-                    light_hits_fast_cold(sc.fltris, sc.ltri_i, sc.ltri_s, o, d, impact);
-                } else {
-                    const uint32_t nl = (nc_all >> 8) & 0xFFu;
-#if WF_SPLIT_CONFIRM
-                    // k_wf_confirm has evaluated the terms; they are summed here in list order
-                    // (= the reference's DFS order, bvh.rs:188-210)
-                    for (uint32_t k = 0; k < nl; ++k) {
-                        const double term = b.lres[k * N + slot];
-                        if (term != -1.0) impact += term;
-                    }
-#else
-                    for (uint32_t k = 0; k < nl; ++k) light_confirm(sc.ltri_i, sc.ltri_s, o, d, b.lcand[k * N + slot], impact);
-#endif
-                }
+                const double impact = b.lres[slot];     // folded by k_wf_confirm or answered by k_wf_exact
                 pd.v = ld_soa(b.pv, N, slot);
                 pd.cos_pdf = b.pcos[slot];
                 if (!apply_pending(pd, impact / (double)sc.n_lights, T)) ended = true;
             }
             if (!ended) {
-                ++c.seg;
                 ShapeBest sb;
                 const uint32_t sid = b.sh_id[slot];
                 sb.has = sid != kNoShape; sb.kind = sb.has ? (int)(sid >> 28) : -1; sb.prim = sid & 0x0FFFFFFFu; sb.t = b.sh_t[slot];
                 FBest fb;
-                fb.has = false; fb.t = 0.0; fb.u = 0.0; fb.v = 0.0; fb.prim = 0;
+                fbest_clear(fb);
                 bool skip;
-                float tmax = shapes_tmax(sb, skip);
-                if (!skip) {
-                    if (nc_all & kOverflowClosest) {
-                        closest_fast_cold(sc.ftris, sc.tri_i, o, d, tmax, fb);
-                    } else {
-                        const uint32_t nc = nc_all & 0xFFu;
-#if WF_SPLIT_CONFIRM
-                        for (uint32_t k = 0; k < nc; ++k) {
-                            const double u = b.res_u[k * N + slot];
-                            if (u != -1.0) {                // same rule as confirm(): nearest, then lowest primitive index
-                                const double t = b.res_t[k * N + slot];
-                                const uint32_t prim = b.cand[k * N + slot];
-                                if (!fb.has || t < fb.t || (t == fb.t && prim < fb.prim)) {
-                                    fb.has = true; fb.t = t; fb.u = u; fb.v = b.res_v[k * N + slot]; fb.prim = prim;
-                                }
-                            }
-                        }
-                        (void)tmax;
-#else
-                        for (uint32_t k = 0; k < nc; ++k)
-                            if (b.cand_t[k * N + slot] <= tmax) confirm(sc.tri_i, o, d, b.cand[k * N + slot], fb, tmax);
-#endif
-                    }
+                const float tmax = shapes_tmax(sb, skip);
+                (void)tmax;
+                if (!skip && (nc_all & 0xFFu)) {        // the nearest confirmed triangle, folded by k_wf_confirm
+                    fb.has = true; fb.prim = b.cand[slot];
+                    fb.t = b.res_t[slot]; fb.u = b.res_u[slot]; fb.v = b.res_v[slot];
                 }
+                ++c.seg;
                 const SceneHit h = finish_hit<SHAPES>(sc, o, d, sb, fb);
                 const int r = shade_hit<SHAPES>(sc, h, o, d, T, L, rng, pd);
                 --left;
@@ -280,7 +297,13 @@ __global__ void __launch_bounds__(128, WF_SHADE_MINB) k_wf_shade(DScene sc, WfBu
                 }
             }
         }
-        if (!alive || ended) {
+        if (defer) {
+            // k_wf_confirm could not prove that the reference finds the same hits for this ray
+            // (hit_fragile / a tie): k_wf_exact is answering both searches with the reference's own
+            // traversal while this kernel runs.  Nothing is shaded, stored or traced for the slot
+            // in this iteration; it stays in the list and is picked up in the next one.
+            keep = true;
+        } else if (!alive || ended) {
             if (alive) {                                // main.rs:102
                 const size_t p = (size_t)slot * 3;
                 accum[p] += L.x; accum[p + 1] += L.y; accum[p + 2] += L.z;
@@ -299,7 +322,7 @@ __global__ void __launch_bounds__(128, WF_SHADE_MINB) k_wf_shade(DScene sc, WfBu
                 fresh = true;
             }
         }
-        if (alive) {                                    // hand the ray to the trace kernel
+        if (alive && !defer) {                          // hand the ray to the trace kernel
             if (SHAPES) {
                 const ShapeBest sb = shapes_closest(sc, o, d, c);
                 b.sh_id[slot] = sb.has ? (((uint32_t)sb.kind << 28) | sb.prim) : kNoShape;
@@ -320,7 +343,7 @@ __global__ void __launch_bounds__(128, WF_SHADE_MINB) k_wf_shade(DScene sc, WfBu
             b.sample[slot] = s;
             b.flags[slot] = kFlagAlive | (rng.have ? kFlagRngHave : 0u) | (pend_light ? kFlagPendLight : 0u) | (left << 8);
             keep = true;
-        } else {
+        } else if (!defer) {
             b.flags[slot] = 0;
             b.sample[slot] = s;
         }
@@ -343,6 +366,36 @@ __global__ void __launch_bounds__(128, WF_SHADE_MINB) k_wf_shade(DScene sc, WfBu
         }
     }
     flush_counters_wf(c, ctr);
+}
+
+// ---- exact ---------------------------------------------------------------------------------------
+// The slots k_wf_confirm could not vouch for (normally a few dozen per iteration: paths leaving a
+// flat light, rays through a mesh vertex): both searches of the ray redone with the reference's
+// own traversal (exact.cuh) and written back in the form k_wf_confirm leaves its results in — the
+// nearest triangle in entry 0, the complete light impact.  The slot's flag stays set for the whole
+// iteration (the next confirm pass clears it), so whether this kernel is early or late changes nothing.  One such traversal is a long serial chain, so this kernel runs on a forked
+// branch of the graph, next to the shade and trace kernels, which skip these slots meanwhile.
+__global__ void __launch_bounds__(128) k_wf_exact(DScene sc, WfBuf b) {
+    const uint32_t n = *b.n_x, N = b.n;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t slot = b.xlist[i];
+        const uint32_t flags = b.flags[slot];
+        const d3 o = ld_soa(b.ro, N, slot), d = ld_soa(b.rd, N, slot);
+        Cnt scratch;
+        if (flags & kFlagPendLight) {
+            double impact = b.pimp[slot];               // the analytic lights' part (shade kernel), then the triangles
+            light_hits_exact<3>(sc.ltris, sc.ltri_i, sc.ltri_s, o, d, impact, scratch);
+            b.lres[slot] = impact;
+        }
+        const Best bt = closest_exact<3>(sc.tris, sc.tri_i, o, d, scratch);
+        if (bt.has) {
+            double t, u, v;
+            tri_exact(sc.tri_i + bt.prim, o, d, t, u, v);
+            b.cand[slot] = bt.prim;
+            b.res_t[slot] = t; b.res_u[slot] = u; b.res_v[slot] = v;
+        }
+        b.ncand[slot] = bt.has ? 1u : 0u;               // no overflow: nothing left for the shade kernel to search
+    }
 }
 
 // ---- trace -------------------------------------------------------------------------------------
@@ -444,6 +497,8 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
                 uint32_t base = 0;
                 if (lane == leader) base = atomicAdd(b.cursor, (uint32_t)__popc(idle));
                 base = __shfl_sync(kFull, base, leader);
+                // the highest index handed out in this refill tells whether the list ran out
+                if (base + (uint32_t)__popc(idle) >= n) drained = true;
                 if (!has) {
                     const uint32_t idx = base + __popc(idle & ((1u << lane) - 1u));
                     if (idx < n) {
@@ -457,15 +512,15 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
                         const double st = b.sh_t[slot];
                         const bool skip = (sid != kNoShape && st != st) || ray_is_nan(o, dd);
                         tmax = (sid != kNoShape && !skip) ? up_f32(st) : inf;
-                        want_light = (b.flags[slot] & kFlagPendLight) != 0;
+                        const uint32_t fl = b.flags[slot];
+                        want_light = (fl & kFlagPendLight) != 0;
                         nc = 0; nl = 0; over = 0; sp = 0;
                         closest = true;
                         cur = skip ? kFastEmpty : sc.ftris.root; cur_t = 0.0f;
                         WF_ENTER_LEAF()
-                        has = true;
+                        has = !(fl & kFlagExactPending);        // k_wf_exact is answering this ray: not traced
                     }
                 }
-                if (__any_sync(kFull, !has)) drained = true;   // an index fell off the list: it is empty
             }
             if (drained && !__any_sync(kFull, has)) break;
             wi = has && cur >= 0;
@@ -620,7 +675,7 @@ __global__ void __launch_bounds__(128) k_wf_finish(DScene sc, WfBuf b, int list,
 }
 
 // ---- host loop -----------------------------------------------------------------------------------
-size_t wf_bytes_per_slot() { return 15 * 8 + 3 * 8 + 7 * 4 + kWfCand * 12 + kWfCand * 32 + 2 * 4; }
+size_t wf_bytes_per_slot() { return 15 * 8 + 3 * 8 + 7 * 4 + kWfCand * 12 + kWfCand * 32 + 3 * 4; }
 int wf_trace_blocks(int device) {
     int sms = 148, per_sm = 4;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -634,8 +689,9 @@ cudaError_t launch_render_wavefront(cudaStream_t st, const DScene &sc, uint32_t 
     const unsigned blocks = (n_region + 127) / 128;
     k_wf_init<<<blocks, 128, 0, st>>>(b, rg, sc.width);
     ++*launches;
-    const uint64_t max_iters = (uint64_t)sample_count * (sc.ray_depth ? sc.ray_depth : 1) + 2;
-    bool poll_pending = false;
+    // a segment takes one iteration, two when it is deferred to k_wf_exact
+    const uint64_t max_iters = 2 * (uint64_t)sample_count * (sc.ray_depth ? sc.ray_depth : 1) + 8;
+    bool poll_pending = false, finished = false;
     // scenes without planes / boxes / ellipsoids (every glTF scene) run the kernel compiled without them
     const bool shapes = sc.n_planes || sc.boxes.n_prims || sc.ellipsoids.n_prims || sc.lboxes.n_prims || sc.lellipsoids.n_prims;
     const uint32_t tail_threshold = n_region / 16 + 1;       // below this many live slots, finish in one kernel
@@ -643,15 +699,29 @@ cudaError_t launch_render_wavefront(cudaStream_t st, const DScene &sc, uint32_t 
     // started from) are captured ONCE into a CUDA graph and replayed, so the host issues one launch
     // per four iterations instead of sixteen — the inner loop is launch-bound on small images and
     // in the last iterations of every render.
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        const cudaError_t e = cudaGetLastError();
+        if (side) cudaStreamDestroy(side);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        return e != cudaSuccess ? e : cudaErrorUnknown;
+    }
     auto issue_iteration = [&](int from) {
         cudaMemsetAsync(&b.n_live[2 * (from ^ 1)], 0, 2 * sizeof(uint32_t), st);   // next list starts empty
-        cudaMemsetAsync(b.cursor, 0, sizeof(uint32_t), st);                  // trace fetch position
-#if WF_SPLIT_CONFIRM
+        cudaMemsetAsync(b.cursor, 0, 2 * sizeof(uint32_t), st);              // trace fetch position, deferred-slot count (cursor[1])
         k_wf_confirm<<<blocks, 128, 0, st>>>(sc, b, from);
-#endif
+        // fork: k_wf_exact works on the few slots the confirm pass handed over while the shade and
+        // trace kernels run (they skip those slots); joined at the end of the iteration
+        cudaEventRecord(ev_fork, st);
+        cudaStreamWaitEvent(side, ev_fork, 0);
+        k_wf_exact<<<64, 128, 0, side>>>(sc, b);
+        cudaEventRecord(ev_join, side);
         if (shapes) k_wf_shade<true><<<blocks, 128, 0, st>>>(sc, b, from, sample_begin, sample_count, seed, accum, ctr);
         else k_wf_shade<false><<<blocks, 128, 0, st>>>(sc, b, from, sample_begin, sample_count, seed, accum, ctr);
         k_wf_trace<<<trace_blocks, 128, 0, st>>>(sc, b, from ^ 1, ctr);
+        cudaStreamWaitEvent(st, ev_join, 0);
     };
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
@@ -669,14 +739,15 @@ cudaError_t launch_render_wavefront(cudaStream_t st, const DScene &sc, uint32_t 
         } else {
             for (int k = 0; k < 4; ++k) issue_iteration(0);
         }
-        *launches += WF_SPLIT_CONFIRM ? 12 : 8;
+        *launches += 16;
         // four iterations end on list 0 again; poll its live count without stalling the stream
         if (poll_pending) {
             result = cudaEventSynchronize(ev);
             if (result != cudaSuccess) break;
             const uint32_t n_left = host_live[0] + host_live[1];       // front + back of list 0
-            if (n_left == 0) break;
+            if (n_left == 0) { finished = true; break; }
             if (n_left < tail_threshold) {
+                finished = true;
                 // few slots left: finish them in one kernel (the count can only have shrunk since)
                 k_wf_finish<<<(tail_threshold + 127) / 128, 128, 0, st>>>(sc, b, 1, sample_begin, sample_count, seed, accum, ctr);
                 ++*launches;
@@ -687,6 +758,14 @@ cudaError_t launch_render_wavefront(cudaStream_t st, const DScene &sc, uint32_t 
         cudaEventRecord(ev, st);
         poll_pending = true;
     }
+    if (!finished && result == cudaSuccess) {       // cannot happen (max_iters bounds every path); finish whatever is in flight
+        k_wf_finish<<<blocks, 128, 0, st>>>(sc, b, 1, sample_begin, sample_count, seed, accum, ctr);
+        ++*launches;
+    }
+    cudaStreamSynchronize(side);                    // (already joined into st; makes the destroy below trivially safe)
+    cudaEventDestroy(ev_fork);
+    cudaEventDestroy(ev_join);
+    cudaStreamDestroy(side);
     if (exec) cudaGraphExecDestroy(exec);
     if (graph) cudaGraphDestroy(graph);
     if (result != cudaSuccess) return result;
