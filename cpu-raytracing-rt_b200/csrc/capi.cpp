@@ -95,7 +95,6 @@ cudaError_t ensure_wavefront(rt_ctx *ctx) {
     for (uint32_t **q : u1s) *q = (uint32_t *)take((size_t)n * 4);
     b.cand = (uint32_t *)take((size_t)n * 4 * kWfCand);
     b.lcand = (uint32_t *)take((size_t)n * 4 * kWfCand);
-    b.cand_t = (float *)take((size_t)n * 4 * kWfCand);
     double **res[4] = {&b.res_t, &b.res_u, &b.res_v, &b.lres};
     for (double **q : res) *q = (double *)take((size_t)n * 8 * kWfCand);
     b.live[0] = (uint32_t *)take((size_t)n * 4);

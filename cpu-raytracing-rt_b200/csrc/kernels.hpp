@@ -23,8 +23,7 @@ struct WfBuf {                          // per-pixel path slots, structure of ar
     double *ro, *rd, *T, *L, *pv;       // 3 * n: ray origin / direction, throughput, radiance, pending weight
     double *pcos, *pimp, *sh_t;         // n: Cosine::pdf, light impact of analytic lights, shapes' best t
     uint32_t *sh_id, *rng_block, *rng_s0, *rng_s1, *sample, *flags, *ncand;    // n
-    uint32_t *cand, *lcand;             // kWfCand * n: triangle candidates (scene / lights)
-    float *cand_t;                      // kWfCand * n: lower bound of each scene candidate's distance
+    uint32_t *cand, *lcand;             // kWfCand * n: triangle candidates (scene / lights) that survived the fp32 pre-test
     double *res_t, *res_u, *res_v;      // kWfCand * n: k_wf_confirm's exact (t, u, v) per scene candidate; u == -1: no hit
     double *lres;                       // kWfCand * n: exact Light::pdf term per light candidate; -1: no hit
     uint32_t *live[2];                  // n each: compacted indices of slots with work

@@ -233,10 +233,10 @@ __global__ void __launch_bounds__(128, WF_CONFIRM_MINB) k_wf_confirm(DScene sc, 
 
 // ---- shade -------------------------------------------------------------------------------------
 #ifndef WF_SHADE_MINB
-#define WF_SHADE_MINB 4
+#define WF_SHADE_MINB 6        // glTF variant: 80 registers, no spills to speak of; measured 4 / 5 / 6 / 7 / 8 -> 1240 / 1270 / 1282 / 1276 / 1275 Mseg/s
 #endif
 template <bool SHAPES>
-__global__ void __launch_bounds__(128, WF_SHADE_MINB) k_wf_shade(DScene sc, WfBuf b, int cur_list, uint32_t sample_begin, uint32_t sample_count,
+__global__ void __launch_bounds__(128, SHAPES ? 4 : WF_SHADE_MINB) k_wf_shade(DScene sc, WfBuf b, int cur_list, uint32_t sample_begin, uint32_t sample_count,
                                                   unsigned long long seed, double *__restrict__ accum, DCounters *ctr) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const LiveList ll = live_list(b, cur_list);
@@ -580,7 +580,6 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
                         if (cls == 2) tmax = fminf(tmax, thi);
                         if (nc < (uint32_t)kWfCand) {
                             b.cand[nc * N + slot] = tri_i;
-                            b.cand_t[nc * N + slot] = tlo;
                             ++nc;
                         } else {
                             over |= kOverflowClosest;           // rare: the shade kernel redoes this search
@@ -675,7 +674,7 @@ __global__ void __launch_bounds__(128) k_wf_finish(DScene sc, WfBuf b, int list,
 }
 
 // ---- host loop -----------------------------------------------------------------------------------
-size_t wf_bytes_per_slot() { return 15 * 8 + 3 * 8 + 7 * 4 + kWfCand * 12 + kWfCand * 32 + 3 * 4; }
+size_t wf_bytes_per_slot() { return 15 * 8 + 3 * 8 + 7 * 4 + kWfCand * 8 + kWfCand * 32 + 3 * 4; }
 int wf_trace_blocks(int device) {
     int sms = 148, per_sm = 4;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
