@@ -313,7 +313,7 @@ def main():
                     "ms_per_step": e2e_s / max(1, args.steps) * 1e3},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (prof["dram_bytes_per_spp_at_1080p"] * S * (args.width * args.height / 2073600.0)) if (args.sched == "wavefront" and "dram_bytes_per_spp_at_1080p" in prof) else None,
-                         "traffic_source": prof.get("source"), "peak_source": peak_src, "kernel": ("k_wf_trace + k_wf_shade (one wavefront render call)" if args.sched == "wavefront" else "k_render_mega<FastPolicy>") if args.mode == "fast" else "k_render_mega<ExactPolicy>",
+                         "traffic_source": prof.get("source"), "peak_source": peak_src, "kernel": ("k_wf_confirm + k_wf_shade + k_wf_trace per iteration (one wavefront render call)" if args.sched == "wavefront" else "k_render_mega<FastPolicy>") if args.mode == "fast" else "k_render_mega<ExactPolicy>",
                          "kernel_ms_per_launch": kernel_ms, "algorithmic_bytes_per_segment": bytes_per_segment,
                          "aabb_tests_per_segment": exact_c["aabb_tests"] / max(1, exact_c["segments"]),
                          "prim_tests_per_segment": exact_c["prim_tests"] / max(1, exact_c["segments"])},

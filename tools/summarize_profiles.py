@@ -1,4 +1,5 @@
-"""Turns gpurun_out/r01_launches.csv and the two --set full captures into the tracked summaries
+"""Turns gpurun_out/r01_launches.csv and the --set full capture (r01_wf_all.ncu-rep: one launch each of
+k_wf_confirm, k_wf_shade, k_wf_trace of the same iteration) into the tracked summaries
 under profiles/ (launch summary, per-kernel key metrics, measured DRAM traffic)."""
 import collections
 import csv
@@ -50,11 +51,12 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_active"]
 summ = {}
-for k in ("trace", "shade"):
-    txt = subprocess.run(["ncu", "-i", f"gpurun_out/{tag}_wf_{k}.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rr = list(csv.reader(txt.splitlines()))
+txt = subprocess.run(["ncu", "-i", f"gpurun_out/{tag}_wf_all.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rr = list(csv.reader(txt.splitlines()))
+i_name = rr[0].index("Kernel Name")
+for row in rr[2:]:
     m = {}
-    for h, u, v in zip(rr[0], rr[1], rr[2]):
+    for h, u, v in zip(rr[0], rr[1], row):
         if h in want or ("smsp__average_warps_issue_stalled" in h and h.endswith("per_issue_active.ratio")):
             try:
                 fv = float(v.replace(",", ""))
@@ -63,7 +65,7 @@ for k in ("trace", "shade"):
             if "stalled" in h and fv < 0.2:
                 continue
             m[h] = [fv, u]
-    summ["k_wf_" + k] = m
+    summ[row[i_name].split("(")[0].replace("void ", "").split("<")[0]] = m
 json.dump(summ, open(f"profiles/{tag}_ncu_full_summary.json", "w"), indent=1)
 for k, m in summ.items():
     print(k, {h.split(".")[0].replace("smsp__average_warps_issue_stalled_", "stall_").replace("_per_issue_active", ""): round(v[0], 2) for h, v in m.items()})
