@@ -20,6 +20,17 @@ out["triangles"], out["generate_s"] = n, round(time.time() - t, 2)
 t = time.time()
 scene = rtb200.Scene.load_gltf("/tmp/sc/c5.gltf", 1920, 1080, spp)
 out["load_and_bvh_build_s"] = round(time.time() - t, 2)
+if os.environ.get("CACHE", "1") != "0":      # on-disk cache of the built hierarchies (rt_scene_load_gltf_cached)
+    del scene
+    os.makedirs("/tmp/sc/cache", exist_ok=True)
+    t = time.time()
+    scene = rtb200.Scene.load_gltf("/tmp/sc/c5.gltf", 1920, 1080, spp, cache_dir="/tmp/sc/cache")
+    out["load_build_and_write_cache_s"], hit0 = round(time.time() - t, 2), scene.cache_hit
+    del scene
+    t = time.time()
+    scene = rtb200.Scene.load_gltf("/tmp/sc/c5.gltf", 1920, 1080, spp, cache_dir="/tmp/sc/cache")
+    out["load_from_cache_s"], out["cache_hit"] = round(time.time() - t, 2), [hit0, scene.cache_hit]
+    out["cache_file_GB"] = round(sum(os.path.getsize(os.path.join("/tmp/sc/cache", f)) for f in os.listdir("/tmp/sc/cache")) / 1e9, 2)
 out["bvh_nodes"], out["bvh_depth"] = int(scene.info.bvh_nodes[2]), int(scene.info.bvh_depth[2])
 ctx = rtb200.Context(0)
 t = time.time()
