@@ -147,3 +147,70 @@ def test_renders_agree_on_adversarial_soups(ctx, flavour):
         images.append(ctx.accum())
     assert images[0].tobytes() == images[1].tobytes() == images[2].tobytes()
     assert np.isfinite(images[0]).all() and images[0].sum() > 0
+
+
+def _random_text_scene(rng, n_shapes, n_tris):
+    """A random scene of the TEXT format's kinds: planes, rotated boxes and ellipsoids, and
+    model-space triangles with their own position + rotation (src/scene.rs:139-165), a third of the
+    primitives emissive so that all three light hierarchies are populated."""
+    raw = RawScene(width=40, height=32, samples=2, ray_depth=5)
+    raw.tri_mode = T.TRI_MODEL
+    raw.cam_position = (0.0, 0.5, -9.0)
+    raw.bg_color = (0.1, 0.1, 0.2)
+    raw.materials = [{"kind": T.MAT_DIFFUSE, "color": (0.7, 0.7, 0.7)}, {"kind": T.MAT_DIFFUSE, "emission": (4.0, 3.0, 2.0)},
+                     {"kind": T.MAT_METALLIC, "color": (0.9, 0.8, 0.7)}, {"kind": T.MAT_DIELECTRIC, "ior": 1.4, "color": (1.0, 1.0, 1.0)}]
+
+    def quat():
+        q = rng.normal(size=4)
+        return tuple(q / np.linalg.norm(q))
+
+    shapes = [{"type": T.SHAPE_PLANE, "material": 0, "param": (0.0, 1.0, 0.0), "position": (0.0, -3.0, 0.0)},
+              {"type": T.SHAPE_PLANE, "material": 0, "param": tuple(rng.normal(size=3)), "position": (0.0, 0.0, 6.0), "rotation": quat()}]
+    for _ in range(n_shapes):
+        shapes.append({"type": int(rng.choice([T.SHAPE_BOX, T.SHAPE_ELLIPSOID])), "material": int(rng.choice([0, 0, 1, 2, 3])),
+                       "param": tuple(10.0 ** rng.uniform(-1.5, 0.3, 3)), "position": tuple(rng.uniform(-3, 3, 3)), "rotation": quat()})
+    raw.shapes = shapes
+    c = rng.uniform(-3, 3, (n_tris, 1, 3))
+    raw.tri_pos = (c + rng.normal(scale=0.6, size=(n_tris, 3, 3))).reshape(n_tris, 9)
+    raw.tri_mat = rng.choice([0, 0, 1, 2, 3], n_tris).astype(np.uint32)
+    xf = np.zeros((n_tris, 7))
+    xf[:, :3] = rng.uniform(-1, 1, (n_tris, 3))
+    q = rng.normal(size=(n_tris, 4))
+    xf[:, 3:] = q / np.linalg.norm(q, axis=1, keepdims=True)
+    raw.tri_xform = xf
+    return raw
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_random_text_format_scenes(orc, ctx, seed):
+    """All four primitive kinds with random rotations, all three materials, all three light
+    hierarchies: hits and light PDFs bitwise against the oracle in EXACT mode, FAST == EXACT,
+    and the three render paths agree bit for bit."""
+    rng = np.random.default_rng(seed)
+    raw = _random_text_scene(rng, int(rng.integers(3, 40)), int(rng.integers(0, 400)))
+    prod, oracle = rtb200.Scene.from_raw(raw), orc.OracleScene(raw)
+    helpers.assert_scene_equal(prod, oracle)
+    ctx.upload(prod)
+    n = 20000
+    o = rng.uniform(-5, 5, (n, 3))
+    d = rng.normal(size=(n, 3)) * 10.0 ** rng.uniform(-2, 2, (n, 1))
+    axis = rng.uniform(size=n) < 0.15                           # zero direction components: the slab special cases
+    d[axis] = np.eye(3)[rng.integers(0, 3, axis.sum())] * rng.choice([-1.0, 1.0], (axis.sum(), 1))
+    inside = rng.uniform(size=n) < 0.2                          # origins inside boxes / ellipsoids
+    pick = rng.integers(2, len(raw.shapes), inside.sum())
+    o[inside] = np.array([raw.shapes[i]["position"] for i in pick]) + rng.normal(scale=0.01, size=(inside.sum(), 3))
+    exact = ctx.trace_rays(o, d, T.MODE_EXACT)
+    _assert_equal(exact, oracle.trace_rays(o, d)[0], "EXACT vs oracle")
+    _assert_equal(ctx.trace_rays(o, d, T.MODE_FAST), exact, "FAST vs EXACT")
+    assert len(set(exact["kind"].tolist())) >= 4                # misses, planes, boxes or ellipsoids, triangles all occur
+    dn = d / np.linalg.norm(d, axis=1, keepdims=True)
+    pe = ctx.light_pdf(o, dn, T.MODE_EXACT)
+    assert pe.tobytes() == oracle.light_pdf(o, dn)[0].tobytes()
+    assert ctx.light_pdf(o, dn, T.MODE_FAST).tobytes() == pe.tobytes()
+    images = []
+    for mode, sched in ((T.MODE_EXACT, T.SCHED_MEGAKERNEL), (T.MODE_FAST, T.SCHED_MEGAKERNEL), (T.MODE_FAST, T.SCHED_WAVEFRONT)):
+        ctx.render_accum(0, 2, 5, mode, sched, clear=True)
+        images.append(ctx.accum())
+    assert images[0].tobytes() == images[1].tobytes() == images[2].tobytes()
+    acc, _ = oracle.render_accum(0, 2, 5)
+    np.testing.assert_allclose(images[0], acc.reshape(images[0].shape), rtol=1e-9, atol=1e-12)
