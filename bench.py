@@ -305,7 +305,8 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args, n_tris), "spp_per_step_per_gpu": S, "mode": args.mode,
                        "scheduler": args.sched, "shard": args.shard if world > 1 else "none", "l2": f"inputs larger than L2: {scene_bytes / 1e6:.0f} MB of scene records per GPU, no flush",
-                       "segments_per_path": segments / max(1.0, paths), "light_pdf_rays_per_segment": lrays / max(1.0, segments)},
+                       "segments_per_path": segments / max(1.0, paths), "light_pdf_rays_per_segment": lrays / max(1.0, segments),
+                       "exact_fallbacks_per_million_segments": 1e6 * counters.get("exact_fallbacks", 0) / max(1.0, segments / world)},
             "time_to_1024spp_s": (ms * 1e-3) / max(1, args.steps) / (S * world) * 1024,
             "gpu_launches": int(counters["kernel_launches"]),
             "clocks": clocks,

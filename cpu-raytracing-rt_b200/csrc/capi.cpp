@@ -819,6 +819,7 @@ int rt_get_counters(rt_ctx *ctx, rt_counters *out) {
     out->aabb_tests = c.aabb_tests; out->prim_tests = c.prim_tests;
     out->light_aabb_tests = c.light_aabb_tests; out->light_prim_tests = c.light_prim_tests;
     out->kernel_launches = ctx->launches;
+    out->exact_fallbacks = c.exact_fallbacks;
     return RT_OK;
 }
 int rt_reset_counters(rt_ctx *ctx) {

@@ -119,6 +119,7 @@ struct DRegion {
 
 struct DCounters {                      // mirrors rt_counters (kernel_launches is host-side)
     unsigned long long segments, light_pdf_rays, paths, aabb_tests, prim_tests, light_aabb_tests, light_prim_tests;
+    unsigned long long exact_fallbacks;     // FAST mode: rays handed to the exact traversal (failed proof, tie, list overflow)
 };
 
 }  // namespace rt

@@ -15,6 +15,7 @@ constexpr uint32_t kNoChild = 0xFFFFFFFFu;
 
 struct Cnt {                            // per-thread event counters, flushed once per kernel
     uint32_t seg = 0, lray = 0, paths = 0, aabb = 0, prim = 0, laabb = 0, lprim = 0;
+    uint32_t xf = 0;                    // FAST mode: rays handed to the exact traversal
 };
 
 RT_D double dinf() { return __longlong_as_double(0x7FF0000000000000ll); }

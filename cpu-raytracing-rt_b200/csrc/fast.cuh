@@ -434,7 +434,7 @@ RT_D SceneHit intersect_fast(const DScene &sc, d3 o, d3 d, Cnt &c) {
     bool skip;
     const float tmax0 = shapes_tmax(sb, skip);
     if (!skip) closest_fast(sc.ftris, sc.tri_i, o, d, tmax0, fb);
-    if (triangle_hit_needs_exact(sc, o, d, sb, fb)) return intersect_exact_cold(sc, o, d);
+    if (triangle_hit_needs_exact(sc, o, d, sb, fb)) { ++c.xf; return intersect_exact_cold(sc, o, d); }
     return finish_hit(sc, o, d, sb, fb);
 }
 
@@ -502,9 +502,10 @@ static __device__ __noinline__ void light_tris_exact_cold(const DScene &sc, d3 o
     light_hits_exact<3>(sc.ltris, sc.ltri_i, sc.ltri_s, o, dir, impact, scratch);
 }
 // the emissive triangles' part of Light::pdf, added to `impact` (which holds the analytic lights' part)
-RT_D void light_tris_impact_fast(const DScene &sc, d3 o, d3 dir, double &impact) {
+RT_D void light_tris_impact_fast(const DScene &sc, d3 o, d3 dir, double &impact, Cnt &c) {
     const double base = impact;
     if (light_hits_fast(sc.fltris, sc.ltri_i, sc.ltri_s, o, dir, impact)) {
+        ++c.xf;
         impact = base;
         light_tris_exact_cold(sc, o, dir, impact);
     }
@@ -512,7 +513,7 @@ RT_D void light_tris_impact_fast(const DScene &sc, d3 o, d3 dir, double &impact)
 RT_D double light_pdf_fast(const DScene &sc, d3 o, d3 dir, Cnt &c) {
     ++c.lray;
     double impact = light_shapes_impact(sc, o, dir, c);
-    light_tris_impact_fast(sc, o, dir, impact);
+    light_tris_impact_fast(sc, o, dir, impact, c);
     return impact / (double)sc.n_lights;
 }
 

@@ -13,13 +13,13 @@ namespace rt {
 
 // ---- helpers ---------------------------------------------------------------------------------
 __device__ __forceinline__ void flush_counters(const Cnt &c, DCounters *out) {
-    unsigned long long v[7] = {c.seg, c.lray, c.paths, c.aabb, c.prim, c.laabb, c.lprim};
-    unsigned long long *dst[7] = {&out->segments, &out->light_pdf_rays, &out->paths, &out->aabb_tests,
-                                  &out->prim_tests, &out->light_aabb_tests, &out->light_prim_tests};
+    unsigned long long v[8] = {c.seg, c.lray, c.paths, c.aabb, c.prim, c.laabb, c.lprim, c.xf};
+    unsigned long long *dst[8] = {&out->segments, &out->light_pdf_rays, &out->paths, &out->aabb_tests,
+                                  &out->prim_tests, &out->light_aabb_tests, &out->light_prim_tests, &out->exact_fallbacks};
     __syncwarp();                       // every lane of every warp reaches this call
     const int lane = threadIdx.x & 31;
 #pragma unroll
-    for (int k = 0; k < 7; ++k) {
+    for (int k = 0; k < 8; ++k) {
         unsigned long long s = v[k];
         for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xFFFFFFFFu, s, off);
         if (lane == 0 && s) atomicAdd(dst[k], s);

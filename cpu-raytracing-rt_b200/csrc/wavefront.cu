@@ -37,19 +37,10 @@ constexpr uint32_t kNoShape = 0xFFFFFFFFu;
 RT_D d3 ld_soa(const double *base, uint32_t n, uint32_t i) { return mk3(base[i], base[n + i], base[2u * n + i]); }
 RT_D void st_soa(double *base, uint32_t n, uint32_t i, d3 v) { base[i] = v.x; base[n + i] = v.y; base[2u * n + i] = v.z; }
 
-#ifndef WF_COUNT_DEFER
-#define WF_COUNT_DEFER 0
-#endif
 __device__ __forceinline__ void flush_counters_wf(const Cnt &c, DCounters *out) {
-#if WF_COUNT_DEFER
-    constexpr int kN = 6;       // diagnostics: deferred slots by reason in the (otherwise unused in FAST mode) test counters
-    unsigned long long v[kN] = {c.seg, c.lray, c.paths, c.aabb, c.laabb, c.lprim};
-    unsigned long long *dst[kN] = {&out->segments, &out->light_pdf_rays, &out->paths, &out->aabb_tests, &out->light_aabb_tests, &out->light_prim_tests};
-#else
-    constexpr int kN = 3;
-    unsigned long long v[kN] = {c.seg, c.lray, c.paths};
-    unsigned long long *dst[kN] = {&out->segments, &out->light_pdf_rays, &out->paths};
-#endif
+    constexpr int kN = 4;
+    unsigned long long v[kN] = {c.seg, c.lray, c.paths, c.xf};
+    unsigned long long *dst[kN] = {&out->segments, &out->light_pdf_rays, &out->paths, &out->exact_fallbacks};
     const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int k = 0; k < kN; ++k) {
@@ -118,7 +109,7 @@ __global__ void k_wf_init(WfBuf b, DRegion rg, uint32_t width) {
 #ifndef WF_CONFIRM_MINB
 #define WF_CONFIRM_MINB 8
 #endif
-__global__ void __launch_bounds__(128, WF_CONFIRM_MINB) k_wf_confirm(DScene sc, WfBuf b, int list) {
+__global__ void __launch_bounds__(128, WF_CONFIRM_MINB) k_wf_confirm(DScene sc, WfBuf b, int list, DCounters *ctr) {
     __shared__ uint32_t s_slot[128];
     __shared__ uint16_t s_pair[128 * 2 * kWfCand];
     __shared__ uint32_t s_warp[4];
@@ -227,6 +218,7 @@ __global__ void __launch_bounds__(128, WF_CONFIRM_MINB) k_wf_confirm(DScene sc, 
         if (need_exact) {
             b.flags[slot] = flags | kFlagExactPending;
             b.xlist[atomicAdd(b.n_x, 1u)] = slot;
+            atomicAdd(&ctr->exact_fallbacks, 1ull);     // rare
         }
     }
 }
@@ -710,7 +702,7 @@ cudaError_t launch_render_wavefront(cudaStream_t st, const DScene &sc, uint32_t 
     auto issue_iteration = [&](int from) {
         cudaMemsetAsync(&b.n_live[2 * (from ^ 1)], 0, 2 * sizeof(uint32_t), st);   // next list starts empty
         cudaMemsetAsync(b.cursor, 0, 2 * sizeof(uint32_t), st);              // trace fetch position, deferred-slot count (cursor[1])
-        k_wf_confirm<<<blocks, 128, 0, st>>>(sc, b, from);
+        k_wf_confirm<<<blocks, 128, 0, st>>>(sc, b, from, ctr);
         // fork: k_wf_exact works on the few slots the confirm pass handed over while the shade and
         // trace kernels run (they skip those slots); joined at the end of the iteration
         cudaEventRecord(ev_fork, st);

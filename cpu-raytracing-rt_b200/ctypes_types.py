@@ -72,7 +72,7 @@ class Counters(C.Structure):
     _fields_ = [("segments", C.c_uint64), ("light_pdf_rays", C.c_uint64), ("paths", C.c_uint64),
                 ("aabb_tests", C.c_uint64), ("prim_tests", C.c_uint64),
                 ("light_aabb_tests", C.c_uint64), ("light_prim_tests", C.c_uint64),
-                ("kernel_launches", C.c_uint64)]
+                ("kernel_launches", C.c_uint64), ("exact_fallbacks", C.c_uint64)]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

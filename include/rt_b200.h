@@ -286,6 +286,9 @@ typedef struct rt_counters {
     uint64_t light_aabb_tests;      /* same two for the all-hits light traversals           */
     uint64_t light_prim_tests;
     uint64_t kernel_launches;       /* kernels of this library launched since the last reset */
+    uint64_t exact_fallbacks;       /* FAST mode: rays answered by the exact traversal because the
+                                       proof that the reference finds the same hit failed (a hit
+                                       on the edge of its own box, a tie, a full candidate list) */
 } rt_counters;
 RT_API int rt_get_counters(rt_ctx *ctx, rt_counters *out);      /* syncs the stream */
 RT_API int rt_reset_counters(rt_ctx *ctx);

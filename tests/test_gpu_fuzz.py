@@ -110,8 +110,11 @@ def test_fast_equals_exact_equals_oracle_on_adversarial_soups(orc, ctx, flavour,
     ctx.upload(prod)
     o, d, _ = _rays(rng, tri, 40000)
     exact = ctx.trace_rays(o, d, T.MODE_EXACT)
+    ctx.reset_counters()
     fast = ctx.trace_rays(o, d, T.MODE_FAST)
     _assert_equal(fast, exact, "FAST vs EXACT")
+    # these inputs are built so that the proof fails often: the exact traversal must have been used
+    assert ctx.counters()["exact_fallbacks"] > 0
     sub = slice(0, 6000)
     _assert_equal(exact[sub], oracle.trace_rays(o[sub], d[sub])[0], "EXACT vs oracle")
     assert (exact["kind"] >= 0).mean() > 0.2

@@ -25,4 +25,4 @@ for rep in range(reps):
     dt = time.time() - t
     c = ctx.counters()
     print("render %d spp: %.1f ms, %.1f Mseg/s launches %d%s" % (spp, dt * 1e3, c["segments"] / dt / 1e6, c["kernel_launches"],
-          " deferred %d (light fragile %d, closest fragile %d, rest ties) of %d segments" % (c["aabb_tests"], c["light_aabb_tests"], c["light_prim_tests"], c["segments"]) if c["aabb_tests"] else ""), flush=True)
+          " exact fallbacks %d" % c["exact_fallbacks"]), flush=True)
