@@ -53,3 +53,22 @@ def test_custom_and_gltf_cli(orc, tmp_path):
     # a panic in the reference is a non-zero exit here
     r = subprocess.run([BIN, "glTF", os.path.join(str(tmp_path), "missing.gltf"), "4", "4", "1", out2], capture_output=True, text=True)
     assert r.returncode == 101
+
+
+def test_cli_cache_and_preview(tmp_path):
+    """RT_BVH_CACHE (on-disk hierarchy cache) and RT_PREVIEW (output rewritten after every chunk)
+    change how the image is produced, never the image."""
+    gltf, _ = helpers.heightfield(tmp_path, 30, 60)
+    cache = os.path.join(str(tmp_path), "cache")
+    os.makedirs(cache)
+    env = dict(os.environ, RT_SEED="777")
+    images = []
+    for k, extra in enumerate(({}, {"RT_BVH_CACHE": cache}, {"RT_BVH_CACHE": cache, "RT_PREVIEW": "1"})):
+        out = os.path.join(str(tmp_path), f"c{k}.ppm")
+        r = subprocess.run([BIN, "glTF", gltf, "48", "32", "45", out], capture_output=True, text=True, env=dict(env, **extra), timeout=300)
+        assert r.returncode == 0, r.stderr
+        percents = [ln for ln in r.stdout.split("\n") if ln.endswith("%")]
+        assert percents[-1] == "100%" and len(percents) == len(set(percents)) >= 10       # 45 spp in chunks of 3
+        images.append(_read_ppm(out))
+    assert len(os.listdir(cache)) == 1                      # written by the second run, read by the third
+    assert np.array_equal(images[0], images[1]) and np.array_equal(images[0], images[2])
