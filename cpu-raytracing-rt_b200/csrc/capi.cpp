@@ -96,7 +96,7 @@ cudaError_t ensure_wavefront(rt_ctx *ctx) {
     b.cand = (uint32_t *)take((size_t)n * 4 * kWfCand);
     b.lcand = (uint32_t *)take((size_t)n * 4 * kWfCand);
     double **res[4] = {&b.res_t, &b.res_u, &b.res_v, &b.lres};
-    for (double **q : res) *q = (double *)take((size_t)n * 8 * kWfCand);
+    for (double **q : res) *q = (double *)take((size_t)n * 8);
     b.live[0] = (uint32_t *)take((size_t)n * 4);
     b.live[1] = (uint32_t *)take((size_t)n * 4);
     b.n_live = (uint32_t *)take(16);

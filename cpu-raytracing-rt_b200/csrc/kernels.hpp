@@ -24,8 +24,8 @@ struct WfBuf {                          // per-pixel path slots, structure of ar
     double *pcos, *pimp, *sh_t;         // n: Cosine::pdf, light impact of analytic lights, shapes' best t
     uint32_t *sh_id, *rng_block, *rng_s0, *rng_s1, *sample, *flags, *ncand;    // n
     uint32_t *cand, *lcand;             // kWfCand * n: triangle candidates (scene / lights) that survived the fp32 pre-test
-    double *res_t, *res_u, *res_v;      // kWfCand * n: k_wf_confirm's exact (t, u, v) per scene candidate; u == -1: no hit
-    double *lres;                       // kWfCand * n: exact Light::pdf term per light candidate; -1: no hit
+    double *res_t, *res_u, *res_v;      // n: exact (t, u, v) of the nearest confirmed triangle (k_wf_confirm / k_wf_exact), valid when ncand = 1
+    double *lres;                       // n: complete Light::pdf impact of the ray in flight (analytic lights + emissive triangles)
     uint32_t *live[2];                  // n each: compacted indices of slots with work
     uint32_t *n_live;                   // [4]: per list, entries filled from the front / from the back (8-byte aligned pairs)
     uint32_t *cursor;                   // trace kernel's fetch position in the live list

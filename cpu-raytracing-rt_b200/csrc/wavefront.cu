@@ -109,11 +109,15 @@ __global__ void k_wf_init(WfBuf b, DRegion rg, uint32_t width) {
 #ifndef WF_CONFIRM_MINB
 #define WF_CONFIRM_MINB 8
 #endif
+// pair results a block keeps in shared memory between the two phases (0.9 pairs per ray on C3: 128
+// rays need ~115); the rays of a block whose pairs do not fit are answered by k_wf_exact
+constexpr uint32_t kConfirmPairs = 448;
 __global__ void __launch_bounds__(128, WF_CONFIRM_MINB) k_wf_confirm(DScene sc, WfBuf b, int list, DCounters *ctr) {
     __shared__ uint32_t s_slot[128];
     __shared__ uint16_t s_pair[128 * 2 * kWfCand];
     __shared__ uint32_t s_warp[4];
     __shared__ double s_ray[6][128];
+    __shared__ double s_t[kConfirmPairs], s_u[kConfirmPairs], s_v[kConfirmPairs];   // phase 1 -> phase 2
     const uint32_t tid = threadIdx.x, i = blockIdx.x * 128 + tid, lane = tid & 31, wid = tid >> 5;
     const LiveList ll = live_list(b, list);
     const uint32_t N = b.n;
@@ -159,7 +163,7 @@ __global__ void __launch_bounds__(128, WF_CONFIRM_MINB) k_wf_confirm(DScene sc, 
     for (uint32_t k = 0; k < nc; ++k) s_pair[base + nl + k] = (uint16_t)(tid | (k << 7));
     __syncthreads();
     // ---- phase 1: pairs.  res_u / lres: -1 = no hit, -2 = a hit the reference may not reach
-    for (uint32_t e = tid; e < total; e += 128) {
+    for (uint32_t e = tid; e < min(total, kConfirmPairs); e += 128) {
         const uint32_t pr = s_pair[e], owner = pr & 127u, k = (pr >> 7) & 7u;
         const bool light = (pr & 0x400u) != 0;
         const size_t at = (size_t)k * N + s_slot[owner];
@@ -178,34 +182,34 @@ __global__ void __launch_bounds__(128, WF_CONFIRM_MINB) k_wf_confirm(DScene sc, 
                 const double inv_area = __ldg(&sc.ltri_s[prim].inv_area);
                 term = inv_area * (t * t / fabs(dot3(d, mk3(q0.x, q0.y, q1.x))));
             }
-            b.lres[at] = term;
+            s_t[e] = term;
         } else {
-            b.res_u[at] = hit ? (frag ? -2.0 : u) : -1.0;
-            if (hit) { b.res_t[at] = t; b.res_v[at] = v; }
+            s_u[e] = hit ? (frag ? -2.0 : u) : -1.0;
+            s_t[e] = t; s_v[e] = v;
         }
     }
-    __syncthreads();                                    // the block's results are visible to the block
+    __syncthreads();
     // ---- phase 2: one ray per thread
     if (mine) {
         // a candidate list that overflowed (rare: more than kWfCand survivors of the fp32 pre-test)
         // is not worth a second fp32 search: the exact traversal answers the ray
-        bool need_exact = (nc_all & (kOverflowClosest | kOverflowLight)) != 0;
-        if ((flags & kFlagPendLight) && !(nc_all & kOverflowLight)) {
+        bool need_exact = (nc_all & (kOverflowClosest | kOverflowLight)) != 0 || base + nl + nc > kConfirmPairs;
+        if ((flags & kFlagPendLight) && !need_exact) {
             double impact = b.pimp[slot];
             for (uint32_t k = 0; k < nl; ++k) {
-                const double term = b.lres[(size_t)k * N + slot];
+                const double term = s_t[base + k];
                 if (term == -2.0) need_exact = true;
                 else if (term != -1.0) impact += term;
             }
             b.lres[slot] = impact;
         }
-        if (!(nc_all & kOverflowClosest)) {
+        if (!need_exact) {
             FBest fb;
             fbest_clear(fb);
             for (uint32_t k = 0; k < nc; ++k) {
-                const size_t at = (size_t)k * N + slot;
-                const double u = b.res_u[at];
-                if (u != -1.0) fbest_take(fb, b.res_t[at], u, b.res_v[at], b.cand[at], u == -2.0);
+                const uint32_t e = base + nl + k;
+                const double u = s_u[e];
+                if (u != -1.0) fbest_take(fb, s_t[e], u, s_v[e], b.cand[(size_t)k * N + slot], u == -2.0);
             }
             if (fb.has) {
                 const d3 o = mk3(s_ray[0][tid], s_ray[1][tid], s_ray[2][tid]), d = mk3(s_ray[3][tid], s_ray[4][tid], s_ray[5][tid]);
@@ -666,7 +670,7 @@ __global__ void __launch_bounds__(128) k_wf_finish(DScene sc, WfBuf b, int list,
 }
 
 // ---- host loop -----------------------------------------------------------------------------------
-size_t wf_bytes_per_slot() { return 15 * 8 + 3 * 8 + 7 * 4 + kWfCand * 8 + kWfCand * 32 + 3 * 4; }
+size_t wf_bytes_per_slot() { return 15 * 8 + 3 * 8 + 7 * 4 + kWfCand * 8 + 4 * 8 + 3 * 4; }
 int wf_trace_blocks(int device) {
     int sms = 148, per_sm = 4;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
