@@ -412,6 +412,9 @@ __global__ void __launch_bounds__(128) k_wf_exact(DScene sc, WfBuf b) {
 #define WF_VOTE_I 1            // the INNER step runs when WF_VOTE_I * (#lanes at a node) >= WF_VOTE_T * (#lanes at a leaf)
 #define WF_VOTE_T 1
 #endif
+#ifndef WF_TAIL_DIV
+#define WF_TAIL_DIV 16         // hand the last n/16 live slots to the tail kernel; measured 2 / 4 / 8 / 16 / 64 / 256 -> 1017 / 794 / 750 / 750 / 764 / 792 ms per 256 spp
+#endif
 #ifndef WF_REFILL
 #define WF_REFILL 16
 #endif
@@ -689,7 +692,7 @@ cudaError_t launch_render_wavefront(cudaStream_t st, const DScene &sc, uint32_t 
     bool poll_pending = false, finished = false;
     // scenes without planes / boxes / ellipsoids (every glTF scene) run the kernel compiled without them
     const bool shapes = sc.n_planes || sc.boxes.n_prims || sc.ellipsoids.n_prims || sc.lboxes.n_prims || sc.lellipsoids.n_prims;
-    const uint32_t tail_threshold = n_region / 16 + 1;       // below this many live slots, finish in one kernel
+    const uint32_t tail_threshold = n_region / WF_TAIL_DIV + 1;       // below this many live slots, finish in one kernel
     // One iteration = 2 memset nodes + shade + trace; four iterations (ending on the list they
     // started from) are captured ONCE into a CUDA graph and replayed, so the host issues one launch
     // per four iterations instead of sixteen — the inner loop is launch-bound on small images and
