@@ -10,6 +10,9 @@
 #include <cstring>
 #include <limits>
 #include <stdexcept>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <thread>
 
 #include "scene_host.hpp"
@@ -48,19 +51,35 @@ inline int64_t order_key(double v) {            // f64::total_cmp as an integer 
 struct Item {
     int64_t key;
     uint32_t idx;
+    uint32_t pos;                   // position before the sort: (key, pos) makes an unstable sort stable
 };
 
+// Runs fn(t) for t in [0, team) on `team` threads (the caller is one of them).  Used by the few
+// nodes at the top of the hierarchy, where one node is all the work there is: their sorts and
+// sweeps are split over the threads that the subtree tasks further down will use afterwards.
+template <class F>
+void run_team(int team, F &&fn) {
+    if (team <= 1) { fn(0); return; }
+    std::vector<std::thread> ts;
+    ts.reserve(team - 1);
+    for (int t = 1; t < team; ++t) ts.emplace_back([&fn, t]() { fn(t); });
+    fn(0);
+    for (auto &th : ts) th.join();
+}
+inline size_t chunk_begin(size_t n, int team, int t) { return n * (size_t)t / (size_t)team; }
+
 // Stable sort of `ord[0..n)` by the midpoint of `axis`.  Small ranges: insertion sort; large
-// ranges: LSD radix over the key bytes that actually differ; otherwise std::stable_sort.
+// ranges: LSD radix over the key bytes that actually differ; otherwise introsort on (key, position).
 struct Sorter {
     std::vector<Item> a, b;
-    void sort(const Box6 *boxes, uint32_t *ord, size_t n, int axis) {
+    void sort(const Box6 *boxes, uint32_t *ord, size_t n, int axis, int team = 1) {
         a.resize(n);
+        if (team > 1) { sort_team(boxes, ord, n, axis, team); return; }
         int64_t all_or = 0, all_and = -1;
         for (size_t i = 0; i < n; ++i) {
             const Box6 &bx = boxes[ord[i]];
             const int64_t k = order_key((bx.lo[axis] + bx.hi[axis]) / 2.0);     // src/bvh.rs:138
-            a[i] = Item{k, ord[i]};
+            a[i] = Item{k, ord[i], (uint32_t)i};
             all_or |= k;
             all_and &= k;
         }
@@ -74,9 +93,53 @@ struct Sorter {
         } else if (n >= 4096) {
             radix(n, (uint64_t)(all_or ^ all_and));
         } else {
-            std::stable_sort(a.begin(), a.end(), [](const Item &x, const Item &y) { return x.key < y.key; });
+            // introsort on (key, incoming position): the stable order without stable_sort's allocation
+            std::sort(a.begin(), a.end(), [](const Item &x, const Item &y) { return x.key < y.key || (x.key == y.key && x.pos < y.pos); });
         }
         for (size_t i = 0; i < n; ++i) ord[i] = a[i].idx;
+    }
+    // The same LSD radix sort with every pass split over a team: per-thread histograms of
+    // contiguous chunks, bucket offsets ordered (digit, thread), so the result is the stable
+    // order — identical to the sequential one.
+    void sort_team(const Box6 *boxes, uint32_t *ord, size_t n, int axis, int team) {
+        b.resize(n);
+        std::vector<int64_t> ors(team, 0), ands(team, -1);
+        run_team(team, [&](int t) {
+            int64_t o = 0, an = -1;
+            for (size_t i = chunk_begin(n, team, t); i < chunk_begin(n, team, t + 1); ++i) {
+                const Box6 &bx = boxes[ord[i]];
+                const int64_t k = order_key((bx.lo[axis] + bx.hi[axis]) / 2.0);
+                a[i] = Item{k, ord[i], (uint32_t)i};
+                o |= k; an &= k;
+            }
+            ors[t] = o; ands[t] = an;
+        });
+        int64_t all_or = 0, all_and = -1;
+        for (int t = 0; t < team; ++t) { all_or |= ors[t]; all_and &= ands[t]; }
+        const uint64_t differing = (uint64_t)(all_or ^ all_and);
+        Item *src = a.data(), *dst = b.data();
+        std::vector<size_t> hist((size_t)team * 256);
+        for (int pass = 0; pass < 8; ++pass) {
+            if (((differing >> (pass * 8)) & 0xFF) == 0) continue;
+            const int sh = pass * 8;
+            const uint64_t flip = pass == 7 ? 0x80u : 0u;
+            run_team(team, [&](int t) {
+                size_t *h = hist.data() + (size_t)t * 256;
+                for (int d = 0; d < 256; ++d) h[d] = 0;
+                for (size_t i = chunk_begin(n, team, t); i < chunk_begin(n, team, t + 1); ++i) ++h[(((uint64_t)src[i].key >> sh) & 0xFF) ^ flip];
+            });
+            size_t sum = 0;
+            for (int d = 0; d < 256; ++d)
+                for (int t = 0; t < team; ++t) { size_t &h = hist[(size_t)t * 256 + d]; const size_t c = h; h = sum; sum += c; }
+            run_team(team, [&](int t) {
+                size_t *h = hist.data() + (size_t)t * 256;
+                for (size_t i = chunk_begin(n, team, t); i < chunk_begin(n, team, t + 1); ++i) dst[h[(((uint64_t)src[i].key >> sh) & 0xFF) ^ flip]++] = src[i];
+            });
+            std::swap(src, dst);
+        }
+        run_team(team, [&](int t) {
+            for (size_t i = chunk_begin(n, team, t); i < chunk_begin(n, team, t + 1); ++i) ord[i] = src[i].idx;
+        });
     }
     void radix(size_t n, uint64_t differing) {
         b.resize(n);
@@ -96,6 +159,16 @@ struct Sorter {
         if (src != a.data()) std::memcpy(a.data(), src, n * sizeof(Item));
     }
 };
+
+// nodes this large split their own sorts / sweeps over idle threads (RT_TEAM_MIN overrides: tests)
+size_t team_min() {
+    static const size_t v = []() {
+        const char *e = std::getenv("RT_TEAM_MIN");
+        const long long x = e ? std::atoll(e) : 0;
+        return x >= 64 ? (size_t)x : (size_t)262144;
+    }();
+    return v;
+}
 
 struct BuildShared {
     const Box6 *boxes;
@@ -125,6 +198,49 @@ struct Worker {
         }
     }
 
+    // The same sweep over a team: min / max are exactly associative, so per-chunk partial boxes
+    // combined in order give bit-identical prefix and suffix boxes; every thread then scores its
+    // chunk and the first minimum over the chunks in order is the sequential answer (strict <).
+    void sweep_team(const uint32_t *ord, size_t n, int axis, size_t &best_first, double &best_score, int &best_axis, int team) {
+        suffix.resize(n);
+        std::vector<Box6> part(team), pre(team);
+        run_team(team, [&](int t) {             // suffix boxes inside each chunk
+            Box6 acc = empty_box();
+            const size_t lo = std::max<size_t>(chunk_begin(n, team, t), 1), hi = chunk_begin(n, team, t + 1);
+            for (size_t i = hi; i-- > lo;) { grow(acc, sh.boxes[ord[i]]); suffix[i] = acc; }
+            part[t] = acc;
+        });
+        std::vector<Box6> after(team);          // union of all chunks to the right of chunk t
+        Box6 acc = empty_box();
+        for (int t = team - 1; t >= 0; --t) { after[t] = acc; grow(acc, part[t]); }
+        run_team(team, [&](int t) {             // complete the suffix boxes, prefix box of each chunk
+            const size_t lo = std::max<size_t>(chunk_begin(n, team, t), 1), hi = chunk_begin(n, team, t + 1);
+            for (size_t i = lo; i < hi; ++i) grow(suffix[i], after[t]);
+            Box6 p = empty_box();
+            for (size_t i = chunk_begin(n, team, t); i < hi; ++i) grow(p, sh.boxes[ord[i]]);
+            pre[t] = p;
+        });
+        std::vector<Box6> before(team);
+        acc = empty_box();
+        for (int t = 0; t < team; ++t) { before[t] = acc; grow(acc, pre[t]); }
+        std::vector<size_t> bf(team, n);
+        std::vector<double> bs(team, best_score);
+        run_team(team, [&](int t) {
+            Box6 left = before[t];
+            size_t f = n;
+            double sc = best_score;             // candidates must beat the incoming best, like the sequential loop
+            for (size_t i = chunk_begin(n, team, t); i < chunk_begin(n, team, t + 1) && i + 1 < n; ++i) {
+                grow(left, sh.boxes[ord[i]]);
+                const size_t left_cnt = i + 1, right_cnt = n - left_cnt;
+                const double score = half_area(left) * (double)left_cnt + half_area(suffix[i + 1]) * (double)right_cnt;
+                if (score < sc) { f = left_cnt; sc = score; }
+            }
+            bf[t] = f; bs[t] = sc;
+        });
+        for (int t = 0; t < team; ++t)
+            if (bf[t] != n && bs[t] < best_score) { best_first = bf[t]; best_score = bs[t]; best_axis = axis; }
+    }
+
     // build_nodes, src/bvh.rs:75-113.  Nodes are appended to `out` in pre-order; child indices
     // are relative to out[0].
     uint32_t build(uint32_t *ord, size_t n, size_t global_offset, std::vector<HostNode> &out) {
@@ -138,12 +254,23 @@ struct Worker {
         size_t best_first = n;
         double best_score = half_area(box) * (double)n;
         int best_axis = -1;
-        for (int axis = 0; axis < 3; ++axis) {
-            sorter.sort(sh.boxes, ord, n, axis);
-            sweep(ord, n, axis, best_first, best_score, best_axis);
+        // a node of the top levels borrows the idle threads for its own sorts and sweeps
+        int team = 1;
+        if (n >= team_min()) {
+            const int want = (int)std::min<size_t>(n / (team_min() / 2), 64) - 1;
+            int got = 0;
+            while (got < want && sh.spare_threads.fetch_sub(1) > 0) ++got;
+            if (got < want) sh.spare_threads.fetch_add(1);          // undo the failed attempt
+            team = got + 1;
         }
+        for (int axis = 0; axis < 3; ++axis) {
+            sorter.sort(sh.boxes, ord, n, axis, team);
+            if (team > 1) sweep_team(ord, n, axis, best_first, best_score, best_axis, team);
+            else sweep(ord, n, axis, best_first, best_score, best_axis);
+        }
+        if (best_axis >= 0 && best_axis != 2) sorter.sort(sh.boxes, ord, n, best_axis, team);   // a stable re-sort by Z of a Z-sorted range is the identity
+        if (team > 1) sh.spare_threads.fetch_add(team - 1);
         if (best_axis < 0) return leaf();
-        if (best_axis != 2) sorter.sort(sh.boxes, ord, n, best_axis);   // a stable re-sort by Z of a Z-sorted range is the identity
         const uint32_t me = (uint32_t)out.size();
         out.push_back(HostNode{box, RT_NO_CHILD, RT_NO_CHILD, 0, 0});
         const size_t nl = best_first, nr = n - best_first;
@@ -341,6 +468,15 @@ void build_scene(const rt_raw_scene &raw, HostScene &s) {
         else if (sh.type == RT_SHAPE_PLANE) s.planes.push_back(bake_shape(sh, (uint32_t)s.planes.size()));
         else throw std::runtime_error("unknown shape type");
     }
+    // RT_TIMING=1: phase times of the host build on stderr (development aid)
+    const bool timing = std::getenv("RT_TIMING") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!timing) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[rt_b200] %-28s %8.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+        t0 = t1;
+    };
     std::vector<HostTri> tris(raw.n_triangles);
     {
         const uint64_t n = raw.n_triangles;
@@ -362,6 +498,7 @@ void build_scene(const rt_raw_scene &raw, HostScene &s) {
             if (emits(s.materials[p.material])) out.push_back(p);
         return out;
     };
+    lap("bake triangles");
     const bool gltf = raw.tri_mode == RT_TRI_BAKED && raw.n_shapes == 0;
     // lights first (src/scene.rs:209-213), then the scene sets (:215-220); glTF scenes use
     // BVH::new_empty for the shape hierarchies (gltf/scene_builder.rs:14-15): no nodes at all.
@@ -374,7 +511,9 @@ void build_scene(const rt_raw_scene &raw, HostScene &s) {
         make_bvh(std::move(ellipsoids), s.ellipsoids);
         make_bvh(std::move(boxes), s.boxes);
     }
+    lap("light + shape hierarchies");
     make_bvh(std::move(tris), s.tris);
+    lap("triangle hierarchy");
 }
 
 }  // namespace rt

@@ -276,3 +276,18 @@ def test_scene_cache_rejects_damaged_files(tmp_path):
     assert e.value.code == 4 and "pre-order" in str(e.value)
     with pytest.raises(rtb200.RtError):                             # unwritable cache directory
         rtb200.Scene.load_gltf(path, 16, 16, 1, cache_dir=str(tmp_path / "missing" / "dir"))
+
+
+def test_bvh_build_team_path_is_bit_exact():
+    """The top-level nodes of a large build split their own sorts and sweeps over idle threads
+    (scene_build.cpp: sort_team / sweep_team).  RT_TEAM_MIN=64 forces that path on every node of
+    the small test hierarchies (read once per process, hence the child process): the soups, the
+    tie-heavy grid and the 120k-triangle mesh must still match the oracle bit for bit."""
+    import subprocess
+    import sys
+    if os.environ.get("RT_TEAM_MIN"):
+        pytest.skip("already inside the forced-team run")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_host_scene.py", "-x", "-q", "-k", "soups or ties or larger_mesh"],
+                       cwd=root, env=dict(os.environ, RT_TEAM_MIN="64"), capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
