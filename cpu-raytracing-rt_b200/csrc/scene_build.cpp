@@ -70,11 +70,17 @@ inline size_t chunk_begin(size_t n, int team, int t) { return n * (size_t)t / (s
 
 // Stable sort of `ord[0..n)` by the midpoint of `axis`.  Small ranges: insertion sort; large
 // ranges: LSD radix over the key bytes that actually differ; otherwise introsort on (key, position).
+// LSD radix digits: 11 bits -> 6 passes over a 64-bit key instead of 8 (the 2048-entry histogram
+// still sits in L1)
+constexpr int kRadixBits = 11, kRadixPasses = 6;
+constexpr uint64_t kRadixMask = (1ull << kRadixBits) - 1;
+
 struct Sorter {
     std::vector<Item> a, b;
-    void sort(const Box6 *boxes, uint32_t *ord, size_t n, int axis, int team = 1) {
+    // returns true when no two keys are equal: the order is then a function of the keys alone
+    bool sort(const Box6 *boxes, uint32_t *ord, size_t n, int axis, int team = 1) {
         a.resize(n);
-        if (team > 1) { sort_team(boxes, ord, n, axis, team); return; }
+        if (team > 1) return sort_team(boxes, ord, n, axis, team);
         int64_t all_or = 0, all_and = -1;
         for (size_t i = 0; i < n; ++i) {
             const Box6 &bx = boxes[ord[i]];
@@ -96,12 +102,15 @@ struct Sorter {
             // introsort on (key, incoming position): the stable order without stable_sort's allocation
             std::sort(a.begin(), a.end(), [](const Item &x, const Item &y) { return x.key < y.key || (x.key == y.key && x.pos < y.pos); });
         }
-        for (size_t i = 0; i < n; ++i) ord[i] = a[i].idx;
+        bool ties = false;
+        ord[0] = a[0].idx;
+        for (size_t i = 1; i < n; ++i) { ord[i] = a[i].idx; ties |= a[i].key == a[i - 1].key; }
+        return !ties;
     }
     // The same LSD radix sort with every pass split over a team: per-thread histograms of
     // contiguous chunks, bucket offsets ordered (digit, thread), so the result is the stable
     // order — identical to the sequential one.
-    void sort_team(const Box6 *boxes, uint32_t *ord, size_t n, int axis, int team) {
+    bool sort_team(const Box6 *boxes, uint32_t *ord, size_t n, int axis, int team) {
         b.resize(n);
         std::vector<int64_t> ors(team, 0), ands(team, -1);
         run_team(team, [&](int t) {
@@ -118,42 +127,52 @@ struct Sorter {
         for (int t = 0; t < team; ++t) { all_or |= ors[t]; all_and &= ands[t]; }
         const uint64_t differing = (uint64_t)(all_or ^ all_and);
         Item *src = a.data(), *dst = b.data();
-        std::vector<size_t> hist((size_t)team * 256);
-        for (int pass = 0; pass < 8; ++pass) {
-            if (((differing >> (pass * 8)) & 0xFF) == 0) continue;
-            const int sh = pass * 8;
-            const uint64_t flip = pass == 7 ? 0x80u : 0u;
+        constexpr size_t kDigits = kRadixMask + 1;
+        std::vector<size_t> hist((size_t)team * kDigits);
+        for (int pass = 0; pass < kRadixPasses; ++pass) {
+            const int sh = pass * kRadixBits;
+            if (((differing >> sh) & kRadixMask) == 0) continue;
+            const uint64_t flip = pass == kRadixPasses - 1 ? (1ull << (63 - sh)) : 0u;
             run_team(team, [&](int t) {
-                size_t *h = hist.data() + (size_t)t * 256;
-                for (int d = 0; d < 256; ++d) h[d] = 0;
-                for (size_t i = chunk_begin(n, team, t); i < chunk_begin(n, team, t + 1); ++i) ++h[(((uint64_t)src[i].key >> sh) & 0xFF) ^ flip];
+                size_t *h = hist.data() + (size_t)t * kDigits;
+                for (size_t d = 0; d < kDigits; ++d) h[d] = 0;
+                for (size_t i = chunk_begin(n, team, t); i < chunk_begin(n, team, t + 1); ++i) ++h[(((uint64_t)src[i].key >> sh) & kRadixMask) ^ flip];
             });
             size_t sum = 0;
-            for (int d = 0; d < 256; ++d)
-                for (int t = 0; t < team; ++t) { size_t &h = hist[(size_t)t * 256 + d]; const size_t c = h; h = sum; sum += c; }
+            for (size_t d = 0; d < kDigits; ++d)
+                for (int t = 0; t < team; ++t) { size_t &h = hist[(size_t)t * kDigits + d]; const size_t c = h; h = sum; sum += c; }
             run_team(team, [&](int t) {
-                size_t *h = hist.data() + (size_t)t * 256;
-                for (size_t i = chunk_begin(n, team, t); i < chunk_begin(n, team, t + 1); ++i) dst[h[(((uint64_t)src[i].key >> sh) & 0xFF) ^ flip]++] = src[i];
+                size_t *h = hist.data() + (size_t)t * kDigits;
+                for (size_t i = chunk_begin(n, team, t); i < chunk_begin(n, team, t + 1); ++i) dst[h[(((uint64_t)src[i].key >> sh) & kRadixMask) ^ flip]++] = src[i];
             });
             std::swap(src, dst);
         }
+        std::vector<char> tie(team, 0);
         run_team(team, [&](int t) {
-            for (size_t i = chunk_begin(n, team, t); i < chunk_begin(n, team, t + 1); ++i) ord[i] = src[i].idx;
+            bool ties = false;
+            for (size_t i = chunk_begin(n, team, t); i < chunk_begin(n, team, t + 1); ++i) {
+                ord[i] = src[i].idx;
+                ties |= i > 0 && src[i].key == src[i - 1].key;
+            }
+            tie[t] = ties;
         });
+        for (int t = 0; t < team; ++t)
+            if (tie[t]) return false;
+        return true;
     }
     void radix(size_t n, uint64_t differing) {
         b.resize(n);
         Item *src = a.data(), *dst = b.data();
-        for (int pass = 0; pass < 8; ++pass) {
-            if (((differing >> (pass * 8)) & 0xFF) == 0) continue;      // byte identical in all keys
-            size_t hist[256] = {0};
-            const int sh = pass * 8;
-            // signed order: flip the top bit of the most significant byte
-            const uint64_t flip = pass == 7 ? 0x80u : 0u;
-            for (size_t i = 0; i < n; ++i) ++hist[(((uint64_t)src[i].key >> sh) & 0xFF) ^ flip];
+        for (int pass = 0; pass < kRadixPasses; ++pass) {
+            const int sh = pass * kRadixBits;
+            if (((differing >> sh) & kRadixMask) == 0) continue;        // digit identical in all keys
+            size_t hist[kRadixMask + 1] = {0};
+            // signed order: flip the sign bit, which is the top bit of the last (9-bit) digit
+            const uint64_t flip = pass == kRadixPasses - 1 ? (1ull << (63 - sh)) : 0u;
+            for (size_t i = 0; i < n; ++i) ++hist[(((uint64_t)src[i].key >> sh) & kRadixMask) ^ flip];
             size_t sum = 0;
-            for (int d = 0; d < 256; ++d) { size_t c = hist[d]; hist[d] = sum; sum += c; }
-            for (size_t i = 0; i < n; ++i) dst[hist[(((uint64_t)src[i].key >> sh) & 0xFF) ^ flip]++] = src[i];
+            for (size_t d = 0; d <= kRadixMask; ++d) { size_t c = hist[d]; hist[d] = sum; sum += c; }
+            for (size_t i = 0; i < n; ++i) dst[hist[(((uint64_t)src[i].key >> sh) & kRadixMask) ^ flip]++] = src[i];
             std::swap(src, dst);
         }
         if (src != a.data()) std::memcpy(a.data(), src, n * sizeof(Item));
@@ -179,6 +198,7 @@ struct Worker {
     BuildShared &sh;
     Sorter sorter;
     std::vector<Box6> suffix;
+    std::vector<uint32_t> saved[2];         // the X- and Y-sorted arrangements of the node being split
     explicit Worker(BuildShared &s) : sh(s) {}
 
     // Evaluates every split position of the current arrangement (src/bvh.rs:120-135).
@@ -263,12 +283,19 @@ struct Worker {
             if (got < want) sh.spare_threads.fetch_add(1);          // undo the failed attempt
             team = got + 1;
         }
+        bool tie_free[3];
         for (int axis = 0; axis < 3; ++axis) {
-            sorter.sort(sh.boxes, ord, n, axis, team);
+            tie_free[axis] = sorter.sort(sh.boxes, ord, n, axis, team);
+            // without equal keys the arrangement is a function of the keys alone: the re-sort by
+            // the winning axis below would reproduce exactly this one, so keep a copy instead
+            if (axis < 2 && tie_free[axis] && n > 32) saved[axis].assign(ord, ord + n);
             if (team > 1) sweep_team(ord, n, axis, best_first, best_score, best_axis, team);
             else sweep(ord, n, axis, best_first, best_score, best_axis);
         }
-        if (best_axis >= 0 && best_axis != 2) sorter.sort(sh.boxes, ord, n, best_axis, team);   // a stable re-sort by Z of a Z-sorted range is the identity
+        if (best_axis >= 0 && best_axis != 2) {     // a stable re-sort by Z of a Z-sorted range is the identity
+            if (tie_free[best_axis] && n > 32) std::memcpy(ord, saved[best_axis].data(), n * sizeof(uint32_t));
+            else sorter.sort(sh.boxes, ord, n, best_axis, team);
+        }
         if (team > 1) sh.spare_threads.fetch_add(team - 1);
         if (best_axis < 0) return leaf();
         const uint32_t me = (uint32_t)out.size();
