@@ -691,6 +691,11 @@ int rt_light_pdf(rt_ctx *ctx, int mode, uint64_t n, const double *pos, const dou
 int rt_render_accum(rt_ctx *ctx, const rt_render_params *p) {
     if (int r = need_scene(ctx)) return r;
     if (!p) return set_err(ctx, RT_ERR_INVALID_ARG, "null params");
+    rt_render_params resolved = *p;                     // RT_MODE_AUTO / RT_SCHED_AUTO -> what suits the scene
+    const bool has_tris = ctx->dsc.tris.n_prims != 0;
+    if (resolved.mode == RT_MODE_AUTO) resolved.mode = has_tris ? RT_MODE_FAST : RT_MODE_EXACT;
+    if (resolved.sched == RT_SCHED_AUTO) resolved.sched = (resolved.mode == RT_MODE_FAST && has_tris) ? RT_SCHED_WAVEFRONT : RT_SCHED_MEGAKERNEL;
+    p = &resolved;
     if (int r = check_mode(ctx, p->mode)) return r;
     if (p->sched != RT_SCHED_MEGAKERNEL && p->sched != RT_SCHED_WAVEFRONT) return set_err(ctx, RT_ERR_INVALID_ARG, "unknown scheduler");
     if ((uint64_t)p->sample_begin + p->sample_count > 0xFFFFFFFFull) return set_err(ctx, RT_ERR_INVALID_ARG, "sample range overflows u32");

@@ -68,7 +68,8 @@ int main(int argc, char **argv) {
     std::puts("Started raytracing");
     const char *seed_s = std::getenv("RT_SEED"), *mode_s = std::getenv("RT_MODE");
     const uint64_t seed = seed_s ? std::strtoull(seed_s, nullptr, 0) : 0xC0FFEEull;
-    const int mode = (mode_s && !std::strcmp(mode_s, "exact")) ? RT_MODE_EXACT : RT_MODE_FAST;
+    // default: FAST + wavefront for scenes with triangles, EXACT + megakernel for purely analytic ones
+    const int mode = !mode_s ? RT_MODE_AUTO : (!std::strcmp(mode_s, "exact") ? RT_MODE_EXACT : RT_MODE_FAST);
     std::vector<double> rgb((size_t)info.width * info.height * 3);
     // The reference prints "N%" lines while it renders (src/main.rs:105-110) and writes the image
     // once at the end.  Here the samples are rendered in 20 chunks: one line per chunk, and with
@@ -76,7 +77,7 @@ int main(int argc, char **argv) {
     const char *preview_s = std::getenv("RT_PREVIEW");
     Progress pg{output, info.width, info.height, preview_s && *preview_s && std::strcmp(preview_s, "0") != 0, 0};
     const uint32_t chunk = info.samples >= 20 ? (info.samples + 19) / 20 : 1;
-    const int sched = mode == RT_MODE_FAST ? RT_SCHED_WAVEFRONT : RT_SCHED_MEGAKERNEL;
+    const int sched = mode == RT_MODE_AUTO ? RT_SCHED_AUTO : (mode == RT_MODE_FAST ? RT_SCHED_WAVEFRONT : RT_SCHED_MEGAKERNEL);
     if (rt_render_progressive(ctx, seed, mode, sched, chunk, on_progress, &pg, rgb.data(), nullptr)) return die("render", ctx);
     if (pg.last_percent < 100) std::puts("100%");
     if (rt_save_ppm(output, info.width, info.height, rgb.data())) return die("Cannot create output file", nullptr);

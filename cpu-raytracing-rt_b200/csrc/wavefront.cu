@@ -412,6 +412,9 @@ __global__ void __launch_bounds__(128) k_wf_exact(DScene sc, WfBuf b) {
 #define WF_VOTE_I 1            // the INNER step runs when WF_VOTE_I * (#lanes at a node) >= WF_VOTE_T * (#lanes at a leaf)
 #define WF_VOTE_T 1
 #endif
+#ifndef WF_FINISH_MINB
+#define WF_FINISH_MINB 2
+#endif
 #ifndef WF_TAIL_DIV
 #define WF_TAIL_DIV 16         // hand the last n/16 live slots to the tail kernel; measured 2 / 4 / 8 / 16 / 64 / 256 -> 1017 / 794 / 750 / 750 / 764 / 792 ms per 256 spp
 #endif
@@ -616,7 +619,7 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
 // its throughput.  The remaining slots are then finished by one kernel in which every thread
 // runs its pixel's paths to completion (the megakernel loop, same arithmetic), starting from the
 // ray the last shade step handed over.
-__global__ void __launch_bounds__(128) k_wf_finish(DScene sc, WfBuf b, int list, uint32_t sample_begin, uint32_t sample_count,
+__global__ void __launch_bounds__(128, WF_FINISH_MINB) k_wf_finish(DScene sc, WfBuf b, int list, uint32_t sample_begin, uint32_t sample_count,
                                                    unsigned long long seed, double *__restrict__ accum, DCounters *ctr) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const LiveList ll = live_list(b, list);

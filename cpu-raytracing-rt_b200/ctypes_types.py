@@ -91,5 +91,5 @@ FOV_X, FOV_Y = 0, 1
 TRI_BAKED, TRI_MODEL = 0, 1
 BVH_BOXES, BVH_ELLIPSOIDS, BVH_TRIANGLES, BVH_LIGHT_BOXES, BVH_LIGHT_ELLIPSOIDS, BVH_LIGHT_TRIANGLES = range(6)
 NO_CHILD = 0xFFFFFFFF
-MODE_EXACT, MODE_FAST = 0, 1
-SCHED_MEGAKERNEL, SCHED_WAVEFRONT = 0, 1
+MODE_EXACT, MODE_FAST, MODE_AUTO = 0, 1, 2
+SCHED_MEGAKERNEL, SCHED_WAVEFRONT, SCHED_AUTO = 0, 1, 2

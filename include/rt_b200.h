@@ -202,10 +202,13 @@ RT_API int rt_scene_device_bytes(rt_ctx *ctx, uint64_t *bytes);
  * included) and its DFS visit order: it is the parity anchor.  FAST culls with conservative
  * fp32 boxes and an fp32 triangle pre-test, then confirms every candidate with the same exact
  * f64 test, so hit ids / t / normals are the EXACT ones ("fast mode"). */
-enum { RT_MODE_EXACT = 0, RT_MODE_FAST = 1 };
+enum { RT_MODE_EXACT = 0, RT_MODE_FAST = 1,
+       RT_MODE_AUTO = 2 };      /* render calls only: FAST + wavefront when the scene has triangles, else EXACT +
+                                   megakernel (analytic primitives gain nothing from fp32 culling; the images are
+                                   bit for bit the same either way).  Pair it with RT_SCHED_AUTO. */
 /* Schedulers for rt_render_accum: one persistent thread per pixel walking its samples
  * (megakernel), or queue-based wavefront with ballot/prefix-sum compaction of live paths. */
-enum { RT_SCHED_MEGAKERNEL = 0, RT_SCHED_WAVEFRONT = 1 };
+enum { RT_SCHED_MEGAKERNEL = 0, RT_SCHED_WAVEFRONT = 1, RT_SCHED_AUTO = 2 };
 
 typedef struct rt_hit {             /* intersections::Intersection + which primitive */
     double   t;

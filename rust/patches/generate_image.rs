@@ -51,7 +51,7 @@ fn generate_image(scene: &Scene) -> Image {
         check(rt_create(0, &mut ctx), std::ptr::null());
         check(rt_upload_scene(ctx, s), ctx);
         // Image.bytes is Vec<Vector3<f64>>: three f64 per pixel, row-major — the layout rt_render writes
-        check(rt_render(ctx, rand::random::<u64>(), RT_MODE_FAST, RT_SCHED_WAVEFRONT, img.bytes.as_mut_ptr() as *mut f64), ctx);
+        check(rt_render(ctx, rand::random::<u64>(), RT_MODE_AUTO, RT_SCHED_AUTO, img.bytes.as_mut_ptr() as *mut f64), ctx);
         rt_destroy(ctx);
         rt_scene_free(s);
     }

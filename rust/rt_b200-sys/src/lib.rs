@@ -17,8 +17,10 @@ pub const RT_TRI_BAKED: i32 = 0;
 pub const RT_TRI_MODEL: i32 = 1;
 pub const RT_MODE_EXACT: c_int = 0;
 pub const RT_MODE_FAST: c_int = 1;
+pub const RT_MODE_AUTO: c_int = 2;
 pub const RT_SCHED_MEGAKERNEL: c_int = 0;
 pub const RT_SCHED_WAVEFRONT: c_int = 1;
+pub const RT_SCHED_AUTO: c_int = 2;
 
 #[repr(C)]
 #[derive(Clone, Copy, Default)]

@@ -194,3 +194,25 @@ def test_progressive_render(ctx, tmp_path):
         ctx.render_progressive(3, lambda d, t, img: 1 // 0, seed=5)
     with pytest.raises(rtb200.RtError):
         ctx.render_progressive(0, None, seed=5)
+
+
+def test_auto_mode_picks_by_scene_and_changes_nothing(ctx, tmp_path):
+    """RT_MODE_AUTO / RT_SCHED_AUTO: wavefront FAST for scenes with triangles, megakernel EXACT for
+    purely analytic ones (one launch); the image is the explicit modes' image bit for bit."""
+    from tests import helpers
+    text = helpers.cornell(tmp_path, 40, 32, 3, 5, extra=False)          # planes, boxes, ellipsoids only
+    ctx.upload(rtb200.Scene.load_text(text))
+    ctx.reset_counters()
+    ctx.render_accum(0, 3, 9, T.MODE_AUTO, T.SCHED_AUTO, clear=True)
+    auto = ctx.accum()
+    assert ctx.counters()["kernel_launches"] == 1                         # the megakernel
+    ctx.render_accum(0, 3, 9, T.MODE_FAST, T.SCHED_WAVEFRONT, clear=True)
+    assert ctx.accum().tobytes() == auto.tobytes() and auto.sum() > 0
+    path, _ = helpers.heightfield(tmp_path, 24, 32)
+    ctx.upload(rtb200.Scene.load_gltf(path, 48, 32, 3))
+    ctx.reset_counters()
+    ctx.render_accum(0, 3, 9, T.MODE_AUTO, T.SCHED_AUTO, clear=True)
+    auto = ctx.accum()
+    assert ctx.counters()["kernel_launches"] > 4                          # the wavefront pipeline
+    ctx.render_accum(0, 3, 9, T.MODE_EXACT, T.SCHED_MEGAKERNEL, clear=True)
+    assert ctx.accum().tobytes() == auto.tobytes()
