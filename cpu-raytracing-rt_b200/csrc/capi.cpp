@@ -100,12 +100,19 @@ cudaError_t ensure_wavefront(rt_ctx *ctx) {
     b.live[0] = (uint32_t *)take((size_t)n * 4);
     b.live[1] = (uint32_t *)take((size_t)n * 4);
     b.n_live = (uint32_t *)take(16);
+    b.n_slots = n;
+    b.ring = kWfRing;
+    b.pix = (uint32_t *)take((size_t)n * 4);
+    b.ord = (uint32_t *)take((size_t)n * 4);
+    b.side = (double *)take((size_t)n * 24 * kWfRing);
+    b.item = (unsigned long long *)take(24);
+    b.plane = (uint32_t *)take(16);
     b.cursor = (uint32_t *)take(8);
     b.n_x = b.cursor + 1;
     b.xlist = (uint32_t *)take((size_t)n * 4);
     if ((size_t)(p - ctx->wf_arena) > total) return cudaErrorMemoryAllocation;
     if (!ctx->wf_host_live) {
-        e = cudaHostAlloc((void **)&ctx->wf_host_live, 2 * sizeof(uint32_t), cudaHostAllocDefault);
+        e = cudaHostAlloc((void **)&ctx->wf_host_live, 4 * sizeof(uint32_t), cudaHostAllocDefault);
         if (e != cudaSuccess) return e;
         e = cudaEventCreateWithFlags(&ctx->wf_event, cudaEventDisableTiming);
         if (e != cudaSuccess) return e;

@@ -18,7 +18,8 @@ cudaError_t launch_render_mega(cudaStream_t st, const DScene &sc, int mode, uint
                                uint64_t seed, double *accum, DCounters *ctr, DRegion rg);
 // ---- wavefront scheduler (wavefront.cu) ----------------------------------------------------------
 constexpr int kWfCand = 6;              // deferred candidates kept per ray and per search
-struct WfBuf {                          // per-pixel path slots, structure of arrays; n = width * height
+constexpr uint32_t kWfRing = 16;        // sample planes of finished radiance kept before they are added to the image, in order
+struct WfBuf {                          // path slots, structure of arrays; n = width * height = capacity of every array
     uint32_t n;
     double *ro, *rd, *T, *L, *pv;       // 3 * n: ray origin / direction, throughput, radiance, pending weight
     double *pcos, *pimp, *sh_t;         // n: Cosine::pdf, light impact of analytic lights, shapes' best t
@@ -29,6 +30,11 @@ struct WfBuf {                          // per-pixel path slots, structure of ar
     uint32_t *live[2];                  // n each: compacted indices of slots with work
     uint32_t *n_live;                   // [4]: per list, entries filled from the front / from the back (8-byte aligned pairs)
     uint32_t *cursor;                   // trace kernel's fetch position in the live list
+    uint32_t n_slots, ring;             // slots in use (<= n), planes in the ring of finished samples
+    uint32_t *pix, *ord;                // n: pixel (index in the image) / ordinal (in the region's tile order) a slot works on
+    double *side;                       // ring * 3 * n: radiance of finished samples: plane (sample % ring), component, ordinal
+    unsigned long long *item;           // [0] next unclaimed item, [1] claim limit, [2] items of this call
+    uint32_t *plane;                    // [0] planes added to accum, [1] oldest sample in flight, [2] ring, [3] planes complete
     uint32_t *xlist, *n_x;              // slots deferred to k_wf_exact in this iteration (n entries), their count (= cursor + 1)
 };
 size_t wf_bytes_per_slot();

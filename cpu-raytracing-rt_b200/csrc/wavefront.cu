@@ -22,6 +22,8 @@
 // the megakernel in FAST mode, so both schedulers produce bitwise the same accumulation buffer.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include "../../include/rt_b200.h"
 #include "fast.cuh"
 #include "kernels.hpp"
@@ -72,27 +74,29 @@ RT_D LiveList live_list(const WfBuf &b, int list) {
     return l;
 }
 
-#ifndef WF_TILE
-#define WF_TILE 1
-#endif
-__global__ void k_wf_init(WfBuf b, DRegion rg, uint32_t width) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, n = rg.w * rg.h;
-    if (i < n) {
-#if WF_TILE
-        // the static list walks the region in 8x4 pixel tiles, one tile per warp (partial tiles at
-        // the right / bottom edge shrink, the map stays a bijection): the camera rays a warp
-        // regenerates together — a run in the trace list — cover a compact patch of the image
-        const uint32_t ty = i / (4u * rg.w), r = i - ty * 4u * rg.w, ht = min(4u, rg.h - 4u * ty);
-        const uint32_t tx = r / (8u * ht), l = r - tx * 8u * ht, wt = min(8u, rg.w - 8u * tx);
-        const uint32_t slot = (rg.y0 + 4u * ty + l / wt) * width + rg.x0 + 8u * tx + l % wt;
-#else
-        const uint32_t ly = i / rg.w, slot = (rg.y0 + ly) * width + rg.x0 + (i - ly * rg.w);
-#endif
-        b.flags[slot] = 0;
-        b.sample[slot] = 0;
-        b.live[0][i] = slot;
+// ordinal i of a region (0 .. w*h-1) -> pixel index in the whole image.  The region is walked in
+// 8x4 pixel tiles, one tile per 32 consecutive ordinals (partial tiles at the right / bottom edge
+// shrink, the map stays a bijection): the camera rays a warp starts together — a run in the trace
+// list — cover a compact patch of the image.
+RT_D uint32_t region_tile_pixel(const DRegion &rg, uint32_t width, uint32_t i) {
+    const uint32_t ty = i / (4u * rg.w), r = i - ty * 4u * rg.w, ht = min(4u, rg.h - 4u * ty);
+    const uint32_t tx = r / (8u * ht), l = r - tx * 8u * ht, wt = min(8u, rg.w - 8u * tx);
+    return (rg.y0 + 4u * ty + l / wt) * width + rg.x0 + 8u * tx + l % wt;
+}
+__global__ void k_wf_init(WfBuf b, uint32_t n_px, uint32_t sample_count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < b.n_slots) {
+        b.flags[i] = 0;
+        b.sample[i] = 0;
+        b.live[0][i] = i;                               // the static list of all slots (k_wf_confirm)
     }
-    if (i == 0) { b.n_live[0] = n; b.n_live[1] = 0; b.n_live[2] = 0; b.n_live[3] = 0; *b.cursor = 0; }
+    if (i == 0) {
+        b.n_live[0] = b.n_slots; b.n_live[1] = 0; b.n_live[2] = 0; b.n_live[3] = 0;
+        b.cursor[0] = 0; b.cursor[1] = 0;
+        const unsigned long long total = (unsigned long long)n_px * sample_count, first = (unsigned long long)(b.ring - 2u) * n_px;
+        b.item[0] = 0; b.item[1] = first < total ? first : total; b.item[2] = total;
+        b.plane[0] = 0; b.plane[1] = 0xFFFFFFFFu; b.plane[2] = b.ring; b.plane[3] = 0;
+    }
 }
 
 // ---- confirm -----------------------------------------------------------------------------------
@@ -232,27 +236,31 @@ __global__ void __launch_bounds__(128, WF_CONFIRM_MINB) k_wf_confirm(DScene sc, 
 #define WF_SHADE_MINB 6        // glTF variant: 80 registers, no spills to speak of; measured 4 / 5 / 6 / 7 / 8 -> 1240 / 1270 / 1282 / 1276 / 1275 Mseg/s
 #endif
 template <bool SHAPES>
-__global__ void __launch_bounds__(128, SHAPES ? 4 : WF_SHADE_MINB) k_wf_shade(DScene sc, WfBuf b, int cur_list, uint32_t sample_begin, uint32_t sample_count,
-                                                  unsigned long long seed, double *__restrict__ accum, DCounters *ctr) {
+__global__ void __launch_bounds__(128, SHAPES ? 4 : WF_SHADE_MINB) k_wf_shade(DScene sc, WfBuf b, DRegion rg, uint32_t sample_begin,
+                                                  unsigned long long seed, DCounters *ctr) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const LiveList ll = live_list(b, cur_list);
-    const uint32_t N = b.n;
-    uint32_t *__restrict__ next_live = b.live[cur_list ^ 1];
+    const uint32_t N = b.n, n_px = rg.w * rg.h;
+    const int lane = threadIdx.x & 31;
+    uint32_t *__restrict__ next_live = b.live[1];
     Cnt c;
-    bool keep = false, fresh = false;
-    uint32_t slot = 0;
-    if (i < ll.n) {
-        slot = ll.at(i);
-        uint32_t flags = b.flags[slot], s = b.sample[slot];
-        Rng rng;
-        rng.init(seed, slot, sample_begin + s);
-        d3 o = mk3(0.0, 0.0, 0.0), d = o, T = o, L = o;
-        uint32_t left = (flags >> 8) & 0xFFu;
-        const bool defer = (flags & kFlagExactPending) != 0;
-        bool alive = (flags & kFlagAlive) != 0 && !defer, ended = false, pend_light = false;
-        Pending pd;
-        pd.v = o; pd.cos_pdf = 0.0;
+    bool keep = false, fresh = false, in_range = i < b.n_slots, want = false, alive = false, defer = false, pend_light = false;
+    const uint32_t slot = i;                            // slots are walked in index order; which PIXEL a slot works on changes
+    uint32_t smp = 0, pix = 0, ord = 0, left = 0;
+    Rng rng;
+    rng.init(seed, 0u, 0u);
+    d3 o = mk3(0.0, 0.0, 0.0), d = o, T = o, L = o;
+    Pending pd;
+    pd.v = o; pd.cos_pdf = 0.0;
+    if (in_range) {
+        const uint32_t flags = b.flags[slot];
+        smp = b.sample[slot];
+        left = (flags >> 8) & 0xFFu;
+        defer = (flags & kFlagExactPending) != 0;
+        alive = (flags & kFlagAlive) != 0 && !defer;
+        bool ended = false;
         if (alive) {
+            pix = b.pix[slot];
+            rng.init(seed, pix, sample_begin + smp);
             rng.block = b.rng_block[slot]; rng.s0 = b.rng_s0[slot]; rng.s1 = b.rng_s1[slot];
             rng.have = (flags & kFlagRngHave) != 0;
             o = ld_soa(b.ro, N, slot); d = ld_soa(b.rd, N, slot);
@@ -292,33 +300,73 @@ __global__ void __launch_bounds__(128, SHAPES ? 4 : WF_SHADE_MINB) k_wf_shade(DS
                     pend_light = r == kPathPendingPdf;
                 }
             }
+            if (ended) {
+                // The finished sample's radiance goes to the plane of its sample index; k_wf_sum
+                // adds the planes to the accumulation buffer in sample order (main.rs:102), whatever
+                // slot computed them and whenever.
+                const uint32_t od = b.ord[slot];
+                double *sp = b.side + (size_t)(smp % b.ring) * 3u * n_px + od;
+                sp[0] = L.x; sp[n_px] = L.y; sp[2u * (size_t)n_px] = L.z;
+                alive = false;
+            }
         }
+        // A slot without a path (k_wf_exact's slots excepted) takes the next item of the queue.
+        want = !alive && !defer;
+    }
+    // ---- claim: item j = sample (j / n_px) of the pixel with ordinal (j % n_px) in the region's
+    // tile order.  One compare-and-swap per warp hands out a run of consecutive items — the lanes
+    // of a warp that start a path together get neighbouring pixels — and never passes the limit
+    // (the planes of the ring that are still being filled).
+    __syncwarp();
+    const unsigned mw = __ballot_sync(kFull, want);
+    if (mw) {
+        const int leader = __ffs(mw) - 1;
+        unsigned long long first = 0;
+        uint32_t got = 0, s0 = 0, o0 = 0;
+        if (lane == leader) {
+            // One atomicAdd per warp, no retry loop (a compare-and-swap on this one address from
+            // 65 000 warps at once does not scale).  The limit is checked on a plain read first, so
+            // all the warps of one launch together can overshoot it by at most one item per slot =
+            // one plane (n_slots <= n_px): k_wf_plan keeps two planes of the ring in reserve.
+            const unsigned long long limit = b.item[1], total = b.item[2];
+            const uint32_t cnt = (uint32_t)__popc(mw);
+            if (*(volatile unsigned long long *)b.item < limit) {
+                first = atomicAdd(b.item, (unsigned long long)cnt);
+                got = first < total ? (uint32_t)min((unsigned long long)cnt, total - first) : 0u;
+            }
+            s0 = (uint32_t)(first / n_px);
+            o0 = (uint32_t)(first - (unsigned long long)s0 * n_px);
+        }
+        got = __shfl_sync(kFull, got, leader);
+        s0 = __shfl_sync(kFull, s0, leader);
+        o0 = __shfl_sync(kFull, o0, leader);
+        const uint32_t rank = __popc(mw & ((1u << lane) - 1u));
+        if (want && rank < got) {
+            smp = s0;
+            unsigned long long oo = (unsigned long long)o0 + rank;
+            while (oo >= n_px) { oo -= n_px; ++smp; }
+            ord = (uint32_t)oo;
+            pix = region_tile_pixel(rg, sc.width, ord);
+            rng.init(seed, pix, sample_begin + smp);
+            const double jx = rng.range(0.0, 1.0), jy = rng.range(0.0, 1.0);       // camera.rs:49-50
+            camera_ray(sc.cam, pix % sc.width, pix / sc.width, jx, jy, o, d);
+            ++c.paths;
+            T = mk3(1.0, 1.0, 1.0);
+            L = mk3(0.0, 0.0, 0.0);
+            left = sc.ray_depth;
+            pend_light = false;
+            fresh = true;
+            alive = true;
+        }
+    }
+    if (in_range) {
         if (defer) {
             // k_wf_confirm could not prove that the reference finds the same hits for this ray
             // (hit_fragile / a tie): k_wf_exact is answering both searches with the reference's own
             // traversal while this kernel runs.  Nothing is shaded, stored or traced for the slot
             // in this iteration; it stays in the list and is picked up in the next one.
             keep = true;
-        } else if (!alive || ended) {
-            if (alive) {                                // main.rs:102
-                const size_t p = (size_t)slot * 3;
-                accum[p] += L.x; accum[p + 1] += L.y; accum[p + 2] += L.z;
-                ++s;
-            }
-            alive = s < sample_count;
-            if (alive) {
-                rng.init(seed, slot, sample_begin + s);
-                const double jx = rng.range(0.0, 1.0), jy = rng.range(0.0, 1.0);       // camera.rs:49-50
-                camera_ray(sc.cam, slot % sc.width, slot / sc.width, jx, jy, o, d);
-                ++c.paths;
-                T = mk3(1.0, 1.0, 1.0);
-                L = mk3(0.0, 0.0, 0.0);
-                left = sc.ray_depth;
-                pend_light = false;
-                fresh = true;
-            }
-        }
-        if (alive && !defer) {                          // hand the ray to the trace kernel
+        } else if (alive) {                             // hand the ray to the trace kernel
             if (SHAPES) {
                 const ShapeBest sb = shapes_closest(sc, o, d, c);
                 b.sh_id[slot] = sb.has ? (((uint32_t)sb.kind << 28) | sb.prim) : kNoShape;
@@ -336,23 +384,26 @@ __global__ void __launch_bounds__(128, SHAPES ? 4 : WF_SHADE_MINB) k_wf_shade(DS
             st_soa(b.ro, N, slot, o); st_soa(b.rd, N, slot, d);
             st_soa(b.T, N, slot, T); st_soa(b.L, N, slot, L);
             b.rng_block[slot] = rng.block; b.rng_s0[slot] = rng.s0; b.rng_s1[slot] = rng.s1;
-            b.sample[slot] = s;
+            if (fresh) { b.sample[slot] = smp; b.pix[slot] = pix; b.ord[slot] = ord; }
             b.flags[slot] = kFlagAlive | (rng.have ? kFlagRngHave : 0u) | (pend_light ? kFlagPendLight : 0u) | (left << 8);
             keep = true;
-        } else if (!defer) {
+        } else {
             b.flags[slot] = 0;
-            b.sample[slot] = s;
         }
     }
+    // the oldest sample still in flight: every plane before it is complete (k_wf_plan)
+    {
+        uint32_t m = (in_range && (alive || defer)) ? smp : 0xFFFFFFFFu;
+        for (int off = 16; off > 0; off >>= 1) m = min(m, __shfl_xor_sync(kFull, m, off));
+        if (lane == 0 && m != 0xFFFFFFFFu) atomicMin(&b.plane[1], m);
+    }
     // stream compaction of the live slots: ballot + prefix sum inside the warp, one 64-bit atomic
-    // per warp reserves room at both ends of the next list (front: fresh camera rays, back: the rest)
-    __syncwarp();
+    // per warp reserves room at both ends of the trace list (front: fresh camera rays, back: the rest)
     const unsigned mf = __ballot_sync(kFull, keep && fresh), mb = __ballot_sync(kFull, keep && !fresh);
     if (mf | mb) {
-        const int lane = threadIdx.x & 31;
         unsigned long long base = 0;
         if (lane == 0)
-            base = atomicAdd(reinterpret_cast<unsigned long long *>(b.n_live + 2 * (cur_list ^ 1)),
+            base = atomicAdd(reinterpret_cast<unsigned long long *>(b.n_live + 2),
                              (unsigned long long)__popc(mf) | ((unsigned long long)__popc(mb) << 32));
         base = __shfl_sync(kFull, base, 0);
         const unsigned below = (1u << lane) - 1u;
@@ -362,6 +413,45 @@ __global__ void __launch_bounds__(128, SHAPES ? 4 : WF_SHADE_MINB) k_wf_shade(DS
         }
     }
     flush_counters_wf(c, ctr);
+}
+
+// ---- sum -----------------------------------------------------------------------------------------
+// Slots are not tied to pixels: a slot takes whatever item is next, so all slots stay busy until
+// the last sample of the call has been started, however unevenly path lengths are spread over the
+// image.  What keeps the result the megakernel's bit for bit is the ORDER of the additions: every
+// finished sample is parked in the plane of its sample index, and complete planes are added to the
+// accumulation buffer one after the other, sample 0 first (main.rs:100-103).
+// k_wf_plan (one thread, after the shade kernel): planes [summed, upto) are complete — fully
+// claimed and older than the oldest sample still in flight — and the claim limit moves on.
+__global__ void k_wf_plan(WfBuf b, uint32_t n_px) {
+    const uint32_t summed = b.plane[3];                 // the sum kernel of the last iteration has run
+    b.plane[0] = summed;
+    const unsigned long long total = b.item[2], next = min(b.item[0], total);
+    const unsigned long long claimed = next / n_px;     // planes whose items have all been handed out
+    const uint32_t oldest = b.plane[1];
+    uint32_t upto = (uint32_t)min(claimed, (unsigned long long)oldest);
+    // batches of four planes amortise the read-modify-write of the accumulation buffer; at the end
+    // of the call (nothing left to claim) everything that is complete goes
+    if (upto < summed + 4u && next < total) upto = summed;
+    if (upto < summed) upto = summed;
+    b.plane[3] = upto;
+    // two planes of the ring stay in reserve: the claims of one launch can pass the limit by a plane
+    const unsigned long long limit = ((unsigned long long)upto + b.ring - 2u) * n_px;
+    b.item[1] = limit < total ? limit : total;
+    b.plane[1] = 0xFFFFFFFFu;
+}
+__global__ void __launch_bounds__(256) k_wf_sum(WfBuf b, DRegion rg, uint32_t width, double *__restrict__ accum) {
+    const uint32_t from = b.plane[0], upto = b.plane[3], n_px = rg.w * rg.h;
+    if (upto <= from) return;
+    for (uint32_t od = blockIdx.x * blockDim.x + threadIdx.x; od < n_px; od += gridDim.x * blockDim.x) {
+        const size_t p = (size_t)region_tile_pixel(rg, width, od) * 3;
+        double ax = accum[p], ay = accum[p + 1], az = accum[p + 2];
+        for (uint32_t smp = from; smp < upto; ++smp) {
+            const double *sp = b.side + (size_t)(smp % b.ring) * 3u * n_px + od;
+            ax += sp[0]; ay += sp[n_px]; az += sp[2u * (size_t)n_px];
+        }
+        accum[p] = ax; accum[p + 1] = ay; accum[p + 2] = az;
+    }
 }
 
 // ---- exact ---------------------------------------------------------------------------------------
@@ -411,12 +501,6 @@ __global__ void __launch_bounds__(128) k_wf_exact(DScene sc, WfBuf b) {
 #ifndef WF_VOTE_I
 #define WF_VOTE_I 1            // the INNER step runs when WF_VOTE_I * (#lanes at a node) >= WF_VOTE_T * (#lanes at a leaf)
 #define WF_VOTE_T 1
-#endif
-#ifndef WF_FINISH_MINB
-#define WF_FINISH_MINB 2
-#endif
-#ifndef WF_TAIL_DIV
-#define WF_TAIL_DIV 16         // hand the last n/16 live slots to the tail kernel; measured 2 / 4 / 8 / 16 / 64 / 256 -> 1017 / 794 / 750 / 750 / 764 / 792 ms per 256 spp
 #endif
 #ifndef WF_REFILL
 #define WF_REFILL 16
@@ -614,69 +698,8 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
 #endif
 }
 
-// ---- tail ----------------------------------------------------------------------------------------
-// When few slots are left alive an iteration costs the latency of its single slowest ray, not
-// its throughput.  The remaining slots are then finished by one kernel in which every thread
-// runs its pixel's paths to completion (the megakernel loop, same arithmetic), starting from the
-// ray the last shade step handed over.
-__global__ void __launch_bounds__(128, WF_FINISH_MINB) k_wf_finish(DScene sc, WfBuf b, int list, uint32_t sample_begin, uint32_t sample_count,
-                                                   unsigned long long seed, double *__restrict__ accum, DCounters *ctr) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const LiveList ll = live_list(b, list);
-    const uint32_t N = b.n;
-    Cnt c;
-    if (i < ll.n) {
-        const uint32_t slot = ll.at(i);
-        const uint32_t flags = b.flags[slot];
-        uint32_t s = b.sample[slot], left = (flags >> 8) & 0xFFu;
-        Rng rng;
-        rng.init(seed, slot, sample_begin + s);
-        rng.block = b.rng_block[slot]; rng.s0 = b.rng_s0[slot]; rng.s1 = b.rng_s1[slot];
-        rng.have = (flags & kFlagRngHave) != 0;
-        d3 o = ld_soa(b.ro, N, slot), d = ld_soa(b.rd, N, slot), T = ld_soa(b.T, N, slot), L = ld_soa(b.L, N, slot);
-        const size_t p = (size_t)slot * 3;
-        d3 sum = mk3(accum[p], accum[p + 1], accum[p + 2]);
-        bool alive = (flags & kFlagAlive) != 0;
-        if (alive && (flags & kFlagPendLight)) {        // Light::pdf of the ray in flight (already counted)
-            Pending pd;
-            pd.v = ld_soa(b.pv, N, slot);
-            pd.cos_pdf = b.pcos[slot];
-            Cnt scratch;
-            if (!apply_pending(pd, light_pdf_fast(sc, o, d, scratch), T)) { sum = add(sum, L); alive = false; ++s; }
-        }
-        for (;;) {
-            if (!alive) {
-                if (s >= sample_count) break;
-                rng.init(seed, slot, sample_begin + s);
-                const double jx = rng.range(0.0, 1.0), jy = rng.range(0.0, 1.0);
-                camera_ray(sc.cam, slot % sc.width, slot / sc.width, jx, jy, o, d);
-                ++c.paths;
-                T = mk3(1.0, 1.0, 1.0);
-                L = mk3(0.0, 0.0, 0.0);
-                left = sc.ray_depth;
-                alive = true;
-            }
-            bool more = false;
-            if (left > 0) {
-                more = bounce<FastPolicy>(sc, o, d, T, L, rng, c);
-                --left;
-            }
-            if (!more || left == 0) {
-                sum = add(sum, L);
-                alive = false;
-                ++s;
-            }
-        }
-        accum[p] = sum.x; accum[p + 1] = sum.y; accum[p + 2] = sum.z;
-        b.flags[slot] = 0;
-        b.sample[slot] = s;
-    }
-    __syncwarp();
-    flush_counters_wf(c, ctr);
-}
-
 // ---- host loop -----------------------------------------------------------------------------------
-size_t wf_bytes_per_slot() { return 15 * 8 + 3 * 8 + 7 * 4 + kWfCand * 8 + 4 * 8 + 3 * 4; }
+size_t wf_bytes_per_slot() { return 15 * 8 + 3 * 8 + 7 * 4 + kWfCand * 8 + 4 * 8 + 3 * 4 + 2 * 4 + kWfRing * 24; }
 int wf_trace_blocks(int device) {
     int sms = 148, per_sm = 4;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -684,51 +707,58 @@ int wf_trace_blocks(int device) {
     return sms * per_sm;
 }
 cudaError_t launch_render_wavefront(cudaStream_t st, const DScene &sc, uint32_t sample_begin, uint32_t sample_count,
-                                    uint64_t seed, double *accum, DCounters *ctr, const WfBuf &b, volatile uint32_t *host_live,
+                                    uint64_t seed, double *accum, DCounters *ctr, const WfBuf &b_in, volatile uint32_t *host_live,
                                     cudaEvent_t ev, int trace_blocks, uint64_t *launches, DRegion rg) {
-    const uint32_t n_region = rg.w * rg.h;
-    const unsigned blocks = (n_region + 127) / 128;
-    k_wf_init<<<blocks, 128, 0, st>>>(b, rg, sc.width);
+    const uint32_t n_px = rg.w * rg.h;
+    WfBuf b = b_in;
+    b.n_slots = n_px < b.n ? n_px : b.n;               // one plane's worth of slots at most (bounds the overshoot of the claim limit)
+    const unsigned blocks = (b.n_slots + 127) / 128;
+    const unsigned long long total_items = (unsigned long long)n_px * sample_count;
+    k_wf_init<<<blocks, 128, 0, st>>>(b, n_px, sample_count);
     ++*launches;
-    // a segment takes one iteration, two when it is deferred to k_wf_exact
-    const uint64_t max_iters = 2 * (uint64_t)sample_count * (sc.ray_depth ? sc.ray_depth : 1) + 8;
+    // a segment takes one iteration, two when it is deferred to k_wf_exact; an item can wait for
+    // a free plane of the ring: generous bound, reaching it is reported as an error
+    const uint64_t max_iters = 4 * ((uint64_t)sample_count * n_px / b.n_slots + 1) * (sc.ray_depth ? sc.ray_depth : 1) + 64;
     bool poll_pending = false, finished = false;
     // scenes without planes / boxes / ellipsoids (every glTF scene) run the kernel compiled without them
     const bool shapes = sc.n_planes || sc.boxes.n_prims || sc.ellipsoids.n_prims || sc.lboxes.n_prims || sc.lellipsoids.n_prims;
-    const uint32_t tail_threshold = n_region / WF_TAIL_DIV + 1;       // below this many live slots, finish in one kernel
-    // One iteration = 2 memset nodes + shade + trace; four iterations (ending on the list they
-    // started from) are captured ONCE into a CUDA graph and replayed, so the host issues one launch
-    // per four iterations instead of sixteen — the inner loop is launch-bound on small images and
-    // in the last iterations of every render.
+    const unsigned sum_blocks = (unsigned)std::min<uint64_t>((n_px + 255) / 256, 148 * 8);
     cudaStream_t side = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_plan = nullptr, ev_join = nullptr;
     if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&ev_plan, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess) {
         const cudaError_t e = cudaGetLastError();
         if (side) cudaStreamDestroy(side);
         if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_plan) cudaEventDestroy(ev_plan);
         return e != cudaSuccess ? e : cudaErrorUnknown;
     }
-    auto issue_iteration = [&](int from) {
-        cudaMemsetAsync(&b.n_live[2 * (from ^ 1)], 0, 2 * sizeof(uint32_t), st);   // next list starts empty
+    // One iteration: confirm -> shade -> trace on the main stream; on a forked branch k_wf_exact
+    // (after confirm) and k_wf_sum (after the one-thread k_wf_plan that follows shade), joined
+    // before the next iteration.  Four iterations are captured ONCE into a CUDA graph and
+    // replayed: the inner loop is launch-bound on small images and at the end of every render.
+    auto issue_iteration = [&]() {
+        cudaMemsetAsync(&b.n_live[2], 0, 2 * sizeof(uint32_t), st);         // the trace list starts empty
         cudaMemsetAsync(b.cursor, 0, 2 * sizeof(uint32_t), st);              // trace fetch position, deferred-slot count (cursor[1])
-        k_wf_confirm<<<blocks, 128, 0, st>>>(sc, b, from, ctr);
-        // fork: k_wf_exact works on the few slots the confirm pass handed over while the shade and
-        // trace kernels run (they skip those slots); joined at the end of the iteration
+        k_wf_confirm<<<blocks, 128, 0, st>>>(sc, b, 0, ctr);
         cudaEventRecord(ev_fork, st);
         cudaStreamWaitEvent(side, ev_fork, 0);
         k_wf_exact<<<64, 128, 0, side>>>(sc, b);
+        if (shapes) k_wf_shade<true><<<blocks, 128, 0, st>>>(sc, b, rg, sample_begin, seed, ctr);
+        else k_wf_shade<false><<<blocks, 128, 0, st>>>(sc, b, rg, sample_begin, seed, ctr);
+        k_wf_plan<<<1, 1, 0, st>>>(b, n_px);
+        cudaEventRecord(ev_plan, st);
+        cudaStreamWaitEvent(side, ev_plan, 0);
+        k_wf_sum<<<sum_blocks, 256, 0, side>>>(b, rg, sc.width, accum);
         cudaEventRecord(ev_join, side);
-        if (shapes) k_wf_shade<true><<<blocks, 128, 0, st>>>(sc, b, from, sample_begin, sample_count, seed, accum, ctr);
-        else k_wf_shade<false><<<blocks, 128, 0, st>>>(sc, b, from, sample_begin, sample_count, seed, accum, ctr);
-        k_wf_trace<<<trace_blocks, 128, 0, st>>>(sc, b, from ^ 1, ctr);
+        k_wf_trace<<<trace_blocks, 128, 0, st>>>(sc, b, 1, ctr);
         cudaStreamWaitEvent(st, ev_join, 0);
     };
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     bool use_graph = false;
     if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-        for (int k = 0; k < 4; ++k) issue_iteration(0);
+        for (int k = 0; k < 4; ++k) issue_iteration();
         if (cudaStreamEndCapture(st, &graph) == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) use_graph = true;
     }
     if (!use_graph) cudaGetLastError();             // fall back to plain launches (same kernels, same order)
@@ -738,38 +768,40 @@ cudaError_t launch_render_wavefront(cudaStream_t st, const DScene &sc, uint32_t 
             result = cudaGraphLaunch(exec, st);
             if (result != cudaSuccess) break;
         } else {
-            for (int k = 0; k < 4; ++k) issue_iteration(0);
+            for (int k = 0; k < 4; ++k) issue_iteration();
         }
-        *launches += 16;
-        // four iterations end on list 0 again; poll its live count without stalling the stream
+        *launches += 24;
+        // poll the state after the PREVIOUS group of four without stalling the stream: nothing in
+        // flight and nothing left to claim means the call is done
         if (poll_pending) {
             result = cudaEventSynchronize(ev);
             if (result != cudaSuccess) break;
-            const uint32_t n_left = host_live[0] + host_live[1];       // front + back of list 0
-            if (n_left == 0) { finished = true; break; }
-            if (n_left < tail_threshold) {
-                finished = true;
-                // few slots left: finish them in one kernel (the count can only have shrunk since)
-                k_wf_finish<<<(tail_threshold + 127) / 128, 128, 0, st>>>(sc, b, 1, sample_begin, sample_count, seed, accum, ctr);
-                ++*launches;
-                break;
-            }
+            const unsigned long long next = (unsigned long long)host_live[2] | ((unsigned long long)host_live[3] << 32);
+            if (host_live[0] + host_live[1] == 0 && next >= total_items) { finished = true; break; }
         }
         cudaMemcpyAsync((void *)host_live, &b.n_live[2], 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync((void *)(host_live + 2), b.item, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
         cudaEventRecord(ev, st);
         poll_pending = true;
     }
-    if (!finished && result == cudaSuccess) {       // cannot happen (max_iters bounds every path); finish whatever is in flight
-        k_wf_finish<<<blocks, 128, 0, st>>>(sc, b, 1, sample_begin, sample_count, seed, accum, ctr);
-        ++*launches;
+    if (result == cudaSuccess) {
+        // the planes completed by the last iterations (k_wf_plan sees no path in flight and nothing
+        // left to claim, so everything that remains goes)
+        k_wf_plan<<<1, 1, 0, st>>>(b, n_px);
+        k_wf_sum<<<sum_blocks, 256, 0, st>>>(b, rg, sc.width, accum);
+        k_wf_plan<<<1, 1, 0, st>>>(b, n_px);
+        k_wf_sum<<<sum_blocks, 256, 0, st>>>(b, rg, sc.width, accum);
+        *launches += 4;
     }
     cudaStreamSynchronize(side);                    // (already joined into st; makes the destroy below trivially safe)
     cudaEventDestroy(ev_fork);
+    cudaEventDestroy(ev_plan);
     cudaEventDestroy(ev_join);
     cudaStreamDestroy(side);
     if (exec) cudaGraphExecDestroy(exec);
     if (graph) cudaGraphDestroy(graph);
     if (result != cudaSuccess) return result;
+    if (!finished) return cudaErrorLaunchTimeout;   // iteration bound reached with work left: never a silent partial image
     return cudaGetLastError();
 }
 
