@@ -21,7 +21,7 @@ SYMBOLS = [
     "rt_scene_get_bvh", "rt_scene_get_triangle", "rt_scene_get_shape", "rt_scene_get_material", "rt_save_ppm",
     "rt_device_count", "rt_create", "rt_destroy", "rt_last_error", "rt_upload_scene", "rt_scene_device_bytes", "rt_trace_rays",
     "rt_trace_primary", "rt_light_pdf", "rt_render_accum", "rt_accum_device_ptr", "rt_get_accum", "rt_set_accum",
-    "rt_postprocess", "rt_render", "rt_render_progressive", "rt_sync", "rt_stream", "rt_get_counters", "rt_reset_counters", "rt_debug_rng", "rt_debug_wavefront",
+    "rt_postprocess", "rt_render", "rt_render_progressive", "rt_sync", "rt_stream", "rt_get_counters", "rt_reset_counters", "rt_debug_rng",
 ]
 
 
@@ -85,7 +85,6 @@ def lib():
         L.rt_get_counters.argtypes = [vp, C.POINTER(T.Counters)]
         L.rt_reset_counters.argtypes = [vp]
         L.rt_debug_rng.argtypes = [vp, u64, u32, u32, u64, vp, vp]
-        L.rt_debug_wavefront.argtypes = [vp, vp, vp, vp]
         _LIB = L
     return _LIB
 
@@ -371,12 +370,6 @@ class Context:
 
     def reset_counters(self):
         _check(lib().rt_reset_counters(self._h), self._h)
-
-    def debug_wavefront(self):
-        n = self.scene.width * self.scene.height
-        nc, fl, rays = np.zeros(n, np.uint32), np.zeros(n, np.uint32), np.zeros((6, n))
-        _check(lib().rt_debug_wavefront(self._h, _p(nc), _p(fl), _p(rays)), self._h)
-        return nc, fl, rays.T.copy()
 
     def debug_rng(self, seed, pixel, sample, n):
         u = np.zeros(n, np.uint64)

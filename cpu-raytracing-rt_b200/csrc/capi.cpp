@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -76,11 +77,16 @@ void free_wavefront(rt_ctx *ctx) {
     ctx->wf = WfBuf{};
 }
 cudaError_t ensure_wavefront(rt_ctx *ctx) {
-    const uint32_t n = (uint32_t)ctx->n_px;
-    if (ctx->wf_arena && ctx->wf.n == n) return cudaSuccess;
+    // Slots are not tied to pixels (wavefront.cu): small images still get enough slots to fill the
+    // GPU, large ones one slot per pixel.  RT_WF_CAP overrides the capacity (experiments).
+    const uint32_t n_img = (uint32_t)ctx->n_px;
+    uint64_t cap = wf_slots_for(n_img);
+    if (const char *e = std::getenv("RT_WF_CAP")) { const long long v = std::atoll(e); if (v >= 1024 && v <= (1ll << 28)) cap = (uint64_t)v; }
+    const uint32_t n = (uint32_t)cap;
+    if (ctx->wf_arena && ctx->wf.n == n && ctx->wf.n_px_cap == n_img) return cudaSuccess;
     free_wavefront(ctx);
     const size_t per = (wf_bytes_per_slot() + 15) & ~(size_t)15;
-    const size_t total = per * n + 65536;
+    const size_t total = per * n + (size_t)n_img * 24 * kWfRing + 65536 + 64 * 256;
     cudaError_t e = cudaMalloc(&ctx->wf_arena, total);
     if (e != cudaSuccess) return e;
     char *p = ctx->wf_arena;
@@ -104,7 +110,9 @@ cudaError_t ensure_wavefront(rt_ctx *ctx) {
     b.ring = kWfRing;
     b.pix = (uint32_t *)take((size_t)n * 4);
     b.ord = (uint32_t *)take((size_t)n * 4);
-    b.side = (double *)take((size_t)n * 24 * kWfRing);
+    b.side = (double *)take((size_t)n_img * 24 * kWfRing);
+    b.n_px_cap = n_img;
+    b.reserve = 2;
     b.item = (unsigned long long *)take(24);
     b.plane = (uint32_t *)take(16);
     b.cursor = (uint32_t *)take(8);
@@ -796,18 +804,6 @@ int rt_debug_rng(rt_ctx *ctx, uint64_t seed, uint32_t pixel, uint32_t sample, ui
     CK(ctx, cudaMemcpyAsync(u64_out, u.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaMemcpyAsync(probe8, pr.p, 64, cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
-    return RT_OK;
-}
-int rt_debug_wavefront(rt_ctx *ctx, uint32_t *ncand_out, uint32_t *flags_out, double *rays_out) {
-    if (int r = need_scene(ctx)) return r;
-    if (!ctx->wf_arena) return set_err(ctx, RT_ERR_INVALID_ARG, "no wavefront render has run on this context");
-    CK(ctx, cudaStreamSynchronize(ctx->stream));
-    if (ncand_out) CK(ctx, cudaMemcpy(ncand_out, ctx->wf.ncand, (size_t)ctx->wf.n * 4, cudaMemcpyDeviceToHost));
-    if (flags_out) CK(ctx, cudaMemcpy(flags_out, ctx->wf.flags, (size_t)ctx->wf.n * 4, cudaMemcpyDeviceToHost));
-    if (rays_out) {
-        CK(ctx, cudaMemcpy(rays_out, ctx->wf.ro, (size_t)ctx->wf.n * 24, cudaMemcpyDeviceToHost));
-        CK(ctx, cudaMemcpy(rays_out + (size_t)ctx->wf.n * 3, ctx->wf.rd, (size_t)ctx->wf.n * 24, cudaMemcpyDeviceToHost));
-    }
     return RT_OK;
 }
 int rt_sync(rt_ctx *ctx) {

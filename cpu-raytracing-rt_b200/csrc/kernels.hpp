@@ -30,7 +30,8 @@ struct WfBuf {                          // path slots, structure of arrays; n = 
     uint32_t *live[2];                  // n each: compacted indices of slots with work
     uint32_t *n_live;                   // [4]: per list, entries filled from the front / from the back (8-byte aligned pairs)
     uint32_t *cursor;                   // trace kernel's fetch position in the live list
-    uint32_t n_slots, ring;             // slots in use (<= n), planes in the ring of finished samples
+    uint32_t n_slots, ring, reserve;    // slots in use (<= n), planes in the ring of finished samples, planes kept free for claim overshoot
+    uint32_t n_px_cap;                  // pixels the side planes were allocated for (width * height)
     uint32_t *pix, *ord;                // n: pixel (index in the image) / ordinal (in the region's tile order) a slot works on
     double *side;                       // ring * 3 * n: radiance of finished samples: plane (sample % ring), component, ordinal
     unsigned long long *item;           // [0] next unclaimed item, [1] claim limit, [2] items of this call
@@ -38,6 +39,14 @@ struct WfBuf {                          // path slots, structure of arrays; n = 
     uint32_t *xlist, *n_x;              // slots deferred to k_wf_exact in this iteration (n entries), their count (= cursor + 1)
 };
 size_t wf_bytes_per_slot();
+// Slots a render of n_px pixels uses: twice the pixels for small images (fewer, fuller iterations: the
+// loop is launch-bound there), one per pixel from 2 M pixels on.  Measured on B200 (C3 scene, Mseg/s):
+// 256x256 360 / 567 / 550 at 1x / 2x / 4x; 512x512 1074 / 1073 / 984 at 2x / 3x / 4x; 1080p 1460 / 1475 /
+// 1360 at 1x / 2x / 3x; 4K 1577 / 1554 at 1x / 1.5x.
+inline uint64_t wf_slots_for(uint64_t n_px) {
+    const uint64_t twice = 2 * n_px, most = n_px > (1u << 21) ? n_px : (1u << 21);
+    return twice < most ? twice : most;
+}
 int wf_trace_blocks(int device);
 cudaError_t launch_render_wavefront(cudaStream_t st, const DScene &sc, uint32_t sample_begin, uint32_t sample_count,
                                     uint64_t seed, double *accum, DCounters *ctr, const WfBuf &b, volatile uint32_t *host_live,

@@ -23,6 +23,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "../../include/rt_b200.h"
 #include "fast.cuh"
@@ -93,7 +94,7 @@ __global__ void k_wf_init(WfBuf b, uint32_t n_px, uint32_t sample_count) {
     if (i == 0) {
         b.n_live[0] = b.n_slots; b.n_live[1] = 0; b.n_live[2] = 0; b.n_live[3] = 0;
         b.cursor[0] = 0; b.cursor[1] = 0;
-        const unsigned long long total = (unsigned long long)n_px * sample_count, first = (unsigned long long)(b.ring - 2u) * n_px;
+        const unsigned long long total = (unsigned long long)n_px * sample_count, first = (unsigned long long)(b.ring - b.reserve) * n_px;
         b.item[0] = 0; b.item[1] = first < total ? first : total; b.item[2] = total;
         b.plane[0] = 0; b.plane[1] = 0xFFFFFFFFu; b.plane[2] = b.ring; b.plane[3] = 0;
     }
@@ -435,8 +436,8 @@ __global__ void k_wf_plan(WfBuf b, uint32_t n_px) {
     if (upto < summed + 4u && next < total) upto = summed;
     if (upto < summed) upto = summed;
     b.plane[3] = upto;
-    // two planes of the ring stay in reserve: the claims of one launch can pass the limit by a plane
-    const unsigned long long limit = ((unsigned long long)upto + b.ring - 2u) * n_px;
+    // b.reserve planes of the ring stay free: the claims of one launch can pass the limit by one item per slot
+    const unsigned long long limit = ((unsigned long long)upto + b.ring - b.reserve) * n_px;
     b.item[1] = limit < total ? limit : total;
     b.plane[1] = 0xFFFFFFFFu;
 }
@@ -699,19 +700,33 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
 }
 
 // ---- host loop -----------------------------------------------------------------------------------
-size_t wf_bytes_per_slot() { return 15 * 8 + 3 * 8 + 7 * 4 + kWfCand * 8 + 4 * 8 + 3 * 4 + 2 * 4 + kWfRing * 24; }
+size_t wf_bytes_per_slot() { return 15 * 8 + 3 * 8 + 7 * 4 + kWfCand * 8 + 4 * 8 + 3 * 4 + 2 * 4; }      // + kWfRing * 24 per PIXEL for the side planes
 int wf_trace_blocks(int device) {
     int sms = 148, per_sm = 4;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wf_trace, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
     return sms * per_sm;
 }
+static inline unsigned long long total_items_of(uint32_t n_px, uint32_t samples) { return (unsigned long long)n_px * samples; }
 cudaError_t launch_render_wavefront(cudaStream_t st, const DScene &sc, uint32_t sample_begin, uint32_t sample_count,
                                     uint64_t seed, double *accum, DCounters *ctr, const WfBuf &b_in, volatile uint32_t *host_live,
                                     cudaEvent_t ev, int trace_blocks, uint64_t *launches, DRegion rg) {
     const uint32_t n_px = rg.w * rg.h;
     WfBuf b = b_in;
-    b.n_slots = n_px < b.n ? n_px : b.n;               // one plane's worth of slots at most (bounds the overshoot of the claim limit)
+    // Slots are independent of pixels: all of the buffer's capacity is used, but never more than
+    // (ring - 4) planes' worth — the claims of one launch can pass the limit by one item per slot,
+    // and that many planes of the ring are kept free for it (reserve).
+    unsigned long long want_slots = wf_slots_for(n_px) < b.n ? wf_slots_for(n_px) : b.n;
+    if (const char *e = std::getenv("RT_WF_SLOTS")) {  // experiments
+        const long long v = std::atoll(e);
+        if (v >= 1024 && (unsigned long long)v < want_slots) want_slots = (unsigned long long)v;
+    }
+    const unsigned long long most = (unsigned long long)(b.ring - 4u) * n_px;
+    if (want_slots > most) want_slots = most;
+    if (want_slots > total_items_of(n_px, sample_count)) want_slots = total_items_of(n_px, sample_count);
+    if (want_slots < 1) want_slots = 1;
+    b.n_slots = (uint32_t)want_slots;
+    b.reserve = (uint32_t)((want_slots + n_px - 1) / n_px) + 1u;
     const unsigned blocks = (b.n_slots + 127) / 128;
     const unsigned long long total_items = (unsigned long long)n_px * sample_count;
     k_wf_init<<<blocks, 128, 0, st>>>(b, n_px, sample_count);

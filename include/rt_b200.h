@@ -302,10 +302,6 @@ RT_API int rt_reset_counters(rt_ctx *ctx);
 RT_API int rt_debug_rng(rt_ctx *ctx, uint64_t seed, uint32_t pixel, uint32_t sample, uint64_t n,
                         uint64_t *u64_out, double *probe8);
 
-/* Test hook: per pixel slot, the candidate word (scene candidates | light candidates << 8 |
- * overflow bits 16,17), the state flags and the rays (component-major: ox[n] oy[n] oz[n] dx[n]
- * dy[n] dz[n]) left by the last wavefront render.  Any pointer may be NULL. */
-RT_API int rt_debug_wavefront(rt_ctx *ctx, uint32_t *ncand_out, uint32_t *flags_out, double *rays_out);
 
 #ifdef __cplusplus
 }

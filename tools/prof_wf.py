@@ -14,7 +14,8 @@ reps = int(os.environ.get("REPS", 2))
 os.makedirs("/tmp/sc", exist_ok=True)
 path = "/tmp/sc/p.gltf"
 scenes.write_heightfield_gltf(path, lights=True, spheres=True)
-scene = rtb200.Scene.load_gltf(path, 1920, 1080, spp)
+W, H = int(os.environ.get("W", 1920)), int(os.environ.get("H", 1080))
+scene = rtb200.Scene.load_gltf(path, W, H, spp)
 ctx = rtb200.Context(0).upload(scene)
 for rep in range(reps):
     ctx.reset_counters()
