@@ -86,7 +86,10 @@ cudaError_t ensure_wavefront(rt_ctx *ctx) {
     if (ctx->wf_arena && ctx->wf.n == n && ctx->wf.n_px_cap == n_img) return cudaSuccess;
     free_wavefront(ctx);
     const size_t per = (wf_bytes_per_slot() + 15) & ~(size_t)15;
-    const size_t total = per * n + (size_t)n_img * 24 * kWfRing + 65536 + 64 * 256;
+    uint32_t ring = kWfRing, batch = 4;
+    if (const char *e = std::getenv("RT_WF_RING")) { const int v = std::atoi(e); if (v >= 8 && v <= 256) ring = (uint32_t)v; }     // experiments
+    if (const char *e = std::getenv("RT_WF_BATCH")) { const int v = std::atoi(e); if (v >= 1 && v <= 64) batch = (uint32_t)v; }
+    const size_t total = per * n + (size_t)n_img * 24 * ring + 65536 + 64 * 256;
     cudaError_t e = cudaMalloc(&ctx->wf_arena, total);
     if (e != cudaSuccess) return e;
     char *p = ctx->wf_arena;
@@ -107,10 +110,11 @@ cudaError_t ensure_wavefront(rt_ctx *ctx) {
     b.live[1] = (uint32_t *)take((size_t)n * 4);
     b.n_live = (uint32_t *)take(16);
     b.n_slots = n;
-    b.ring = kWfRing;
+    b.ring = ring;
+    b.batch = batch;
     b.pix = (uint32_t *)take((size_t)n * 4);
     b.ord = (uint32_t *)take((size_t)n * 4);
-    b.side = (double *)take((size_t)n_img * 24 * kWfRing);
+    b.side = (double *)take((size_t)n_img * 24 * ring);
     b.n_px_cap = n_img;
     b.reserve = 2;
     b.item = (unsigned long long *)take(24);

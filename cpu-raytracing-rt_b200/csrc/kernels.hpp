@@ -30,6 +30,7 @@ struct WfBuf {                          // path slots, structure of arrays; n = 
     uint32_t *live[2];                  // n each: compacted indices of slots with work
     uint32_t *n_live;                   // [4]: per list, entries filled from the front / from the back (8-byte aligned pairs)
     uint32_t *cursor;                   // trace kernel's fetch position in the live list
+    uint32_t batch;                     // planes added to the image per k_wf_sum pass (amortises the read-modify-write)
     uint32_t n_slots, ring, reserve;    // slots in use (<= n), planes in the ring of finished samples, planes kept free for claim overshoot
     uint32_t n_px_cap;                  // pixels the side planes were allocated for (width * height)
     uint32_t *pix, *ord;                // n: pixel (index in the image) / ordinal (in the region's tile order) a slot works on

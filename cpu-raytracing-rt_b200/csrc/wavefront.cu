@@ -433,7 +433,7 @@ __global__ void k_wf_plan(WfBuf b, uint32_t n_px) {
     uint32_t upto = (uint32_t)min(claimed, (unsigned long long)oldest);
     // batches of four planes amortise the read-modify-write of the accumulation buffer; at the end
     // of the call (nothing left to claim) everything that is complete goes
-    if (upto < summed + 4u && next < total) upto = summed;
+    if (upto < summed + b.batch && next < total) upto = summed;
     if (upto < summed) upto = summed;
     b.plane[3] = upto;
     // b.reserve planes of the ring stay free: the claims of one launch can pass the limit by one item per slot
