@@ -1,24 +1,30 @@
 // wavefront.cu — the wavefront scheduler of generate_image (reference src/main.rs:94-103).
 //
-// Every pixel owns one SLOT holding the path currently in flight for it (ray, throughput, RNG
-// stream position, pending diffuse weight).  An iteration is two kernels over the LIVE slots:
+// A pool of SLOTS, each holding one path in flight (ray, throughput, RNG stream position, pending
+// diffuse weight), and a queue of ITEMS: item j = sample (j / n_px) of the pixel with ordinal
+// (j % n_px).  A slot whose path has ended takes the next item, whichever pixel it belongs to, so
+// all slots stay busy until the last sample of the call has been started.  An iteration:
 //
-//   k_wf_shade  one thread per live slot, f64, warp-coherent code.  Confirms the candidates the
-//               previous trace found with the reference's exact triangle arithmetic, finishes
-//               the pending Light::pdf weight, runs one bounce of raytrace_impl
-//               (src/raytrace.rs:12-60), and when a path ends adds it to the pixel and starts the
-//               pixel's next sample at once (samples of a pixel complete in index order, so the
-//               sum is deterministic).  Slots that still have work are appended to the next
-//               live list with a warp ballot + prefix-sum (stream compaction of live paths).
-//   k_wf_trace  persistent warps, fp32 only.  Each lane walks the culling hierarchy for one ray
-//               (closest-hit search and, for a pending diffuse bounce, the all-hits search of
-//               the light hierarchy along the same ray) and writes candidate lists.  A lane that
-//               finishes its ray does not wait for the slowest ray of its warp: when too few
-//               lanes remain busy the warp refills the idle ones from the live list.
+//   k_wf_confirm  the exact f64 triangle test of the candidates the previous trace found, one
+//                 (ray, candidate) pair per thread, folded per ray; proves that the reference
+//                 reaches the same hit or hands the ray to
+//   k_wf_exact    (forked branch) the reference's own traversal for those few rays;
+//   k_wf_shade    one thread per slot, f64: finishes the pending Light::pdf weight, runs one bounce
+//                 of raytrace_impl (src/raytrace.rs:12-60); a finished sample's radiance is parked
+//                 in the plane of its sample index and the slot claims the next item; slots with a
+//                 ray are appended to the trace list with a warp ballot + prefix-sum (stream
+//                 compaction of live paths), fresh camera rays at the front;
+//   k_wf_plan / k_wf_sum  complete sample planes are added to the accumulation buffer in sample
+//                 order — main.rs:100-103's order, so the sum is the megakernel's bit for bit;
+//   k_wf_trace    persistent warps, fp32 only.  Each lane walks the culling hierarchy for one ray
+//                 (closest-hit search and, for a pending diffuse bounce, the all-hits search of
+//                 the light hierarchy along the same ray) and writes candidate lists.  A lane that
+//                 finishes its ray does not wait for the slowest ray of its warp: when too few
+//                 lanes remain busy the warp refills the idle ones from the trace list.
 //
 // In a megakernel every lane waits for the slowest of its 32 rays at every bounce (ncu: 7 of 32
 // lanes active in the traversal loop); here the traversal loop stays full and the ~400-instruction
-// f64 confirmation runs with all lanes of a warp at once.  Arithmetic per path is identical to
+// f64 confirmation runs with most lanes of a warp at once.  Arithmetic per path is identical to
 // the megakernel in FAST mode, so both schedulers produce bitwise the same accumulation buffer.
 #include <cuda_runtime.h>
 
