@@ -291,3 +291,59 @@ def test_bvh_build_team_path_is_bit_exact():
     r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_host_scene.py", "-x", "-q", "-k", "soups or ties or larger_mesh"],
                        cwd=root, env=dict(os.environ, RT_TEAM_MIN="64"), capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def _random_scene_text(rng):
+    """A valid scene file with the keywords in random order inside each block, random optional
+    properties, mixed number formats, blank lines and unknown keywords (ignored by the parser,
+    src/scene_parser.rs:40-42)."""
+    def num(v):
+        return rng.choice([repr(float(v)), "%.6f" % v, "%.3e" % v, str(int(v)) if float(v).is_integer() else repr(float(v))])
+
+    def vec(n, lo=-3.0, hi=3.0):
+        return " ".join(num(v) for v in rng.uniform(lo, hi, n))
+
+    head = [f"DIMENSIONS {int(rng.integers(1, 40))} {int(rng.integers(1, 40))}"]
+    opt = [f"SAMPLES {int(rng.integers(1, 9))}", f"RAY_DEPTH {int(rng.integers(0, 20))}", "BG_COLOR " + vec(3, 0, 1),
+           "CAMERA_POSITION " + vec(3), "CAMERA_RIGHT " + vec(3), "CAMERA_UP " + vec(3), "CAMERA_FORWARD " + vec(3),
+           f"CAMERA_FOV_X {num(rng.uniform(0.2, 2.5))}", "SOMETHING_ELSE 1 2 3", ""]
+    head += [o for o in opt if rng.uniform() < 0.6]
+    rng.shuffle(head)
+    lines = list(head)
+    for _ in range(int(rng.integers(0, 25))):
+        kind = rng.choice(["BOX", "PLANE", "ELLIPSOID", "TRIANGLE"])
+        block = [kind + " " + (vec(9) if kind == "TRIANGLE" else vec(3, 0.05, 2.0))]
+        if rng.uniform() < 0.7:
+            block.append("POSITION " + vec(3))
+        if rng.uniform() < 0.5:
+            q = rng.normal(size=4)
+            block.append("ROTATION " + " ".join(num(v) for v in q / np.linalg.norm(q)))
+        if rng.uniform() < 0.7:
+            block.append("COLOR " + vec(3, 0, 1))
+        if rng.uniform() < 0.3:
+            block.append("EMISSION " + vec(3, 0, 9))
+        m = rng.uniform()
+        if m < 0.2:
+            block.append("METALLIC")
+        elif m < 0.4:
+            block += ["DIELECTRIC", f"IOR {num(rng.uniform(1.1, 2.4))}"]
+        rng.shuffle(block)
+        lines += ["NEW_PRIMITIVE"] + block + ([""] if rng.uniform() < 0.2 else [])
+    return "\n".join(lines) + "\n"
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_text_scenes_parse_and_build_like_the_oracle(orc, tmp_path, seed):
+    """Parser + Scene::new defaults + baking + the six hierarchies on random files: the C++ host
+    (scene_parser.rs / scene.rs restated in loaders.cpp, scene_build.cpp) against the oracle's own
+    Python parser and C++ build, bit for bit."""
+    from oracle import loaders
+    rng = np.random.default_rng(100 + seed)
+    text = _random_scene_text(rng)
+    prod = rtb200.Scene.load_text(helpers.write_text(tmp_path, text))
+    raw = loaders.parse_text_scene(text)
+    helpers.assert_scene_equal(prod, orc.OracleScene(raw))
+    i = prod.info
+    assert (i.width, i.height, i.samples, i.ray_depth) == (raw.width, raw.height, raw.samples, raw.ray_depth)
+    for name in ("bg_color", "cam_position", "cam_right", "cam_up", "cam_forward"):
+        assert list(getattr(i, name)) == [float(v) for v in getattr(raw, name)], name
