@@ -347,3 +347,137 @@ def test_random_text_scenes_parse_and_build_like_the_oracle(orc, tmp_path, seed)
     assert (i.width, i.height, i.samples, i.ray_depth) == (raw.width, raw.height, raw.samples, raw.ray_depth)
     for name in ("bg_color", "cam_position", "cam_right", "cam_up", "cam_forward"):
         assert list(getattr(i, name)) == [float(v) for v in getattr(raw, name)], name
+
+
+def _random_gltf(rng, tmp_path, name):
+    """A random glTF inside the subset the reference accepts: several meshes and
+    primitives, interleaved or separate buffer views, u16 / u32 / no indices, a node tree mixing TRS
+    and matrix nodes, random materials (alpha -> dielectric, metallicFactor, emissive + strength)."""
+    import json
+    blob = bytearray()
+    views, accessors, meshes, materials = [], [], [], []
+
+    def add_view(data, stride=None):
+        while len(blob) % 4:
+            blob.append(0)
+        v = {"buffer": 0, "byteOffset": len(blob), "byteLength": len(data)}
+        if stride:
+            v["byteStride"] = stride
+        blob.extend(data)
+        views.append(v)
+        return len(views) - 1
+
+    for _ in range(int(rng.integers(1, 4))):
+        m = {}
+        if rng.uniform() < 0.5:
+            m["pbrMetallicRoughness"] = {}
+            if rng.uniform() < 0.6:
+                m["pbrMetallicRoughness"]["metallicFactor"] = float(rng.choice([0.0, 0.0, 0.4, 1.0]))
+            if rng.uniform() < 0.6:
+                m["pbrMetallicRoughness"]["baseColorFactor"] = [float(v) for v in rng.uniform(0, 1, 3)] + [float(rng.choice([1.0, 0.5]))]
+        if rng.uniform() < 0.4:
+            m["emissiveFactor"] = [float(v) for v in rng.uniform(0, 1, 3)]
+            if rng.uniform() < 0.5:
+                m["extensions"] = {"KHR_materials_emissive_strength": {"emissive_strength": float(rng.uniform(1, 30))}}   # the reference reads this snake_case name
+        materials.append(m)
+    for _ in range(int(rng.integers(1, 4))):
+        prims = []
+        for _ in range(int(rng.integers(1, 3))):
+            nv = int(rng.integers(3, 40))
+            pos = rng.uniform(-2, 2, (nv, 3)).astype(np.float32)
+            nrm = rng.normal(size=(nv, 3)).astype(np.float32)
+            if rng.uniform() < 0.5:                                  # interleaved, stride 24 (+ optional padding)
+                pad = int(rng.choice([0, 8]))
+                inter = np.concatenate([pos, nrm, np.zeros((nv, pad // 4), np.float32)], axis=1)
+                bv = add_view(inter.tobytes(), 24 + pad)
+                accessors.append({"bufferView": bv, "componentType": 5126, "count": nv, "type": "VEC3"})
+                accessors.append({"bufferView": bv, "byteOffset": 12, "componentType": 5126, "count": nv, "type": "VEC3"})
+            else:
+                accessors.append({"bufferView": add_view(pos.tobytes()), "componentType": 5126, "count": nv, "type": "VEC3"})
+                accessors.append({"bufferView": add_view(nrm.tobytes()), "componentType": 5126, "count": nv, "type": "VEC3"})
+            p = {"attributes": {"POSITION": len(accessors) - 2, "NORMAL": len(accessors) - 1}}
+            kind = rng.integers(0, 3)
+            if kind:                                                 # indexed: u16 or u32
+                ni = 3 * int(rng.integers(1, 30))
+                dt, ct = (np.uint16, 5123) if kind == 1 else (np.uint32, 5125)
+                accessors.append({"bufferView": add_view(rng.integers(0, nv, ni).astype(dt).tobytes()), "componentType": ct, "count": ni, "type": "SCALAR"})
+                p["indices"] = len(accessors) - 1
+            else:
+                nv3 = nv - nv % 3                                     # non-indexed: whole triangles only
+                accessors[-2]["count"] = accessors[-1]["count"] = nv3
+            if rng.uniform() < 0.8:
+                p["material"] = int(rng.integers(0, len(materials)))
+            if rng.uniform() < 0.3:
+                p["mode"] = 4
+            prims.append(p)
+        meshes.append({"primitives": prims})
+    nodes = []
+
+    def make_node(depth):
+        n = {}
+        if rng.uniform() < 0.3:
+            q = rng.normal(size=4)
+            q /= np.linalg.norm(q)
+            x, y, z, w = q
+            R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                          [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                          [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+            M = np.eye(4)
+            M[:3, :3] = R * rng.uniform(0.5, 2.0, 3)
+            M[:3, 3] = rng.uniform(-3, 3, 3)
+            n["matrix"] = [float(v) for v in M.T.reshape(-1)]         # column-major
+        else:
+            if rng.uniform() < 0.6:
+                n["translation"] = [float(v) for v in rng.uniform(-3, 3, 3)]
+            if rng.uniform() < 0.6:
+                q = rng.normal(size=4)
+                n["rotation"] = [float(v) for v in q / np.linalg.norm(q)]
+            if rng.uniform() < 0.6:
+                n["scale"] = [float(v) for v in rng.uniform(0.3, 2.5, 3) * rng.choice([-1.0, 1.0], 3)]
+        if rng.uniform() < 0.7:
+            n["mesh"] = int(rng.integers(0, len(meshes)))
+        nodes.append(n)
+        me = len(nodes) - 1
+        if depth < 3:
+            kids = [make_node(depth + 1) for _ in range(int(rng.integers(0, 3)))]
+            if kids:
+                nodes[me]["children"] = kids
+        return me
+
+    roots = [make_node(0) for _ in range(int(rng.integers(1, 4)))]
+    cam = {"camera": 0, "translation": [float(v) for v in rng.uniform(-5, 5, 3)]}
+    q = rng.normal(size=4)
+    cam["rotation"] = [float(v) for v in q / np.linalg.norm(q)]
+    nodes.append(cam)
+    host = int(rng.integers(0, len(nodes) - 1))                       # the camera hangs somewhere in the tree
+    if rng.uniform() < 0.5:
+        nodes[host].setdefault("children", []).append(len(nodes) - 1)
+    else:
+        roots.append(len(nodes) - 1)
+    doc = {"scenes": [{"nodes": roots}], "scene": 0, "nodes": nodes, "meshes": meshes, "materials": materials,
+           "cameras": [{"type": "perspective", "perspective": {"yfov": float(rng.uniform(0.3, 1.5)), "znear": 0.1}}],
+           "buffers": [{"uri": name + ".bin", "byteLength": len(blob)}], "bufferViews": views, "accessors": accessors}
+    open(os.path.join(str(tmp_path), name + ".bin"), "wb").write(bytes(blob))
+    path = os.path.join(str(tmp_path), name + ".gltf")
+    json.dump(doc, open(path, "w"))
+    return path
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_gltf_files_load_and_build_like_the_oracle(orc, tmp_path, seed):
+    """gltf::parse + build_scene (src/gltf/*.rs) restated twice — loaders.cpp for the product,
+    oracle/loaders.py for the oracle — must agree bit for bit on random files: triangle order,
+    world-space vertices and normals, materials, camera axes, then the hierarchies."""
+    from oracle import loaders
+    rng = np.random.default_rng(500 + seed)
+    path = _random_gltf(rng, tmp_path, f"r{seed}")
+    w, h, spp = int(rng.integers(4, 60)), int(rng.integers(4, 60)), int(rng.integers(1, 9))
+    prod = rtb200.Scene.load_gltf(path, w, h, spp)
+    raw = loaders.load_gltf(path, w, h, spp)
+    helpers.assert_scene_equal(prod, orc.OracleScene(raw))
+    assert prod.info.n_materials == len(raw.materials)
+    for k in range(len(raw.materials)):
+        m = prod.material(k)
+        assert m.kind == raw.materials[k]["kind"] and list(m.emission) == [float(v) for v in raw.materials[k].get("emission", (0, 0, 0))], k
+    for name in ("cam_position", "cam_right", "cam_up", "cam_forward"):
+        assert list(getattr(prod.info, name)) == [float(v) for v in getattr(raw, name)], name
