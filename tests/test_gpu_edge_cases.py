@@ -216,3 +216,21 @@ def test_auto_mode_picks_by_scene_and_changes_nothing(ctx, tmp_path):
     assert ctx.counters()["kernel_launches"] > 4                          # the wavefront pipeline
     ctx.render_accum(0, 3, 9, T.MODE_EXACT, T.SCHED_MEGAKERNEL, clear=True)
     assert ctx.accum().tobytes() == auto.tobytes()
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (2, 3), (7, 5), (33, 1)])
+def test_tiny_images_and_regions(ctx, tmp_path, w, h):
+    """Images far smaller than a warp (the item queue then has fewer items per plane than a warp has
+    lanes, and most of the ring is reserve): wavefront == megakernel bit for bit, also for a
+    one-pixel region and for more samples than the ring has planes."""
+    from tests import helpers
+    ctx.upload(rtb200.Scene.load_text(helpers.cornell(tmp_path, w, h, 40, 5)))
+    ctx.render_accum(0, 40, 3, T.MODE_FAST, T.SCHED_MEGAKERNEL, clear=True)
+    want = ctx.accum()
+    ctx.render_accum(0, 40, 3, T.MODE_FAST, T.SCHED_WAVEFRONT, clear=True)
+    assert ctx.accum().tobytes() == want.tobytes() and want.sum() > 0
+    ctx.render_accum(0, 40, 3, T.MODE_FAST, T.SCHED_WAVEFRONT, clear=True, region=(w - 1, h - 1, 1, 1))
+    one = ctx.accum()
+    assert one[h - 1, w - 1].tobytes() == want[h - 1, w - 1].tobytes()
+    one[h - 1, w - 1] = 0
+    assert not one.any()
