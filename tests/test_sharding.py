@@ -81,3 +81,37 @@ def test_row_bands_partition_the_image():
             assert rows == list(range(height)), (height, world)
     with pytest.raises(ValueError):
         sharding.row_band(2, 2, 10, 10)
+
+
+def _band_worker(rank, world, port, text, total, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import loaders, orc
+    raw = loaders.parse_text_scene(text)
+    full, _ = orc.OracleScene(raw).render_accum(0, total, 0xC0FFEE, 1)     # the oracle renders whole images only:
+    band = sharding.row_band(rank, world, raw.width, raw.height)            # keep this rank's band, zero elsewhere
+    mine = np.zeros_like(full)
+    if band is not None:
+        _, y0, _, h = band
+        mine[y0:y0 + h] = full[y0:y0 + h]                                     # (H, W, 3)
+    t = torch.from_numpy(mine)
+    sharding.reduce_accum(t, dst=0)
+    if rank == 0:
+        np.save(out_path, t.numpy())
+    dist.destroy_process_group()
+
+
+def test_two_rank_row_bands_assemble_the_image_exactly(orc, tmp_path):
+    """Tile sharding over a 2-rank gloo group: every pixel receives exactly one non-zero
+    contribution, so the sum-reduce assembles the single-rank buffer BIT FOR BIT (unlike sample
+    ranges, where two partial sums are added)."""
+    from oracle import loaders
+    text = scenes.cornell_text(24, 18, 3, 4, scenes.CORNELL_EXTRA)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = os.path.join(str(tmp_path), "bands.npy")
+    mp.spawn(_band_worker, args=(2, port, text, 3, out), nprocs=2, join=True)
+    want, _ = orc.OracleScene(loaders.parse_text_scene(text)).render_accum(0, 3, 0xC0FFEE, 1)
+    got = np.load(out)
+    assert got.shape == want.shape and got.tobytes() == want.tobytes() and want.sum() > 0
