@@ -9,7 +9,6 @@ host loader of the product, which restates the same code independently.
 """
 import json
 import math
-import os
 
 import numpy as np
 
