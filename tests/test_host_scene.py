@@ -481,3 +481,40 @@ def test_random_gltf_files_load_and_build_like_the_oracle(orc, tmp_path, seed):
         assert m.kind == raw.materials[k]["kind"] and list(m.emission) == [float(v) for v in raw.materials[k].get("emission", (0, 0, 0))], k
     for name in ("cam_position", "cam_right", "cam_up", "cam_forward"):
         assert list(getattr(prod.info, name)) == [float(v) for v in getattr(raw, name)], name
+
+
+def test_scene_cache_survives_random_corruption(tmp_path):
+    """Random byte flips anywhere in a cache file: the load either fails with RT_ERR_IO or yields a
+    scene whose hierarchies pass the structural checks (flipped float payload is not detectable and
+    not dangerous) — it never crashes and never hands out-of-range indices to the device code."""
+    cache = tmp_path / "cache"
+    cache.mkdir()
+    path, _ = helpers.heightfield(tmp_path, 10, 12, lights=True, spheres=False)
+    rtb200.Scene.load_gltf(path, 16, 16, 1, cache_dir=str(cache))
+    (f,) = list(cache.glob("*.rtbvh"))
+    blob = f.read_bytes()
+    rng = np.random.default_rng(3)
+    outcomes = {"error": 0, "loaded": 0}
+    for trial in range(150):
+        bad = bytearray(blob)
+        region = len(blob) if trial % 3 else 4096                      # a third of the trials hit the header / first nodes
+        for _ in range(int(rng.integers(1, 6))):
+            pos = int(rng.integers(16, region))                        # keep the hash field region reachable, magic intact sometimes
+            bad[pos] ^= 1 << int(rng.integers(0, 8))
+        f.write_bytes(bytes(bad))
+        try:
+            sc = rtb200.Scene.load_gltf(path, 16, 16, 1, cache_dir=str(cache))
+        except rtb200.RtError as e:
+            assert e.code == 4, e
+            outcomes["error"] += 1
+            f.write_bytes(blob)                                        # (a hash mismatch rebuilt and rewrote the file: restore)
+            continue
+        outcomes["loaded"] += 1
+        for which in (T.BVH_TRIANGLES, T.BVH_LIGHT_TRIANGLES):
+            b = sc.bvh(which)
+            n, n_prims = len(b["left"]), int(sc.info.bvh_prims[which])
+            leaf = b["left"] == 0xFFFFFFFF
+            assert np.all(b["right"][~leaf] < n) and np.all(b["left"][~leaf] == np.nonzero(~leaf)[0] + 1)
+            assert np.all(b["first"][leaf].astype(np.int64) + b["count"][leaf] <= n_prims)
+        f.write_bytes(blob)
+    assert outcomes["error"] > 0 and outcomes["loaded"] > 0, outcomes
