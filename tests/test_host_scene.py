@@ -518,3 +518,45 @@ def test_scene_cache_survives_random_corruption(tmp_path):
             assert np.all(b["first"][leaf].astype(np.int64) + b["count"][leaf] <= n_prims)
         f.write_bytes(blob)
     assert outcomes["error"] > 0 and outcomes["loaded"] > 0, outcomes
+
+
+def test_loaders_survive_mutated_files(tmp_path):
+    """Truncated / byte-flipped scene files (text, glTF JSON, glTF .bin): the loaders either reject
+    them (RT_ERR_PARSE / RT_ERR_IO, where the reference would panic) or load something — they never
+    crash or read outside the buffers they were given."""
+    rng = np.random.default_rng(9)
+    text = _random_scene_text(np.random.default_rng(1))
+    gltf = _random_gltf(np.random.default_rng(2), tmp_path, "base")
+    gltf_json = open(gltf, "rb").read()
+    gltf_bin = open(gltf[:-5] + ".bin", "rb").read()
+    seen = {"ok": 0, "rejected": 0}
+
+    def mutate(data):
+        data = bytearray(data)
+        kind = rng.integers(0, 3)
+        if kind == 0 and len(data) > 8:
+            del data[int(rng.integers(1, len(data))):]                  # truncate
+        elif kind == 1:
+            for _ in range(int(rng.integers(1, 8))):
+                data[int(rng.integers(0, len(data)))] = int(rng.integers(32, 127))
+        else:
+            a = int(rng.integers(0, len(data)))
+            data[a:a] = bytes(rng.integers(32, 127, int(rng.integers(1, 12)), dtype=np.uint8))
+        return bytes(data)
+
+    def attempt(load):
+        try:
+            load()
+            seen["ok"] += 1
+        except rtb200.RtError as e:
+            assert e.code in (4, 5), e
+            seen["rejected"] += 1
+
+    for trial in range(int(os.environ.get("RT_FUZZ_TRIALS", 120))):
+        p = helpers.write_text(tmp_path, mutate(text.encode()).decode("latin-1"), "m.txt")
+        attempt(lambda: rtb200.Scene.load_text(p))
+        which = trial % 2
+        open(os.path.join(str(tmp_path), "m.gltf"), "wb").write(mutate(gltf_json.replace(b"base.bin", b"m.bin")) if which == 0 else gltf_json.replace(b"base.bin", b"m.bin"))
+        open(os.path.join(str(tmp_path), "m.bin"), "wb").write(gltf_bin if which == 0 else mutate(gltf_bin))
+        attempt(lambda: rtb200.Scene.load_gltf(os.path.join(str(tmp_path), "m.gltf"), 8, 8, 1))
+    assert seen["ok"] > 0 and seen["rejected"] > 0, seen
