@@ -8,6 +8,7 @@
 #include <fstream>
 #include <iostream>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -305,26 +306,15 @@ void import_nodes(const rt_built_bvh &b, HostBvh<P> &out) {
     if (b.n_nodes && (!b.bounds || !b.left || !b.right || !b.first || !b.count)) throw std::runtime_error("null node array");
     if (b.n_nodes >= RT_NO_CHILD || b.n_prims >= RT_NO_CHILD) throw std::runtime_error("hierarchy too large for 32-bit indices");
     out.nodes.resize(b.n_nodes);
-    std::vector<uint32_t> depth(b.n_nodes, 0);
-    if (b.n_nodes) depth[0] = 1;
-    out.depth = 0;
     for (uint64_t i = 0; i < b.n_nodes; ++i) {
         HostNode n{};
         for (int k = 0; k < 3; ++k) { n.box.lo[k] = b.bounds[i * 6 + k]; n.box.hi[k] = b.bounds[i * 6 + 3 + k]; }
         n.left = b.left[i]; n.right = b.right[i]; n.first = b.first[i]; n.count = b.count[i];
-        const bool leaf = n.left == RT_NO_CHILD;
-        if (leaf != (n.right == RT_NO_CHILD)) throw std::runtime_error("node with exactly one child");
-        if (leaf) {
-            if ((uint64_t)n.first + n.count > b.n_prims) throw std::runtime_error("leaf range outside the primitive array");
-        } else {
-            // the reference numbers nodes in pre-order (src/bvh.rs:104-108): left child = node + 1
-            if (n.left != i + 1 || n.right <= n.left || n.right >= b.n_nodes) throw std::runtime_error("nodes are not in the reference's pre-order numbering");
-            depth[n.left] = depth[i] + 1;
-            depth[n.right] = depth[i] + 1;
-        }
-        out.depth = std::max(out.depth, depth[i]);
         out.nodes[i] = n;
     }
+    // pre-order numbering, leaf ranges, one parent per node (a shared child would hide the real depth
+    // from the stack-size check of rt_upload_scene)
+    out.depth = validate_hierarchy(out.nodes, b.n_prims, "");
 }
 }  // namespace
 
@@ -589,7 +579,10 @@ int rt_upload_scene(rt_ctx *ctx, const rt_scene *scene) {
             return set_err(ctx, RT_ERR_LIMIT, "BVH depth " + std::to_string(d) + " exceeds the traversal stack (" + std::to_string(kExactStackHost) + ")");
     return guarded(ctx, RT_ERR_INVALID_ARG, [&]() -> int {
         CK(ctx, cudaSetDevice(ctx->device));
-        if (!scene->image) scene->image = make_image(s);
+        // built once per scene, whichever context (thread) uploads first: one host thread per GPU may
+        // upload the same rt_scene concurrently (rt_b200.h, "Threading")
+        std::call_once(scene->image_once, [&]() { scene->image = make_image(s); });
+        if (!scene->image) return set_err(ctx, RT_ERR_LIMIT, "the flattened scene image could not be built");
         const rt_device_image &im = *scene->image;
         for (int k = 0; k < 2; ++k)
             if (im.tris[k].fh.depth + 2 > (uint32_t)kFastStackHost)

@@ -144,11 +144,9 @@ __global__ void __launch_bounds__(128) k_render_mega(DScene sc, uint32_t sample_
 }
 
 // correct_gamma(aces_tonemap(sum / samples)), reference src/postprocessing.rs:5-38
-__global__ void k_postprocess(unsigned long long n, const double *__restrict__ accum, double inv_unused, double samples,
-                              double *__restrict__ rgb) {
+__global__ void k_postprocess(unsigned long long n, const double *__restrict__ accum, double samples, double *__restrict__ rgb) {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    (void)inv_unused;
     const double x = accum[i] / samples;
     double v = ((2.51 * x + 0.03) * x) / (((2.43 * x + 0.59) * x) + 0.14);
     v = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
@@ -205,7 +203,7 @@ cudaError_t launch_render_mega(cudaStream_t st, const DScene &sc, int mode, uint
 }
 cudaError_t launch_postprocess(cudaStream_t st, uint64_t n, const double *accum, uint32_t samples, double *rgb) {
     if (n == 0) return cudaSuccess;
-    k_postprocess<<<blocks_for(n, 256), 256, 0, st>>>(n, accum, 0.0, (double)samples, rgb);
+    k_postprocess<<<blocks_for(n, 256), 256, 0, st>>>(n, accum, (double)samples, rgb);
     return cudaGetLastError();
 }
 cudaError_t launch_rng_probe(cudaStream_t st, uint64_t seed, uint32_t pixel, uint32_t sample, uint64_t n, unsigned long long *u64_out,

@@ -8,6 +8,8 @@
 #include <algorithm>
 #include <atomic>
 #include <cstring>
+#include <deque>
+#include <exception>
 #include <limits>
 #include <stdexcept>
 #include <chrono>
@@ -57,14 +59,33 @@ struct Item {
 // Runs fn(t) for t in [0, team) on `team` threads (the caller is one of them).  Used by the few
 // nodes at the top of the hierarchy, where one node is all the work there is: their sorts and
 // sweeps are split over the threads that the subtree tasks further down will use afterwards.
+// A worker thread that is ALWAYS joined — also when the spawning scope unwinds (bad_alloc in the
+// other branch) — and whose own exception is re-thrown in the spawning thread by get(): nothing
+// may end in std::terminate behind the C ABI (capi.cpp's guarded() only sees exceptions that
+// arrive on the calling thread).
+class Task {
+    std::exception_ptr err_;
+    std::thread th_;
+public:
+    template <class F>
+    explicit Task(F &&f) : th_([this, fn = std::forward<F>(f)]() mutable {
+        try { fn(); } catch (...) { err_ = std::current_exception(); }
+    }) {}
+    Task(const Task &) = delete;
+    Task &operator=(const Task &) = delete;
+    ~Task() { if (th_.joinable()) th_.join(); }
+    void get() {
+        if (th_.joinable()) th_.join();
+        if (err_) std::rethrow_exception(err_);
+    }
+};
 template <class F>
 void run_team(int team, F &&fn) {
     if (team <= 1) { fn(0); return; }
-    std::vector<std::thread> ts;
-    ts.reserve(team - 1);
+    std::deque<Task> ts;                // a deque never moves its elements (Task hands `this` to its thread)
     for (int t = 1; t < team; ++t) ts.emplace_back([&fn, t]() { fn(t); });
     fn(0);
-    for (auto &th : ts) th.join();
+    for (auto &th : ts) th.get();
 }
 inline size_t chunk_begin(size_t n, int team, int t) { return n * (size_t)t / (size_t)team; }
 
@@ -304,12 +325,12 @@ struct Worker {
         if (n >= 16384 && sh.spare_threads.fetch_sub(1) > 0) {
             // right subtree on another thread into its own array, stitched in afterwards
             std::vector<HostNode> right_nodes;
-            std::thread th([&]() {
+            Task th([&]() {
                 Worker w(sh);
                 w.build(ord + nl, nr, global_offset + nl, right_nodes);
             });
             const uint32_t l = build(ord, nl, global_offset, out);
-            th.join();
+            th.get();
             sh.spare_threads.fetch_add(1);
             const uint32_t shift = (uint32_t)out.size();
             out.reserve(out.size() + right_nodes.size());
@@ -509,12 +530,12 @@ void build_scene(const rt_raw_scene &raw, HostScene &s) {
         const uint64_t n = raw.n_triangles;
         int nt = (int)std::thread::hardware_concurrency();
         if (nt < 1 || n < 65536) nt = 1;
-        std::vector<std::thread> ts;
+        std::deque<Task> ts;
         for (int t = 0; t < nt; ++t)
             ts.emplace_back([&, t]() {
                 for (uint64_t i = n * t / nt; i < n * (t + 1) / nt; ++i) tris[i] = bake_triangle(raw, i);
             });
-        for (auto &t : ts) t.join();
+        for (auto &t : ts) t.get();
         if (raw.tri_mat)
             for (uint64_t i = 0; i < n; ++i) check_mat(raw.tri_mat[i]);
         else if (n) check_mat(0);

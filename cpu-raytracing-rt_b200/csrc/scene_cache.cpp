@@ -10,6 +10,8 @@
 #include <cerrno>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
+#include <unistd.h>
 #include <stdexcept>
 
 #include "scene_host.hpp"
@@ -80,28 +82,40 @@ void get(FILE *f, void *p, size_t n) {
 // read from disk: a damaged file must not become an out-of-range index on the device.
 template <class P>
 void check_hierarchy(HostBvh<P> &b, size_t n_materials) {
-    const size_t nn = b.nodes.size(), np = b.prims.size();
-    std::vector<uint32_t> depth(nn, 0);
-    if (nn) depth[0] = 1;
-    b.depth = 0;
-    for (size_t i = 0; i < nn; ++i) {
-        const HostNode &n = b.nodes[i];
-        const bool leaf = n.left == RT_NO_CHILD;
-        if (leaf != (n.right == RT_NO_CHILD)) throw std::runtime_error("scene cache: node with exactly one child");
-        if (leaf) {
-            if ((uint64_t)n.first + n.count > np) throw std::runtime_error("scene cache: leaf range outside the primitive array");
-        } else {
-            if (n.left != i + 1 || n.right <= n.left || n.right >= nn) throw std::runtime_error("scene cache: nodes are not in pre-order numbering");
-            depth[n.left] = depth[i] + 1;
-            depth[n.right] = depth[i] + 1;
-        }
-        if (depth[i] > b.depth) b.depth = depth[i];
-    }
+    b.depth = validate_hierarchy(b.nodes, b.prims.size(), "scene cache: ");
     for (const P &p : b.prims)
         if (p.material >= n_materials) throw std::runtime_error("scene cache: material index out of range");
 }
 
 }  // namespace
+
+uint32_t validate_hierarchy(const std::vector<HostNode> &nodes, uint64_t n_prims, const char *prefix) {
+    const size_t nn = nodes.size();
+    const std::string pre(prefix);
+    std::vector<uint32_t> depth(nn, 0);
+    std::vector<uint8_t> parents(nn, 0);
+    uint32_t deepest = 0;
+    if (nn) depth[0] = 1;
+    for (size_t i = 0; i < nn; ++i) {
+        const HostNode &n = nodes[i];
+        // children always have larger indices than their parent, so by the time node i is visited
+        // every possible parent of it has been: a non-root node without one is unreachable
+        if (i > 0 && parents[i] != 1) throw std::runtime_error(pre + (parents[i] ? "node with two parents" : "unreachable node"));
+        const bool leaf = n.left == RT_NO_CHILD;
+        if (leaf != (n.right == RT_NO_CHILD)) throw std::runtime_error(pre + "node with exactly one child");
+        if (leaf) {
+            if ((uint64_t)n.first + n.count > n_prims) throw std::runtime_error(pre + "leaf range outside the primitive array");
+        } else {
+            if (n.left != i + 1 || n.right <= n.left || n.right >= nn) throw std::runtime_error(pre + "nodes are not in the reference's pre-order numbering");
+            for (const uint32_t c : {n.left, n.right}) {
+                if (parents[c] < 2) ++parents[c];
+                depth[c] = std::max(depth[c], depth[i] + 1);
+            }
+        }
+        deepest = std::max(deepest, depth[i]);
+    }
+    return deepest;
+}
 
 uint64_t geometry_hash(const rt_raw_scene &raw) {
     Hasher h;
@@ -157,7 +171,8 @@ void save_scene_cache(const std::string &path, uint64_t hash, const HostScene &s
             put(f.f, tr[k]->nodes.data(), tr[k]->nodes.size() * sizeof(HostNode));
             put(f.f, tr[k]->prims.data(), tr[k]->prims.size() * sizeof(HostTri));
         }
-        if (fflush(f.f) != 0) throw std::runtime_error(std::string("scene cache: write failed: ") + strerror(errno));
+        // flushed to the disk before the rename publishes it: a crash must not leave a short file under the final name
+        if (fflush(f.f) != 0 || fsync(fileno(f.f)) != 0) throw std::runtime_error(std::string("scene cache: write failed: ") + strerror(errno));
     }
     if (rename(tmp.c_str(), path.c_str()) != 0) {
         const std::string why = strerror(errno);
@@ -166,7 +181,7 @@ void save_scene_cache(const std::string &path, uint64_t hash, const HostScene &s
     }
 }
 
-bool load_scene_cache(const std::string &path, uint64_t hash, HostScene &s) {
+bool load_scene_cache(const std::string &path, uint64_t hash, const rt_raw_scene *raw, HostScene &s) {
     File f;
     f.f = fopen(path.c_str(), "rb");
     if (!f.f) return false;                                  // not cached yet
@@ -176,6 +191,16 @@ bool load_scene_cache(const std::string &path, uint64_t hash, HostScene &s) {
     if (hd.sz_node != sizeof(HostNode) || hd.sz_tri != sizeof(HostTri) || hd.sz_shape != sizeof(HostShape) || hd.sz_material != sizeof(rt_material))
         throw std::runtime_error("scene cache: " + path + " was written with another record layout");
     if (hd.hash != hash) return false;                       // another mesh under this name
+    if (raw) {
+        // the 64-bit hash is not cryptographic: a file that agrees on the hash but not on the COUNTS of
+        // the caller's scene is another mesh (a collision or a stale file) — a miss, the file is rewritten
+        uint64_t by_type[3] = {0, 0, 0};
+        for (uint32_t i = 0; i < raw->n_shapes; ++i)
+            if (raw->shapes[i].type >= 0 && raw->shapes[i].type < 3) ++by_type[raw->shapes[i].type];
+        if (hd.n_materials != raw->n_materials || hd.n_planes != by_type[RT_SHAPE_PLANE] || hd.n_prims[RT_BVH_BOXES] != by_type[RT_SHAPE_BOX] ||
+            hd.n_prims[RT_BVH_ELLIPSOIDS] != by_type[RT_SHAPE_ELLIPSOID] || hd.n_prims[RT_BVH_TRIANGLES] != raw->n_triangles)
+            return false;
+    }
     for (int k = 0; k < 6; ++k)
         if (hd.n_nodes[k] >= RT_NO_CHILD || hd.n_prims[k] >= RT_NO_CHILD) throw std::runtime_error("scene cache: counts out of range");
     // the counts are bounded by the file size before anything is allocated from them
@@ -231,7 +256,7 @@ bool build_scene_cached(const rt_raw_scene &raw, const std::string &cache_dir, H
     const uint64_t hash = geometry_hash(raw);
     const std::string path = scene_cache_path(cache_dir, hash);
     HostScene cached;
-    if (load_scene_cache(path, hash, cached)) {
+    if (load_scene_cache(path, hash, &raw, cached)) {
         apply_view(raw, cached);
         out = std::move(cached);
         return true;

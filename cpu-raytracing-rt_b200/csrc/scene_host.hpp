@@ -4,6 +4,7 @@
 #pragma once
 #include <cstdint>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -47,6 +48,13 @@ struct HostBvh {                    // src/bvh.rs:6-9
     uint32_t depth = 0;
 };
 
+// Structural check of a node array that did not come from build_bvh (a cache file, rt_scene_from_built):
+// the reference's pre-order numbering (left child = node + 1, src/bvh.rs:104-108), every leaf range
+// inside [0, n_prims), and EXACTLY ONE parent per non-root node — a node shared by two parents (a
+// DAG) would make the real path length exceed the depth computed here, and the traversal stacks are
+// sized from that depth.  Returns the depth (root = 1); throws std::runtime_error(prefix + reason).
+uint32_t validate_hierarchy(const std::vector<HostNode> &nodes, uint64_t n_prims, const char *prefix);
+
 struct HostScene {
     uint32_t width = 0, height = 0, samples = 0, ray_depth = 0;
     d3 bg_color{0, 0, 0};
@@ -74,7 +82,8 @@ void apply_view(const rt_raw_scene &raw, HostScene &s);     // image size, sampl
 uint64_t geometry_hash(const rt_raw_scene &raw);
 std::string scene_cache_path(const std::string &dir, uint64_t hash);
 void save_scene_cache(const std::string &path, uint64_t hash, const HostScene &s);
-bool load_scene_cache(const std::string &path, uint64_t hash, HostScene &s);       // false: absent or another mesh
+// false: absent or another mesh (hash or — when raw is given — the primitive / material counts differ)
+bool load_scene_cache(const std::string &path, uint64_t hash, const rt_raw_scene *raw, HostScene &s);
 bool build_scene_cached(const rt_raw_scene &raw, const std::string &cache_dir, HostScene &out);   // true: cache hit
 
 // Loaders (throw std::runtime_error where the reference would panic).
@@ -96,5 +105,6 @@ void save_ppm(const std::string &path, uint32_t w, uint32_t h, const double *rgb
 struct rt_device_image;                 // flattened, page-locked copy of the scene (capi.cpp)
 struct rt_scene {
     rt::HostScene s;
+    mutable std::once_flag image_once;                  // guards the lazy build below (concurrent uploads from one thread per GPU)
     mutable std::shared_ptr<rt_device_image> image;     // built on the first rt_upload_scene
 };

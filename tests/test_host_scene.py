@@ -218,6 +218,17 @@ def test_prebuilt_scene_round_trip(orc, tmp_path):
     d["count"][-1] += 5                                              # leaf range past the primitive array
     with pytest.raises(rtb200.RtError):
         rtb200.Scene.from_built(built2)
+    d["count"][-1] -= 5
+    # a child shared by two parents (a DAG): passes every per-node check, but the real path length
+    # is no longer what the depth pass computes and the traversal stacks are sized from that depth
+    assert d["left"][1] != 0xFFFFFFFF and d["right"][1] > 2
+    keep_right = d["right"][0]
+    d["right"][0] = d["right"][1]
+    with pytest.raises(rtb200.RtError) as e:
+        rtb200.Scene.from_built(built2)
+    assert "two parents" in str(e.value)
+    d["right"][0] = keep_right
+    rtb200.Scene.from_built(built2)                                  # restored: accepted again
 
 
 def test_scene_cache_round_trip(orc, tmp_path):
@@ -274,6 +285,27 @@ def test_scene_cache_rejects_damaged_files(tmp_path):
     with pytest.raises(rtb200.RtError) as e:
         rtb200.Scene.load_gltf(path, 16, 16, 1, cache_dir=str(cache))
     assert e.value.code == 4 and "pre-order" in str(e.value)
+    # same size, a child shared by two parents: root.right := node1.right
+    bad = bytearray(blob)
+    left1, right1 = struct.unpack_from("<2I", blob, first_node + 64 + 48)
+    assert left1 == 2 and right1 > 2
+    struct.pack_into("<I", bad, first_node + 48 + 4, right1)
+    f.write_bytes(bytes(bad))
+    with pytest.raises(rtb200.RtError) as e:
+        rtb200.Scene.load_gltf(path, 16, 16, 1, cache_dir=str(cache))
+    assert e.value.code == 4 and "two parents" in str(e.value)
+    # a file of another mesh that happens to carry this mesh's hash (collision / stale file): the
+    # counts in the header differ from the caller's scene -> a miss, rebuilt and rewritten, no error
+    other, _ = helpers.heightfield(tmp_path, 10, 12, lights=True, spheres=False, name="other.gltf")
+    cache2 = tmp_path / "cache2"
+    cache2.mkdir()
+    rtb200.Scene.load_gltf(other, 16, 16, 1, cache_dir=str(cache2))
+    (g,) = list(cache2.glob("*.rtbvh"))
+    forged = bytearray(g.read_bytes())
+    forged[32:40] = blob[32:40]                                      # the hash field of the first mesh
+    f.write_bytes(bytes(forged))
+    sc = rtb200.Scene.load_gltf(path, 16, 16, 1, cache_dir=str(cache))
+    assert not sc.cache_hit and f.read_bytes() == blob
     with pytest.raises(rtb200.RtError):                             # unwritable cache directory
         rtb200.Scene.load_gltf(path, 16, 16, 1, cache_dir=str(tmp_path / "missing" / "dir"))
 
