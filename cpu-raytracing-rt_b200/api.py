@@ -22,7 +22,11 @@ SYMBOLS = [
     "rt_device_count", "rt_create", "rt_destroy", "rt_last_error", "rt_upload_scene", "rt_scene_device_bytes", "rt_trace_rays",
     "rt_trace_primary", "rt_light_pdf", "rt_render_accum", "rt_accum_device_ptr", "rt_get_accum", "rt_set_accum",
     "rt_postprocess", "rt_render", "rt_render_progressive", "rt_sync", "rt_stream", "rt_get_counters", "rt_reset_counters", "rt_debug_rng",
+    "rt_shard_sample_range", "rt_comm_unique_id", "rt_comm_init", "rt_comm_info", "rt_reduce_accum",
+    "rt_group_create", "rt_group_destroy", "rt_group_size", "rt_group_ctx", "rt_group_last_error", "rt_group_upload_scene",
+    "rt_group_render_accum", "rt_group_reduce_accum", "rt_group_render", "rt_group_render_progressive",
 ]
+COMM_ID_BYTES = 128
 
 
 class RtError(RuntimeError):
@@ -85,6 +89,24 @@ def lib():
         L.rt_get_counters.argtypes = [vp, C.POINTER(T.Counters)]
         L.rt_reset_counters.argtypes = [vp]
         L.rt_debug_rng.argtypes = [vp, u64, u32, u32, u64, vp, vp]
+        L.rt_shard_sample_range.argtypes = [i32, i32, u32, u32, C.POINTER(u32), C.POINTER(u32)]
+        L.rt_comm_unique_id.argtypes = [vp]
+        L.rt_comm_init.argtypes = [vp, vp, i32, i32]
+        L.rt_comm_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+        L.rt_reduce_accum.argtypes = [vp, i32]
+        L.rt_group_create.argtypes = [i32, C.POINTER(i32), C.POINTER(vp)]
+        L.rt_group_destroy.argtypes = [vp]
+        L.rt_group_destroy.restype = None
+        L.rt_group_size.argtypes = [vp, C.POINTER(i32)]
+        L.rt_group_ctx.argtypes = [vp, i32]
+        L.rt_group_ctx.restype = vp
+        L.rt_group_last_error.argtypes = [vp]
+        L.rt_group_last_error.restype = C.c_char_p
+        L.rt_group_upload_scene.argtypes = [vp, vp]
+        L.rt_group_render_accum.argtypes = [vp, C.POINTER(T.RenderParams)]
+        L.rt_group_reduce_accum.argtypes = [vp]
+        L.rt_group_render.argtypes = [vp, u64, i32, i32, vp]
+        L.rt_group_render_progressive.argtypes = [vp, u64, i32, i32, u32, T.ProgressFn, vp, vp, C.POINTER(u32)]
         _LIB = L
     return _LIB
 
@@ -236,20 +258,54 @@ class Scene:
         return m
 
 
+def shard_sample_range(rank, world, total_samples, first_sample=0):
+    """The library's partition of a sample range over `world` devices -> (begin, count)."""
+    b, c = C.c_uint32(), C.c_uint32()
+    _check(lib().rt_shard_sample_range(rank, world, total_samples, first_sample, C.byref(b), C.byref(c)))
+    return b.value, c.value
+
+
+def comm_unique_id():
+    """128 bytes rank 0 creates and the launcher broadcasts (ncclGetUniqueId inside the library)."""
+    buf = (C.c_ubyte * COMM_ID_BYTES)()
+    _check(lib().rt_comm_unique_id(buf))
+    return bytes(buf)
+
+
 class Context:
     """One CUDA device.  render() == generate_image (src/main.rs:85-114)."""
 
-    def __init__(self, device=0):
-        h = C.c_void_p()
-        _check(lib().rt_create(device, C.byref(h)))
-        self._h = h
+    def __init__(self, device=0, _borrowed=None):
+        if _borrowed is not None:           # a context owned by a Group
+            self._h, self._owned = C.c_void_p(_borrowed), False
+        else:
+            h = C.c_void_p()
+            _check(lib().rt_create(device, C.byref(h)))
+            self._h, self._owned = h, True
         self.device = device
         self.scene = None
 
     def close(self):
         if getattr(self, "_h", None):
-            lib().rt_destroy(self._h)
+            if self._owned:
+                lib().rt_destroy(self._h)
             self._h = None
+
+    def comm_init(self, unique_id, rank, world):
+        """Join the in-library NCCL communicator (collective: every rank calls it)."""
+        assert len(unique_id) == COMM_ID_BYTES
+        buf = (C.c_ubyte * COMM_ID_BYTES).from_buffer_copy(unique_id)
+        _check(lib().rt_comm_init(self._h, buf, rank, world), self._h)
+        return self
+
+    def comm_info(self):
+        r, w, v = C.c_int(), C.c_int(), C.c_int()
+        _check(lib().rt_comm_info(self._h, C.byref(r), C.byref(w), C.byref(v)), self._h)
+        return {"rank": r.value, "world": w.value, "nccl_version": v.value}
+
+    def reduce_accum(self, root=0):
+        """Sum-reduce of the accumulation buffers onto `root` (ncclReduce on the context's stream)."""
+        _check(lib().rt_reduce_accum(self._h, root), self._h)
 
     __del__ = close
 
@@ -376,6 +432,73 @@ class Context:
         probe = np.zeros(8)
         _check(lib().rt_debug_rng(self._h, seed, pixel, sample, n, _p(u), _p(probe)), self._h)
         return u, probe
+
+
+class Group:
+    """Several CUDA devices of this process behind one handle (rt_group_*): the scene is replicated,
+    the sample range is split, the accumulation buffers are sum-reduced to device 0 over NCCL."""
+
+    def __init__(self, devices=None):
+        h = C.c_void_p()
+        if devices is None:
+            _check(lib().rt_group_create(0, None, C.byref(h)))
+        else:
+            ids = (C.c_int * len(devices))(*devices)
+            _check(lib().rt_group_create(len(devices), ids, C.byref(h)))
+        self._h = h
+        n = C.c_int()
+        lib().rt_group_size(self._h, C.byref(n))
+        self.size = n.value
+        self.scene = None
+
+    def _check(self, code):
+        if code != 0:
+            raise RtError(code, (lib().rt_group_last_error(self._h) or b"").decode("utf-8", "replace"))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().rt_group_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def ctx(self, i):
+        """Borrowed Context of device i (0 = root); valid while the group lives."""
+        h = lib().rt_group_ctx(self._h, i)
+        if not h:
+            raise IndexError(i)
+        c = Context(_borrowed=h)
+        c.scene = self.scene
+        return c
+
+    def upload(self, scene):
+        self._check(lib().rt_group_upload_scene(self._h, scene._h))
+        self.scene = scene
+        return self
+
+    def render_accum(self, sample_begin, sample_count, seed, mode=T.MODE_FAST, sched=None, clear=False):
+        if sched is None:
+            sched = T.SCHED_WAVEFRONT if mode == T.MODE_FAST else T.SCHED_MEGAKERNEL
+        p = T.RenderParams(sample_begin, sample_count, seed, mode, sched, 1 if clear else 0, 0)
+        self._check(lib().rt_group_render_accum(self._h, C.byref(p)))
+
+    def reduce_accum(self):
+        self._check(lib().rt_group_reduce_accum(self._h))
+
+    def render(self, seed=0xC0FFEE, mode=T.MODE_FAST, sched=None):
+        if sched is None:
+            sched = T.SCHED_WAVEFRONT if mode == T.MODE_FAST else T.SCHED_MEGAKERNEL
+        out = np.zeros((self.scene.height, self.scene.width, 3))
+        self._check(lib().rt_group_render(self._h, seed, mode, sched, _p(out)))
+        return out
+
+    def render_progressive(self, chunk_samples, seed=0xC0FFEE, mode=T.MODE_FAST, sched=None):
+        if sched is None:
+            sched = T.SCHED_WAVEFRONT if mode == T.MODE_FAST else T.SCHED_MEGAKERNEL
+        out = np.zeros((self.scene.height, self.scene.width, 3))
+        done = C.c_uint32(0)
+        self._check(lib().rt_group_render_progressive(self._h, seed, mode, sched, chunk_samples, C.cast(None, T.ProgressFn), None, _p(out), C.byref(done)))
+        return out, done.value
 
 
 def save_ppm(path, rgb):

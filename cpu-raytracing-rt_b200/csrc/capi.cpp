@@ -21,43 +21,11 @@
 
 using namespace rt;
 
-static thread_local std::string g_last_error;
+#include "ctx.hpp"
 
-struct rt_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    std::string err;
-    char *arena = nullptr;              // one device allocation holding every scene record
-    size_t arena_cap = 0, arena_used = 0;
-    DScene dsc{};
-    bool has_scene = false;
-    double *d_accum = nullptr, *d_rgb = nullptr;
-    size_t n_px = 0;
-    DCounters *d_ctr = nullptr;
-    uint64_t launches = 0;
-    uint32_t samples = 0;
-    size_t scene_bytes = 0;
-    // wavefront scheduler state (allocated on first use, sized by the image)
-    char *wf_arena = nullptr;
-    WfBuf wf{};
-    uint32_t *wf_host_live = nullptr;   // pinned
-    cudaEvent_t wf_event = nullptr;
-    int wf_blocks = 0;
-};
+thread_local std::string rt::g_last_error;
 
 namespace {
-
-int set_err(rt_ctx *ctx, int code, const std::string &msg) {
-    g_last_error = msg;
-    if (ctx) ctx->err = msg;
-    return code;
-}
-#define CK(ctx, call)                                                                                   \
-    do {                                                                                                \
-        cudaError_t e_ = (call);                                                                        \
-        if (e_ != cudaSuccess)                                                                          \
-            return set_err(ctx, RT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));      \
-    } while (0)
 
 template <class F>
 int guarded(rt_ctx *ctx, int code_on_throw, F &&f) {
@@ -82,14 +50,12 @@ cudaError_t ensure_wavefront(rt_ctx *ctx) {
     // GPU, large ones one slot per pixel.  RT_WF_CAP overrides the capacity (experiments).
     const uint32_t n_img = (uint32_t)ctx->n_px;
     uint64_t cap = wf_slots_for(n_img);
-    if (const char *e = std::getenv("RT_WF_CAP")) { const long long v = std::atoll(e); if (v >= 1024 && v <= (1ll << 28)) cap = (uint64_t)v; }
+    if (ctx->knob_cap) cap = ctx->knob_cap;
     const uint32_t n = (uint32_t)cap;
     if (ctx->wf_arena && ctx->wf.n == n && ctx->wf.n_px_cap == n_img) return cudaSuccess;
     free_wavefront(ctx);
     const size_t per = (wf_bytes_per_slot() + 15) & ~(size_t)15;
-    uint32_t ring = kWfRing, batch = 4;
-    if (const char *e = std::getenv("RT_WF_RING")) { const int v = std::atoi(e); if (v >= 8 && v <= 256) ring = (uint32_t)v; }     // experiments
-    if (const char *e = std::getenv("RT_WF_BATCH")) { const int v = std::atoi(e); if (v >= 1 && v <= 64) batch = (uint32_t)v; }
+    const uint32_t ring = ctx->knob_ring, batch = ctx->knob_batch;
     const size_t total = per * n + (size_t)n_img * 24 * ring + 65536 + 64 * 256;
     cudaError_t e = cudaMalloc(&ctx->wf_arena, total);
     if (e != cudaSuccess) return e;
@@ -109,27 +75,21 @@ cudaError_t ensure_wavefront(rt_ctx *ctx) {
     for (double **q : res) *q = (double *)take((size_t)n * 8);
     b.live[0] = (uint32_t *)take((size_t)n * 4);
     b.live[1] = (uint32_t *)take((size_t)n * 4);
-    b.n_live = (uint32_t *)take(16);
-    b.n_slots = n;
+    b.n_live = (uint32_t *)take(32);                    // [0..3] the two lists, [4] cursor, [5] n_x: words 2..5 are cleared together
     b.ring = ring;
     b.batch = batch;
     b.pix = (uint32_t *)take((size_t)n * 4);
     b.ord = (uint32_t *)take((size_t)n * 4);
     b.side = (double *)take((size_t)n_img * 24 * ring);
     b.n_px_cap = n_img;
-    b.reserve = 2;
     b.item = (unsigned long long *)take(24);
     b.plane = (uint32_t *)take(16);
-    b.cursor = (uint32_t *)take(8);
-    b.n_x = b.cursor + 1;
+    b.cursor = b.n_live + 4;
+    b.n_x = b.n_live + 5;
+    b.call = (WfCall *)take(sizeof(WfCall));
     b.xlist = (uint32_t *)take((size_t)n * 4);
     if ((size_t)(p - ctx->wf_arena) > total) return cudaErrorMemoryAllocation;
-    if (!ctx->wf_host_live) {
-        e = cudaHostAlloc((void **)&ctx->wf_host_live, 4 * sizeof(uint32_t), cudaHostAllocDefault);
-        if (e != cudaSuccess) return e;
-        e = cudaEventCreateWithFlags(&ctx->wf_event, cudaEventDisableTiming);
-        if (e != cudaSuccess) return e;
-    }
+    if (!ctx->wf_rt.side && (e = wf_runtime_init(ctx->wf_rt)) != cudaSuccess) return e;
     ctx->wf_blocks = wf_trace_blocks(ctx->device);
     return cudaSuccess;
 }
@@ -554,6 +514,14 @@ int rt_create(int device_id, rt_ctx **out) {
     CK(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CK(nullptr, cudaMalloc(&ctx->d_ctr, sizeof(DCounters)));
     CK(nullptr, cudaMemsetAsync(ctx->d_ctr, 0, sizeof(DCounters), ctx->stream));
+    // experiment knobs of the wavefront scheduler: read here, once, not on the render path
+    if (const char *e = std::getenv("RT_WF_CAP")) { const long long v = std::atoll(e); if (v >= 1024 && v <= (1ll << 28)) ctx->knob_cap = (uint64_t)v; }
+    if (const char *e = std::getenv("RT_WF_RING")) { const int v = std::atoi(e); if (v >= 8 && v <= 256) ctx->knob_ring = (uint32_t)v; }
+    if (const char *e = std::getenv("RT_WF_BATCH")) { const int v = std::atoi(e); if (v >= 1 && v <= 64) ctx->knob_batch = (uint32_t)v; }
+    // k_wf_plan only moves on when `batch` planes are complete, and at most ring - reserve (reserve <= 4)
+    // planes are ever open: a larger batch would never be reached
+    if (ctx->knob_batch > ctx->knob_ring - 4u) ctx->knob_batch = ctx->knob_ring - 4u;
+    if (const char *e = std::getenv("RT_WF_SLOTS")) { const long long v = std::atoll(e); if (v >= 1024) ctx->wf_rt.slots_override = (uint64_t)v; }
     *out = ctx.release();
     return RT_OK;
 }
@@ -561,10 +529,10 @@ void rt_destroy(rt_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    comm_release(ctx);
     free_scene(ctx, false);
     if (ctx->d_ctr) cudaFree(ctx->d_ctr);
-    if (ctx->wf_host_live) cudaFreeHost(ctx->wf_host_live);
-    if (ctx->wf_event) cudaEventDestroy(ctx->wf_event);
+    wf_runtime_destroy(ctx->wf_rt);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -706,6 +674,12 @@ int rt_render_accum(rt_ctx *ctx, const rt_render_params *p) {
     rt_render_params resolved = *p;                     // RT_MODE_AUTO / RT_SCHED_AUTO -> what suits the scene
     const bool has_tris = ctx->dsc.tris.n_prims != 0;
     if (resolved.mode == RT_MODE_AUTO) resolved.mode = has_tris ? RT_MODE_FAST : RT_MODE_EXACT;
+    // A scene whose coordinates leave the range of the fp32 culling arithmetic (fast.cuh, kFastRange)
+    // is rendered by the exact traversal whatever was asked for: same image, bit for bit.
+    if (resolved.mode == RT_MODE_FAST && has_tris && !(ctx->dsc.ftris.bound <= kFastRange)) {
+        resolved.mode = RT_MODE_EXACT;
+        resolved.sched = RT_SCHED_MEGAKERNEL;
+    }
     if (resolved.sched == RT_SCHED_AUTO) resolved.sched = (resolved.mode == RT_MODE_FAST && has_tris) ? RT_SCHED_WAVEFRONT : RT_SCHED_MEGAKERNEL;
     p = &resolved;
     if (int r = check_mode(ctx, p->mode)) return r;
@@ -722,8 +696,8 @@ int rt_render_accum(rt_ctx *ctx, const rt_render_params *p) {
     if (p->sched == RT_SCHED_WAVEFRONT && ctx->dsc.ray_depth > 0) {
         if (p->mode != RT_MODE_FAST) return set_err(ctx, RT_ERR_INVALID_ARG, "the wavefront scheduler runs FAST mode only (EXACT is the megakernel parity anchor)");
         CK(ctx, ensure_wavefront(ctx));
-        CK(ctx, launch_render_wavefront(ctx->stream, ctx->dsc, p->sample_begin, p->sample_count, p->seed, ctx->d_accum, ctx->d_ctr,
-                                        ctx->wf, ctx->wf_host_live, ctx->wf_event, ctx->wf_blocks, &ctx->launches, rg));
+        CK(ctx, launch_render_wavefront(ctx->stream, ctx->wf_rt, ctx->dsc, p->sample_begin, p->sample_count, p->seed, ctx->d_accum,
+                                        ctx->d_ctr, ctx->wf, ctx->wf_blocks, &ctx->launches, rg));
         return RT_OK;
     }
     CK(ctx, launch_render_mega(ctx->stream, ctx->dsc, p->mode, p->sample_begin, p->sample_count, p->seed, ctx->d_accum, ctx->d_ctr, rg));

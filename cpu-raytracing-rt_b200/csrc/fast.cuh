@@ -14,10 +14,15 @@
 //   * every surviving candidate runs tri_exact (the reference's own arithmetic) and only its
 //     f64 (t, u, v) are ever used.  Results are therefore the EXACT-mode ones (ids, t, normals,
 //     light PDFs), which tests/test_gpu_parity.py::test_fast_mode_equals_exact_mode asserts bitwise.
-// Differences from EXACT by construction: equal-t ties between triangles of DIFFERENT leaves go to
-// the lowest primitive index (the reference keeps the first one in its visit order), and rays whose
-// hits lie beyond t ~ 1e9 are out of range of the fp32 slabs.
+// Range: fp32 culling is used while the scene bound and the ray origin stay below kFastRange (1e15:
+// far from every fp32 overflow — triple products of edges, __fdividef's 2^126 limit); beyond it the
+// ray is answered by the exact traversal (fast_in_range).  Inside the range, a ray that starts very
+// far from a small triangle (distance / triangle size ~ 1e9) is dominated by the f64 rounding of
+// `origin - a`, in the reference's arithmetic as much as here: that error is folded into the pre-test's
+// bounds (fast_wpad), so such rays turn into undecided candidates — confirmed exactly — never into
+// wrong rejections.
 #pragma once
+#include "exact_limits.hpp"
 #include "shade.cuh"
 
 namespace rt {
@@ -29,6 +34,21 @@ constexpr float kU = 5.9604645e-8f;         // 2^-24, fp32 unit roundoff
 // relative size u on top of the 4u of the cross-product component it multiplies, so
 // |computed - exact| <= 8u * sum_k |w_k| (|d_i e_j| + |d_j e_i|) <= 8u * |w|_1 |d|_1 |e|_1.
 constexpr float kGamma = 5.4e-7f;           // 9u > 8u (1 + O(u))
+// The pre-test forms w = (o + tref*d) - a in f64 and rounds it once to fp32; its error bounds are
+// proportional to |w|_1 and assume that the f64 step is exact.  It is not: o - a is rounded (relative
+// 2^-53 of |o - a|, the SAME rounded difference the reference's test starts from, triangle.rs:66),
+// the reference's own matrix-vector product adds ~7 roundings of that size, and tref*d adds one.  All of
+// it is bounded by 16 * 2^-53 * (|tref*d|_1 + |o - a|_1) <= 16 * 2^-53 * (2|o|_1 + 6*bound): the entry
+// point o + tref*d lies between the origin and the leaf, and |a|_1 <= 3*bound.  Expressed as an
+// addition to |w|_1 (divide by kGamma) it is one per-ray constant.
+RT_D float fast_wpad(d3 o, float bound) {
+    const float o1 = __double2float_ru(fabs(o.x) + fabs(o.y) + fabs(o.z));
+    return 6.7e-9f * (o1 + 3.0f * bound);   // 2 * 16 * 2^-53 / kGamma = 6.6e-9
+}
+RT_D bool fast_in_range(d3 o, float bound) {
+    // false also for a NaN / infinite origin
+    return fabs(o.x) <= (double)kFastRange && fabs(o.y) <= (double)kFastRange && fabs(o.z) <= (double)kFastRange && bound <= kFastRange;
+}
 
 // Per-ray culling state.  For a box plane b the slab distance (b - o) / d is evaluated as
 // fma(b, id, n) with id = 1/fl(d), n = -(fl(o) * id):  computed = true*(1+eta) + delta with
@@ -113,6 +133,10 @@ RT_D void sort4(Visit4 &v) {
 #undef RT_CE
 }
 
+struct F3 {                 // the ray direction rounded to fp32 (all the pre-test needs of FRay)
+    float dx, dy, dz;
+};
+RT_D F3 f3_of(const FRay &r) { F3 f; f.dx = r.dx; f.dy = r.dy; f.dz = r.dz; return f; }
 struct FTriRec {
     d3 a;
     float bax, bay, baz, cax, cay, caz;
@@ -151,7 +175,7 @@ RT_D bool det_below_threshold(const DTriI *tp, d3 d) {
                        c2.x * (c0.y * c1.z - c1.y * c0.z);
     return fabs(det) < kTriDetMin;
 }
-RT_D int tri_classify(const FTri *tp, const DTriI *xp, const FRay &r, d3 o, d3 d, float tref, float dl1g, float tmax, float &tlo, float &thi) {
+RT_D int tri_classify(const FTri *tp, const DTriI *xp, const F3 r, d3 o, d3 d, float tref, float dl1g, float wpad, float tmax, float &tlo, float &thi) {
     const FTriRec t = load_ftri(tp);
     const double tr = (double)tref;
     const float wx = __double2float_rn(fma(tr, d.x, o.x - t.a.x)), wy = __double2float_rn(fma(tr, d.y, o.y - t.a.y)),
@@ -162,7 +186,7 @@ RT_D int tri_classify(const FTri *tp, const DTriI *xp, const FRay &r, d3 o, d3 d
     const float qx = fmaf(wy, t.baz, -(wz * t.bay)), qy = fmaf(wz, t.bax, -(wx * t.baz)), qz = fmaf(wx, t.bay, -(wy * t.bax));
     const float V = fmaf(r.dx, qx, fmaf(r.dy, qy, r.dz * qz));
     const float Tn = fmaf(t.cax, qx, fmaf(t.cay, qy, t.caz * qz));
-    const float w1 = fabsf(wx) + fabsf(wy) + fabsf(wz);
+    const float w1 = fabsf(wx) + fabsf(wy) + fabsf(wz) + wpad;      // + the f64 rounding of the subtraction (fast_wpad)
     const float lb = fabsf(t.bax) + fabsf(t.bay) + fabsf(t.baz), lc = fabsf(t.cax) + fabsf(t.cay) + fabsf(t.caz);
     const float eu = dl1g * w1 * lc, ev = dl1g * w1 * lb, et = kGamma * w1 * lb * lc, ed = dl1g * lb * lc;
     const float ad = fabsf(det);
@@ -297,6 +321,7 @@ RT_D void closest_fast(const FBvh f, const DTriI *tri_i, d3 o, d3 d, float tmax,
     if (f.root == kFastEmpty || ray_is_nan(o, d)) return;
     const FRay r = make_fray(o, d);
     const float dl1g = kGamma * (fabsf(r.dx) + fabsf(r.dy) + fabsf(r.dz));
+    const float wpad = fast_wpad(o, f.bound);
     int32_t stk_n[kFastStack];
     float stk_t[kFastStack];
     uint32_t cand_p[kCand];
@@ -330,7 +355,7 @@ RT_D void closest_fast(const FBvh f, const DTriI *tri_i, d3 o, d3 d, float tmax,
             const uint32_t code = (uint32_t)~cur, first = code >> 3, count = (code & 7u) + 1u;
             for (uint32_t i = first; i < first + count; ++i) {
                 float tlo, thi;
-                const int cls = tri_classify(f.tris + i, tri_i + i, r, o, d, cur_t, dl1g, tmax, tlo, thi);
+                const int cls = tri_classify(f.tris + i, tri_i + i, f3_of(r), o, d, cur_t, dl1g, wpad, tmax, tlo, thi);
                 if (cls == 0) continue;
                 if (cls == 2) tmax = fminf(tmax, thi);
                 if (nc == kCand) {                  // rare: drop entries the new bound excludes
@@ -428,6 +453,7 @@ static __device__ __noinline__ SceneHit intersect_exact_cold(const DScene &sc, d
     return intersect_exact(sc, o, d, scratch);
 }
 RT_D SceneHit intersect_fast(const DScene &sc, d3 o, d3 d, Cnt &c) {
+    if (sc.ftris.root != kFastEmpty && !fast_in_range(o, sc.ftris.bound) && !ray_is_nan(o, d)) { ++c.xf; return intersect_exact_cold(sc, o, d); }
     const ShapeBest sb = shapes_closest(sc, o, d, c);
     FBest fb;
     fbest_clear(fb);
@@ -458,6 +484,7 @@ RT_D bool light_hits_fast(const FBvh f, const DTriI *tri_i, const DTriS *tri_s, 
     if (f.root == kFastEmpty) return false;
     const FRay r = make_fray(o, d);
     const float dl1g = kGamma * (fabsf(r.dx) + fabsf(r.dy) + fabsf(r.dz));
+    const float wpad = fast_wpad(o, f.bound);
     const float inf = __int_as_float(0x7F800000);
     int32_t stk[kFastStack];
     float stk_t[kFastStack];
@@ -478,7 +505,7 @@ RT_D bool light_hits_fast(const FBvh f, const DTriI *tri_i, const DTriS *tri_s, 
             const uint32_t code = (uint32_t)~cur, first = code >> 3, count = (code & 7u) + 1u;
             for (uint32_t i = first; i < first + count; ++i) {
                 float tlo, thi;
-                if (tri_classify(f.tris + i, tri_i + i, r, o, d, cur_t, dl1g, inf, tlo, thi) == 0) continue;
+                if (tri_classify(f.tris + i, tri_i + i, f3_of(r), o, d, cur_t, dl1g, wpad, inf, tlo, thi) == 0) continue;
                 if (nc == kCand) {                  // flush in visit order, then keep collecting
                     for (int j = 0; j < kCand; ++j) frag = light_confirm(tri_i, tri_s, o, d, cand[j], impact, (double)f.bound) || frag;
                     nc = 0;
@@ -504,7 +531,7 @@ static __device__ __noinline__ void light_tris_exact_cold(const DScene &sc, d3 o
 // the emissive triangles' part of Light::pdf, added to `impact` (which holds the analytic lights' part)
 RT_D void light_tris_impact_fast(const DScene &sc, d3 o, d3 dir, double &impact, Cnt &c) {
     const double base = impact;
-    if (light_hits_fast(sc.fltris, sc.ltri_i, sc.ltri_s, o, dir, impact)) {
+    if ((sc.fltris.root != kFastEmpty && !fast_in_range(o, sc.fltris.bound)) || light_hits_fast(sc.fltris, sc.ltri_i, sc.ltri_s, o, dir, impact)) {
         ++c.xf;
         impact = base;
         light_tris_exact_cold(sc, o, dir, impact);

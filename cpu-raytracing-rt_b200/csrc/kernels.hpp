@@ -19,6 +19,14 @@ cudaError_t launch_render_mega(cudaStream_t st, const DScene &sc, int mode, uint
 // ---- wavefront scheduler (wavefront.cu) ----------------------------------------------------------
 constexpr int kWfCand = 6;              // deferred candidates kept per ray and per search
 constexpr uint32_t kWfRing = 16;        // sample planes of finished radiance kept before they are added to the image, in order
+// What differs from one render call to the next lives in DEVICE memory, so the kernel arguments —
+// and with them the instantiated CUDA graph of the iteration — stay the same for as long as the
+// scene and the buffers do: a call costs one k_wf_init launch, not a capture + instantiate.
+struct WfCall {
+    uint32_t sample_begin, n_slots, reserve, n_px;  // first global sample; slots in use (<= WfBuf::n); planes kept free for claim overshoot; pixels of the region
+    unsigned long long seed;
+    DRegion rg;
+};
 struct WfBuf {                          // path slots, structure of arrays; n = width * height = capacity of every array
     uint32_t n;
     double *ro, *rd, *T, *L, *pv;       // 3 * n: ray origin / direction, throughput, radiance, pending weight
@@ -29,10 +37,11 @@ struct WfBuf {                          // path slots, structure of arrays; n = 
     double *lres;                       // n: complete Light::pdf impact of the ray in flight (analytic lights + emissive triangles)
     uint32_t *live[2];                  // n each: compacted indices of slots with work
     uint32_t *n_live;                   // [4]: per list, entries filled from the front / from the back (8-byte aligned pairs)
-    uint32_t *cursor;                   // trace kernel's fetch position in the live list
+    uint32_t *cursor;                   // trace kernel's fetch position in the live list (= n_live + 4: one memset clears list 1, cursor and n_x)
     uint32_t batch;                     // planes added to the image per k_wf_sum pass (amortises the read-modify-write)
-    uint32_t n_slots, ring, reserve;    // slots in use (<= n), planes in the ring of finished samples, planes kept free for claim overshoot
+    uint32_t ring;                      // planes in the ring of finished samples
     uint32_t n_px_cap;                  // pixels the side planes were allocated for (width * height)
+    WfCall *call;                       // device: the parameters of the render call in flight (written by k_wf_init)
     uint32_t *pix, *ord;                // n: pixel (index in the image) / ordinal (in the region's tile order) a slot works on
     double *side;                       // ring * 3 * n: radiance of finished samples: plane (sample % ring), component, ordinal
     unsigned long long *item;           // [0] next unclaimed item, [1] claim limit, [2] items of this call
@@ -49,9 +58,29 @@ inline uint64_t wf_slots_for(uint64_t n_px) {
     return twice < most ? twice : most;
 }
 int wf_trace_blocks(int device);
-cudaError_t launch_render_wavefront(cudaStream_t st, const DScene &sc, uint32_t sample_begin, uint32_t sample_count,
-                                    uint64_t seed, double *accum, DCounters *ctr, const WfBuf &b, volatile uint32_t *host_live,
-                                    cudaEvent_t ev, int trace_blocks, uint64_t *launches, DRegion rg);
+// Host state a context keeps between render calls: the forked stream, the events and the
+// instantiated graph of four iterations, re-captured only when a kernel argument changes (another
+// scene, other buffers).
+struct WfRuntime {
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_shade = nullptr, ev_join = nullptr, ev_poll = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    bool tried_graph = false;           // capture failed once for this key: plain launches from then on
+    DScene key_sc{};                    // the arguments the graph was captured with
+    WfBuf key_b{};
+    double *key_accum = nullptr;
+    DCounters *key_ctr = nullptr;
+    int key_blocks = 0;
+    volatile uint32_t *host_live = nullptr;     // pinned, 4 words: what the host polls
+    uint64_t slots_override = 0;        // RT_WF_SLOTS (experiments), read once at rt_create
+    uint64_t graph_builds = 0;          // diagnostics: how often the graph was (re)instantiated
+};
+cudaError_t wf_runtime_init(WfRuntime &rt);
+void wf_runtime_destroy(WfRuntime &rt);
+cudaError_t launch_render_wavefront(cudaStream_t st, WfRuntime &rt, const DScene &sc, uint32_t sample_begin, uint32_t sample_count,
+                                    uint64_t seed, double *accum, DCounters *ctr, const WfBuf &b, int trace_blocks,
+                                    uint64_t *launches, DRegion rg);
 
 cudaError_t launch_postprocess(cudaStream_t st, uint64_t n, const double *accum, uint32_t samples, double *rgb);
 cudaError_t launch_rng_probe(cudaStream_t st, uint64_t seed, uint32_t pixel, uint32_t sample, uint64_t n,

@@ -29,7 +29,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
-#include <cstdlib>
+#include <cstring>
 
 #include "../../include/rt_b200.h"
 #include "fast.cuh"
@@ -90,17 +90,19 @@ RT_D uint32_t region_tile_pixel(const DRegion &rg, uint32_t width, uint32_t i) {
     const uint32_t tx = r / (8u * ht), l = r - tx * 8u * ht, wt = min(8u, rg.w - 8u * tx);
     return (rg.y0 + 4u * ty + l / wt) * width + rg.x0 + 8u * tx + l % wt;
 }
-__global__ void k_wf_init(WfBuf b, uint32_t n_px, uint32_t sample_count) {
+__global__ void k_wf_init(WfBuf b, WfCall cl, uint32_t sample_count) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < b.n_slots) {
+    const uint32_t n_px = cl.n_px;
+    if (i < cl.n_slots) {
         b.flags[i] = 0;
         b.sample[i] = 0;
         b.live[0][i] = i;                               // the static list of all slots (k_wf_confirm)
     }
     if (i == 0) {
-        b.n_live[0] = b.n_slots; b.n_live[1] = 0; b.n_live[2] = 0; b.n_live[3] = 0;
+        *b.call = cl;                                   // what the kernels of this call read instead of arguments
+        b.n_live[0] = cl.n_slots; b.n_live[1] = 0; b.n_live[2] = 0; b.n_live[3] = 0;
         b.cursor[0] = 0; b.cursor[1] = 0;
-        const unsigned long long total = (unsigned long long)n_px * sample_count, first = (unsigned long long)(b.ring - b.reserve) * n_px;
+        const unsigned long long total = (unsigned long long)n_px * sample_count, first = (unsigned long long)(b.ring - cl.reserve) * n_px;
         b.item[0] = 0; b.item[1] = first < total ? first : total; b.item[2] = total;
         b.plane[0] = 0; b.plane[1] = 0xFFFFFFFFu; b.plane[2] = b.ring; b.plane[3] = 0;
     }
@@ -243,14 +245,17 @@ __global__ void __launch_bounds__(128, WF_CONFIRM_MINB) k_wf_confirm(DScene sc, 
 #define WF_SHADE_MINB 6        // glTF variant: 80 registers, no spills to speak of; measured 4 / 5 / 6 / 7 / 8 -> 1240 / 1270 / 1282 / 1276 / 1275 Mseg/s
 #endif
 template <bool SHAPES>
-__global__ void __launch_bounds__(128, SHAPES ? 4 : WF_SHADE_MINB) k_wf_shade(DScene sc, WfBuf b, DRegion rg, uint32_t sample_begin,
-                                                  unsigned long long seed, DCounters *ctr) {
+__global__ void __launch_bounds__(128, SHAPES ? 4 : WF_SHADE_MINB) k_wf_shade(DScene sc, WfBuf b, DCounters *ctr) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t N = b.n, n_px = rg.w * rg.h;
+    const WfCall cl = *b.call;                          // uniform: one broadcast load
+    const DRegion rg = cl.rg;
+    const uint32_t sample_begin = cl.sample_begin;
+    const unsigned long long seed = cl.seed;
+    const uint32_t N = b.n, n_px = cl.n_px;
     const int lane = threadIdx.x & 31;
     uint32_t *__restrict__ next_live = b.live[1];
     Cnt c;
-    bool keep = false, fresh = false, in_range = i < b.n_slots, want = false, alive = false, defer = false, pend_light = false;
+    bool keep = false, fresh = false, in_range = i < cl.n_slots, want = false, alive = false, defer = false, pend_light = false;
     const uint32_t slot = i;                            // slots are walked in index order; which PIXEL a slot works on changes
     uint32_t smp = 0, pix = 0, ord = 0, left = 0;
     Rng rng;
@@ -430,7 +435,8 @@ __global__ void __launch_bounds__(128, SHAPES ? 4 : WF_SHADE_MINB) k_wf_shade(DS
 // accumulation buffer one after the other, sample 0 first (main.rs:100-103).
 // k_wf_plan (one thread, after the shade kernel): planes [summed, upto) are complete — fully
 // claimed and older than the oldest sample still in flight — and the claim limit moves on.
-__global__ void k_wf_plan(WfBuf b, uint32_t n_px) {
+__global__ void k_wf_plan(WfBuf b) {
+    const uint32_t n_px = b.call->n_px, reserve = b.call->reserve;
     const uint32_t summed = b.plane[3];                 // the sum kernel of the last iteration has run
     b.plane[0] = summed;
     const unsigned long long total = b.item[2], next = min(b.item[0], total);
@@ -443,13 +449,15 @@ __global__ void k_wf_plan(WfBuf b, uint32_t n_px) {
     if (upto < summed) upto = summed;
     b.plane[3] = upto;
     // b.reserve planes of the ring stay free: the claims of one launch can pass the limit by one item per slot
-    const unsigned long long limit = ((unsigned long long)upto + b.ring - b.reserve) * n_px;
+    const unsigned long long limit = ((unsigned long long)upto + b.ring - reserve) * n_px;
     b.item[1] = limit < total ? limit : total;
     b.plane[1] = 0xFFFFFFFFu;
 }
-__global__ void __launch_bounds__(256) k_wf_sum(WfBuf b, DRegion rg, uint32_t width, double *__restrict__ accum) {
-    const uint32_t from = b.plane[0], upto = b.plane[3], n_px = rg.w * rg.h;
+__global__ void __launch_bounds__(256) k_wf_sum(WfBuf b, uint32_t width, double *__restrict__ accum) {
+    const uint32_t from = b.plane[0], upto = b.plane[3];
     if (upto <= from) return;
+    const DRegion rg = b.call->rg;
+    const uint32_t n_px = b.call->n_px;
     for (uint32_t od = blockIdx.x * blockDim.x + threadIdx.x; od < n_px; od += gridDim.x * blockDim.x) {
         const size_t p = (size_t)region_tile_pixel(rg, width, od) * 3;
         double ax = accum[p], ay = accum[p + 1], az = accum[p + 2];
@@ -531,7 +539,11 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
     __syncthreads();
 #endif
     bool has = false, drained = false, closest = true, want_light = false;
-    uint32_t slot = 0, nc = 0, nl = 0, over = 0, tri_i = 0, tri_end = 0;
+    uint32_t nc = 0, nl = 0, over = 0, tri_i = 0, tri_end = 0;
+    // per-lane values that are written at refill and read only when a candidate is stored or the ray
+    // is published live in shared memory, not in registers (the kernel runs at 64 registers, 8 blocks per SM)
+    __shared__ uint32_t s_slot[128];
+#define slot s_slot[threadIdx.x]
 #if WF_COUNT
     uint32_t n_inner = 0, n_tri = 0, n_cand = 0, n_over = 0;
 #define WF_INC(X) ++X;
@@ -543,7 +555,9 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
     // memory (48 B per thread) instead of 12 registers, which buys one more resident block per SM
     __shared__ double s_ray[6][128];
     double *const my_ray = &s_ray[0][threadIdx.x];
-    float dl1g = 0.0f, tmax = inf, cur_t = 0.0f;     // cur_t: conservative entry distance of `cur`
+    float tmax = inf, cur_t = 0.0f;     // cur_t: conservative entry distance of `cur`
+    __shared__ float s_wpad[128];                    // fast_wpad of the lane's ray (only the triangle pre-test reads it)
+
     int32_t cur = kFastEmpty;
     int sp = 0;
     uint2 stk[kFastStack];                  // (child code, entry distance bits): one 8-byte local access per push / pop
@@ -595,19 +609,28 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
                 if (!has) {
                     const uint32_t idx = base + __popc(idle & ((1u << lane) - 1u));
                     if (idx < n) {
-                        slot = ll.at(idx);
-                        const d3 o = ld_soa(b.ro, N, slot), dd = ld_soa(b.rd, N, slot);
+                        const uint32_t slot_new = ll.at(idx);
+                        slot = slot_new;
+                        const d3 o = ld_soa(b.ro, N, slot_new), dd = ld_soa(b.rd, N, slot_new);
                         my_ray[0] = o.x; my_ray[128] = o.y; my_ray[256] = o.z;
                         my_ray[384] = dd.x; my_ray[512] = dd.y; my_ray[640] = dd.z;
                         r = make_fray(o, dd);
-                        dl1g = kGamma * (fabsf(r.dx) + fabsf(r.dy) + fabsf(r.dz));
-                        const uint32_t sid = b.sh_id[slot];
-                        const double st = b.sh_t[slot];
-                        const bool skip = (sid != kNoShape && st != st) || ray_is_nan(o, dd);
+                        const uint32_t sid = b.sh_id[slot_new];
+                        const double st = b.sh_t[slot_new];
+                        bool skip = (sid != kNoShape && st != st) || ray_is_nan(o, dd);
                         tmax = (sid != kNoShape && !skip) ? up_f32(st) : inf;
-                        const uint32_t fl = b.flags[slot];
+                        const uint32_t fl = b.flags[slot_new];
                         want_light = (fl & kFlagPendLight) != 0;
                         nc = 0; nl = 0; over = 0; sp = 0;
+                        const float range_bound = fmaxf(sc.ftris.bound, sc.fltris.bound);
+                        s_wpad[threadIdx.x] = fast_wpad(o, range_bound);
+                        if (!skip && !fast_in_range(o, range_bound)) {
+                            // outside the range of the fp32 arithmetic: both searches go to k_wf_exact
+                            // (the same route as a candidate list that overflowed)
+                            over = kOverflowClosest | kOverflowLight;
+                            want_light = false;
+                            skip = true;
+                        }
                         closest = true;
                         cur = skip ? kFastEmpty : sc.ftris.root; cur_t = 0.0f;
                         WF_ENTER_LEAF()
@@ -663,10 +686,16 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
             const FTri *tris = closest ? sc.ftris.tris : sc.fltris.tris;
             const DTriI *xtris = closest ? sc.tri_i : sc.ltri_i;
             const d3 o = mk3(my_ray[0], my_ray[128], my_ray[256]), dd = mk3(my_ray[384], my_ray[512], my_ray[640]);
+            const float wpad = s_wpad[threadIdx.x];
+            // the fp32 direction and its error scale are recomputed from the f64 ray in shared memory:
+            // three conversions per leaf are cheaper than four registers held through the INNER steps
+            F3 rd;
+            rd.dx = __double2float_rn(dd.x); rd.dy = __double2float_rn(dd.y); rd.dz = __double2float_rn(dd.z);
+            const float dl1g = kGamma * (fabsf(rd.dx) + fabsf(rd.dy) + fabsf(rd.dz));
             do {
                 WF_INC(n_tri)
                 float tlo, thi;
-                const int cls = tri_classify(tris + tri_i, xtris + tri_i, r, o, dd, cur_t, dl1g, tmax, tlo, thi);
+                const int cls = tri_classify(tris + tri_i, xtris + tri_i, rd, o, dd, cur_t, dl1g, wpad, tmax, tlo, thi);
                 if (cls != 0) {
                     WF_INC(n_cand)
                     if (closest) {
@@ -687,6 +716,7 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
             WF_POP()
         }
     }
+#undef slot
 #undef WF_ENTER_LEAF
 #undef WF_POP
 #undef WF_INC
@@ -713,114 +743,137 @@ int wf_trace_blocks(int device) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wf_trace, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
     return sms * per_sm;
 }
-static inline unsigned long long total_items_of(uint32_t n_px, uint32_t samples) { return (unsigned long long)n_px * samples; }
-cudaError_t launch_render_wavefront(cudaStream_t st, const DScene &sc, uint32_t sample_begin, uint32_t sample_count,
-                                    uint64_t seed, double *accum, DCounters *ctr, const WfBuf &b_in, volatile uint32_t *host_live,
-                                    cudaEvent_t ev, int trace_blocks, uint64_t *launches, DRegion rg) {
+cudaError_t wf_runtime_init(WfRuntime &rt) {
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&rt.side, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    cudaEvent_t *evs[4] = {&rt.ev_fork, &rt.ev_shade, &rt.ev_join, &rt.ev_poll};
+    for (cudaEvent_t *ev : evs)
+        if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+    uint32_t *host = nullptr;
+    if ((e = cudaHostAlloc((void **)&host, 4 * sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess) return e;
+    rt.host_live = host;
+    return cudaSuccess;
+}
+static void wf_drop_graph(WfRuntime &rt) {
+    if (rt.exec) cudaGraphExecDestroy(rt.exec);
+    if (rt.graph) cudaGraphDestroy(rt.graph);
+    rt.exec = nullptr; rt.graph = nullptr; rt.tried_graph = false;
+}
+void wf_runtime_destroy(WfRuntime &rt) {
+    wf_drop_graph(rt);
+    if (rt.side) { cudaStreamSynchronize(rt.side); cudaStreamDestroy(rt.side); }
+    cudaEvent_t evs[4] = {rt.ev_fork, rt.ev_shade, rt.ev_join, rt.ev_poll};
+    for (cudaEvent_t ev : evs) if (ev) cudaEventDestroy(ev);
+    if (rt.host_live) cudaFreeHost((void *)rt.host_live);
+    rt = WfRuntime{};
+}
+
+constexpr int kGraphIters = 4;              // iterations per graph launch
+constexpr int kLaunchesPerIter = 6;         // confirm, exact, shade, plan, sum, trace
+
+cudaError_t launch_render_wavefront(cudaStream_t st, WfRuntime &rt, const DScene &sc, uint32_t sample_begin, uint32_t sample_count,
+                                    uint64_t seed, double *accum, DCounters *ctr, const WfBuf &b, int trace_blocks,
+                                    uint64_t *launches, DRegion rg) {
     const uint32_t n_px = rg.w * rg.h;
-    WfBuf b = b_in;
+    const unsigned long long total_items = (unsigned long long)n_px * sample_count;
     // Slots are independent of pixels: all of the buffer's capacity is used, but never more than
     // (ring - 4) planes' worth — the claims of one launch can pass the limit by one item per slot,
     // and that many planes of the ring are kept free for it (reserve).
     unsigned long long want_slots = wf_slots_for(n_px) < b.n ? wf_slots_for(n_px) : b.n;
-    if (const char *e = std::getenv("RT_WF_SLOTS")) {  // experiments
-        const long long v = std::atoll(e);
-        if (v >= 1024 && (unsigned long long)v < want_slots) want_slots = (unsigned long long)v;
-    }
+    if (rt.slots_override >= 1024 && rt.slots_override < want_slots) want_slots = rt.slots_override;
     const unsigned long long most = (unsigned long long)(b.ring - 4u) * n_px;
     if (want_slots > most) want_slots = most;
-    if (want_slots > total_items_of(n_px, sample_count)) want_slots = total_items_of(n_px, sample_count);
+    if (want_slots > total_items) want_slots = total_items;
     if (want_slots < 1) want_slots = 1;
-    b.n_slots = (uint32_t)want_slots;
-    b.reserve = (uint32_t)((want_slots + n_px - 1) / n_px) + 1u;
-    const unsigned blocks = (b.n_slots + 127) / 128;
-    const unsigned long long total_items = (unsigned long long)n_px * sample_count;
-    k_wf_init<<<blocks, 128, 0, st>>>(b, n_px, sample_count);
+    WfCall cl{};
+    cl.sample_begin = sample_begin;
+    cl.n_slots = (uint32_t)want_slots;
+    cl.reserve = (uint32_t)((want_slots + n_px - 1) / n_px) + 1u;
+    cl.n_px = n_px;
+    cl.seed = seed;
+    cl.rg = rg;
+    // The grids cover the buffer's CAPACITY (threads past n_slots leave at once), so the launch
+    // configuration does not depend on the call either.
+    const unsigned blocks = (b.n + 127) / 128;
+    k_wf_init<<<(cl.n_slots + 127) / 128, 128, 0, st>>>(b, cl, sample_count);
     ++*launches;
     // a segment takes one iteration, two when it is deferred to k_wf_exact; an item can wait for
     // a free plane of the ring: generous bound, reaching it is reported as an error
-    const uint64_t max_iters = 4 * ((uint64_t)sample_count * n_px / b.n_slots + 1) * (sc.ray_depth ? sc.ray_depth : 1) + 64;
-    bool poll_pending = false, finished = false;
+    const uint64_t max_iters = 4 * ((uint64_t)sample_count * n_px / cl.n_slots + 1) * (sc.ray_depth ? sc.ray_depth : 1) + 64;
     // scenes without planes / boxes / ellipsoids (every glTF scene) run the kernel compiled without them
     const bool shapes = sc.n_planes || sc.boxes.n_prims || sc.ellipsoids.n_prims || sc.lboxes.n_prims || sc.lellipsoids.n_prims;
-    const unsigned sum_blocks = (unsigned)std::min<uint64_t>((n_px + 255) / 256, 148 * 8);
-    cudaStream_t side = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_plan = nullptr, ev_join = nullptr;
-    if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ev_plan, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess) {
-        const cudaError_t e = cudaGetLastError();
-        if (side) cudaStreamDestroy(side);
-        if (ev_fork) cudaEventDestroy(ev_fork);
-        if (ev_plan) cudaEventDestroy(ev_plan);
-        return e != cudaSuccess ? e : cudaErrorUnknown;
-    }
-    // One iteration: confirm -> shade -> trace on the main stream; on a forked branch k_wf_exact
-    // (after confirm) and k_wf_sum (after the one-thread k_wf_plan that follows shade), joined
-    // before the next iteration.  Four iterations are captured ONCE into a CUDA graph and
-    // replayed: the inner loop is launch-bound on small images and at the end of every render.
+    const unsigned sum_blocks = (unsigned)std::min<uint64_t>(((uint64_t)b.n_px_cap + 255) / 256, 148 * 8);
+    // One iteration: confirm -> shade -> trace on the main stream; on the forked stream k_wf_exact
+    // (after confirm) and the one-thread k_wf_plan + k_wf_sum (after shade, next to the trace
+    // kernel), joined before the next iteration.  Four iterations are captured ONCE per (scene,
+    // buffers) into a CUDA graph and replayed by every call: the inner loop is launch-bound on small
+    // images and at the end of every render.
     auto issue_iteration = [&]() {
-        cudaMemsetAsync(&b.n_live[2], 0, 2 * sizeof(uint32_t), st);         // the trace list starts empty
-        cudaMemsetAsync(b.cursor, 0, 2 * sizeof(uint32_t), st);              // trace fetch position, deferred-slot count (cursor[1])
+        cudaMemsetAsync(&b.n_live[2], 0, 4 * sizeof(uint32_t), st);         // the trace list starts empty; trace fetch position; deferred-slot count
         k_wf_confirm<<<blocks, 128, 0, st>>>(sc, b, 0, ctr);
-        cudaEventRecord(ev_fork, st);
-        cudaStreamWaitEvent(side, ev_fork, 0);
-        k_wf_exact<<<64, 128, 0, side>>>(sc, b);
-        if (shapes) k_wf_shade<true><<<blocks, 128, 0, st>>>(sc, b, rg, sample_begin, seed, ctr);
-        else k_wf_shade<false><<<blocks, 128, 0, st>>>(sc, b, rg, sample_begin, seed, ctr);
-        k_wf_plan<<<1, 1, 0, st>>>(b, n_px);
-        cudaEventRecord(ev_plan, st);
-        cudaStreamWaitEvent(side, ev_plan, 0);
-        k_wf_sum<<<sum_blocks, 256, 0, side>>>(b, rg, sc.width, accum);
-        cudaEventRecord(ev_join, side);
+        cudaEventRecord(rt.ev_fork, st);
+        cudaStreamWaitEvent(rt.side, rt.ev_fork, 0);
+        k_wf_exact<<<64, 128, 0, rt.side>>>(sc, b);
+        if (shapes) k_wf_shade<true><<<blocks, 128, 0, st>>>(sc, b, ctr);
+        else k_wf_shade<false><<<blocks, 128, 0, st>>>(sc, b, ctr);
+        cudaEventRecord(rt.ev_shade, st);
+        cudaStreamWaitEvent(rt.side, rt.ev_shade, 0);
+        k_wf_plan<<<1, 1, 0, rt.side>>>(b);
+        k_wf_sum<<<sum_blocks, 256, 0, rt.side>>>(b, sc.width, accum);
+        cudaEventRecord(rt.ev_join, rt.side);
         k_wf_trace<<<trace_blocks, 128, 0, st>>>(sc, b, 1, ctr);
-        cudaStreamWaitEvent(st, ev_join, 0);
+        cudaStreamWaitEvent(st, rt.ev_join, 0);
     };
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t exec = nullptr;
-    bool use_graph = false;
-    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-        for (int k = 0; k < 4; ++k) issue_iteration();
-        if (cudaStreamEndCapture(st, &graph) == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) use_graph = true;
+    const bool same_key = rt.tried_graph && std::memcmp(&rt.key_sc, &sc, sizeof sc) == 0 && std::memcmp(&rt.key_b, &b, sizeof b) == 0 &&
+                          rt.key_accum == accum && rt.key_ctr == ctr && rt.key_blocks == trace_blocks;
+    if (!same_key) {
+        wf_drop_graph(rt);
+        std::memcpy(&rt.key_sc, &sc, sizeof sc);
+        std::memcpy(&rt.key_b, &b, sizeof b);
+        rt.key_accum = accum; rt.key_ctr = ctr; rt.key_blocks = trace_blocks;
+        rt.tried_graph = true;
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            for (int k = 0; k < kGraphIters; ++k) issue_iteration();
+            if (cudaStreamEndCapture(st, &rt.graph) != cudaSuccess) rt.graph = nullptr;
+            if (rt.graph && cudaGraphInstantiate(&rt.exec, rt.graph, 0) != cudaSuccess) rt.exec = nullptr;
+        }
+        if (rt.exec) ++rt.graph_builds;
+        else cudaGetLastError();                    // plain launches from now on (same kernels, same order)
     }
-    if (!use_graph) cudaGetLastError();             // fall back to plain launches (same kernels, same order)
+    const bool use_graph = rt.exec != nullptr;
+    volatile uint32_t *host_live = rt.host_live;
+    bool poll_pending = false, finished = false;
     cudaError_t result = cudaSuccess;
-    for (uint64_t it = 0; it < max_iters; it += 4) {
+    for (uint64_t it = 0; it < max_iters; it += kGraphIters) {
         if (use_graph) {
-            result = cudaGraphLaunch(exec, st);
+            result = cudaGraphLaunch(rt.exec, st);
             if (result != cudaSuccess) break;
         } else {
-            for (int k = 0; k < 4; ++k) issue_iteration();
+            for (int k = 0; k < kGraphIters; ++k) issue_iteration();
         }
-        *launches += 24;
+        *launches += kGraphIters * kLaunchesPerIter;
         // poll the state after the PREVIOUS group of four without stalling the stream: nothing in
         // flight and nothing left to claim means the call is done
         if (poll_pending) {
-            result = cudaEventSynchronize(ev);
+            result = cudaEventSynchronize(rt.ev_poll);
             if (result != cudaSuccess) break;
             const unsigned long long next = (unsigned long long)host_live[2] | ((unsigned long long)host_live[3] << 32);
             if (host_live[0] + host_live[1] == 0 && next >= total_items) { finished = true; break; }
         }
         cudaMemcpyAsync((void *)host_live, &b.n_live[2], 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
         cudaMemcpyAsync((void *)(host_live + 2), b.item, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
-        cudaEventRecord(ev, st);
+        cudaEventRecord(rt.ev_poll, st);
         poll_pending = true;
     }
     if (result == cudaSuccess) {
         // the planes completed by the last iterations (k_wf_plan sees no path in flight and nothing
         // left to claim, so everything that remains goes)
-        k_wf_plan<<<1, 1, 0, st>>>(b, n_px);
-        k_wf_sum<<<sum_blocks, 256, 0, st>>>(b, rg, sc.width, accum);
-        k_wf_plan<<<1, 1, 0, st>>>(b, n_px);
-        k_wf_sum<<<sum_blocks, 256, 0, st>>>(b, rg, sc.width, accum);
+        for (int k = 0; k < 2; ++k) {
+            k_wf_plan<<<1, 1, 0, st>>>(b);
+            k_wf_sum<<<sum_blocks, 256, 0, st>>>(b, sc.width, accum);
+        }
         *launches += 4;
     }
-    cudaStreamSynchronize(side);                    // (already joined into st; makes the destroy below trivially safe)
-    cudaEventDestroy(ev_fork);
-    cudaEventDestroy(ev_plan);
-    cudaEventDestroy(ev_join);
-    cudaStreamDestroy(side);
-    if (exec) cudaGraphExecDestroy(exec);
-    if (graph) cudaGraphDestroy(graph);
     if (result != cudaSuccess) return result;
     if (!finished) return cudaErrorLaunchTimeout;   // iteration bound reached with work left: never a silent partial image
     return cudaGetLastError();

@@ -12,6 +12,13 @@
  *   - all host pointers are caller-owned and never retained past the call that received them.
  *   - all arithmetic the reference does in f64 (src/types.rs:5) is exposed as double.
  *   - there is NO CPU fallback for rendering: rt_create fails when no CUDA device is present.
+ *
+ * Threading
+ *   - calls on ONE rt_ctx (or one rt_group) are serialised by the caller; different contexts may
+ *     be driven from different threads at the same time (one host thread per GPU).
+ *   - an rt_scene is immutable once built: any number of contexts may upload the same scene
+ *     concurrently (the flattened, page-locked image is built once, under std::call_once).
+ *   - rt_last_error(NULL) is thread-local.
  */
 #ifndef RT_B200_H
 #define RT_B200_H
@@ -33,7 +40,8 @@ typedef enum rt_status {
     RT_ERR_IO = 4,
     RT_ERR_PARSE = 5,       /* scene text / glTF rejected (the reference would panic here)    */
     RT_ERR_NO_SCENE = 6,
-    RT_ERR_LIMIT = 7        /* BVH deeper than the traversal stack, too many planes, ...      */
+    RT_ERR_LIMIT = 7,       /* out of memory, too many primitives for 32-bit indices, ...     */
+    RT_ERR_COMM = 8         /* NCCL missing or a collective failed (multi-GPU calls only)     */
 } rt_status;
 
 /* ---- scene description (what the reference holds in parsed_scene::Scene / glTF Model) ------- */
@@ -295,6 +303,50 @@ typedef struct rt_counters {
 } rt_counters;
 RT_API int rt_get_counters(rt_ctx *ctx, rt_counters *out);      /* syncs the stream */
 RT_API int rt_reset_counters(rt_ctx *ctx);
+
+/* ---- multi-GPU (the reference has one rayon pool, src/main.rs:94) --------------
+ * The image is partitioned by SAMPLE RANGES: device r of N renders the block
+ * rt_shard_sample_range(r, N, samples, 0) of global sample indices of every pixel (paths are keyed
+ * by pixel and GLOBAL sample, so the union is the one-GPU job), the f64 accumulation buffers are
+ * sum-reduced to the root with ONE ncclReduce over NVLink before the non-linear tonemap
+ * (src/main.rs:104), and only the root postprocesses.  NCCL is loaded at run time (libnccl.so.2);
+ * without it these calls return RT_ERR_COMM and everything single-GPU still works. */
+
+/* Contiguous block partition of [first_sample, first_sample + total_samples): sizes differ by at
+ * most one, earlier ranks take the larger blocks. */
+RT_API int rt_shard_sample_range(int rank, int world, uint32_t total_samples, uint32_t first_sample,
+                                 uint32_t *begin, uint32_t *count);
+
+/* One process per GPU (torchrun / MPI launchers): rank 0 creates the id, the launcher broadcasts
+ * its RT_COMM_ID_BYTES bytes, every rank joins with its own context (ncclCommInitRank on the
+ * context's device; collective: all ranks must call it). */
+#define RT_COMM_ID_BYTES 128
+RT_API int rt_comm_unique_id(void *id128);
+RT_API int rt_comm_init(rt_ctx *ctx, const void *id128, int rank, int world);
+RT_API int rt_comm_info(const rt_ctx *ctx, int *rank, int *world, int *nccl_version);   /* any may be NULL */
+/* accum(root) = sum over ranks of accum (in place, f64), enqueued on the context's stream after the
+ * render kernels; follow it with rt_postprocess on the root.  Collective.  A context without a
+ * communicator is a world of one: a no-op. */
+RT_API int rt_reduce_accum(rt_ctx *ctx, int root);
+
+/* One process, several GPUs (what the CLI uses): n_devices <= 0 takes every visible device.
+ * Device device_ids[0] is the root.  One host thread per device drives the render calls. */
+typedef struct rt_group rt_group;
+RT_API int  rt_group_create(int n_devices, const int *device_ids, rt_group **out);
+RT_API void rt_group_destroy(rt_group *group);
+RT_API int  rt_group_size(const rt_group *group, int *n_devices);
+RT_API rt_ctx *rt_group_ctx(rt_group *group, int i);       /* borrowed; i = 0 is the root */
+RT_API const char *rt_group_last_error(const rt_group *group);
+RT_API int  rt_group_upload_scene(rt_group *group, const rt_scene *scene);     /* replicated on every device */
+/* rt_render_accum with the sample range split over the devices (no reduce); params->clear applies
+ * to the root, the other devices always start their share from zero. */
+RT_API int  rt_group_render_accum(rt_group *group, const rt_render_params *params);
+RT_API int  rt_group_reduce_accum(rt_group *group);         /* onto the root, asynchronous */
+/* generate_image on all devices: split, render, reduce, tonemap on the root, copy to the host. */
+RT_API int  rt_group_render(rt_group *group, uint64_t seed, int mode, int sched, double *rgb_out);
+RT_API int  rt_group_render_progressive(rt_group *group, uint64_t seed, int mode, int sched,
+                                        uint32_t chunk_samples, rt_progress_fn progress, void *user,
+                                        double *rgb_out, uint32_t *samples_done);
 
 /* Test hook: the first n u64 draws of the device RNG stream (seed, pixel, sample) and one value
  * of each rand-0.8 distribution used on the path, for parity with the

@@ -34,6 +34,30 @@ def test_sample_range_partitions_exactly():
         sharding.sample_range(2, 2, 10)
 
 
+def test_library_partition_is_the_python_one():
+    """rt_shard_sample_range (what rt_group_* and the CLI use) == sharding.sample_range."""
+    for total in (0, 1, 7, 64, 1024, 0xFFFFFFF0):
+        for world in (1, 2, 3, 4, 8):
+            for r in range(world):
+                assert rtb200.shard_sample_range(r, world, total, 5) == sharding.sample_range(r, world, total, 5)
+    with pytest.raises(rtb200.RtError):
+        rtb200.shard_sample_range(2, 2, 10)
+
+
+def test_multi_gpu_entry_points_fail_cleanly_without_a_device():
+    """No GPU here: the group constructor reports RT_ERR_NO_DEVICE (2), it never falls back to a CPU path;
+    the communicator id comes from NCCL itself (dlopen'ed) or is RT_ERR_COMM (8) when NCCL is absent."""
+    if rtb200.device_count() == 0:
+        with pytest.raises(rtb200.RtError) as e:
+            rtb200.Group()
+        assert e.value.code == 2
+    try:
+        uid = rtb200.comm_unique_id()
+        assert len(uid) == rtb200.COMM_ID_BYTES and any(uid)
+    except rtb200.RtError as e:
+        assert e.code == 8
+
+
 def _worker(rank, world, port, text, total, out_path):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
