@@ -94,6 +94,33 @@ cudaError_t ensure_wavefront(rt_ctx *ctx) {
     return cudaSuccess;
 }
 
+// L2 residency of the fp32 culling structures.  The trace kernel's node and pre-test records
+// (FNode + FTri, contiguous in the arena: 93 MB on the 1 M-triangle scene) are re-read by every ray,
+// while each iteration also streams the whole path state (0.6 GB at 1080p) through the same 126 MB
+// L2.  An access-policy window marks the culling structures `persisting` on both streams (captured
+// kernel nodes inherit the stream's window), as much of them as the device lets persist.
+cudaError_t apply_l2_window(rt_ctx *ctx) {
+    const FBvh &f = ctx->dsc.ftris;
+    if (!ctx->knob_l2_persist_mb || !f.nodes || !ctx->wf_rt.side) return cudaSuccess;
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+    if (max_persist <= 0 || max_window <= 0) return cudaSuccess;
+    const size_t want = std::min<size_t>((size_t)ctx->knob_l2_persist_mb << 20, (size_t)max_persist);
+    cudaError_t e = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+    if (e != cudaSuccess) return e;
+    const char *lo = (const char *)f.nodes, *hi = (const char *)ctx->arena + ctx->arena_used;     // FNode, FTri (scene), then the light set's
+    const size_t bytes = std::min<size_t>((size_t)(hi - lo), (size_t)max_window);
+    cudaStreamAttrValue v{};
+    v.accessPolicyWindow.base_ptr = (void *)lo;
+    v.accessPolicyWindow.num_bytes = bytes;
+    v.accessPolicyWindow.hitRatio = bytes <= want ? 1.0f : (float)((double)want / (double)bytes);
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if ((e = cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &v)) != cudaSuccess) return e;
+    return cudaStreamSetAttribute(ctx->wf_rt.side, cudaStreamAttributeAccessPolicyWindow, &v);
+}
+
 void free_scene(rt_ctx *ctx, bool keep_arena) {
     if (!keep_arena) {
         free_wavefront(ctx);
@@ -137,6 +164,15 @@ std::vector<DNode> flatten_nodes(const std::vector<HostNode> &nodes) {
     }
     return out;
 }
+// parent[i] of every node, for hierarchies deeper than the explicit traversal stack (empty otherwise)
+std::vector<uint32_t> parents_if_deep(const std::vector<HostNode> &nodes, uint32_t depth) {
+    std::vector<uint32_t> out;
+    if (depth <= (uint32_t)kExactStackHost) return out;
+    out.assign(nodes.size(), 0u);
+    for (size_t i = 0; i < nodes.size(); ++i)
+        if (nodes[i].left != RT_NO_CHILD) { out[nodes[i].left] = (uint32_t)i; out[nodes[i].right] = (uint32_t)i; }
+    return out;
+}
 std::vector<DShape> flatten_shapes(const std::vector<HostShape> &v) {
     std::vector<DShape> out(v.size());
     for (size_t i = 0; i < v.size(); ++i) {
@@ -177,8 +213,10 @@ void flatten_tris(const std::vector<HostTri> &v, std::vector<DTriI> &ti, std::ve
 // repeated uploads (one per generate_image call) are plain DMA transfers.
 }  // namespace
 struct rt_device_image {
-    struct ShapeSet { std::vector<DNode> nodes; std::vector<DShape> prims; };
-    struct TriSet { std::vector<DNode> nodes; std::vector<DTriI> ti; std::vector<DTriS> ts; FastHierarchy fh; };
+    // parent: filled only for a hierarchy deeper than the traversal stack (stackless walk, exact.cuh)
+    struct ShapeSet { std::vector<DNode> nodes; std::vector<DShape> prims; std::vector<uint32_t> parent; };
+    struct TriSet { std::vector<DNode> nodes; std::vector<DTriI> ti; std::vector<DTriS> ts; std::vector<uint32_t> parent; FastHierarchy fh; };
+    bool fast_ok = true;                // false: some hierarchy is too deep for the fp32 traversal's stack -> EXACT answers FAST requests
     ShapeSet shapes[4];                 // boxes, ellipsoids, light boxes, light ellipsoids
     std::vector<DShape> planes;
     TriSet tris[2];                     // scene, lights
@@ -201,14 +239,27 @@ std::shared_ptr<rt_device_image> make_image(const HostScene &s) {
     for (int k = 0; k < 4; ++k) {
         im->shapes[k].nodes = flatten_nodes(sh[k]->nodes);
         im->shapes[k].prims = flatten_shapes(sh[k]->prims);
+        im->shapes[k].parent = parents_if_deep(sh[k]->nodes, sh[k]->depth);
+        if (!im->shapes[k].parent.empty()) im->fast_ok = false;
     }
     im->planes = flatten_shapes(s.planes);
     const HostBvh<HostTri> *tr[2] = {&s.tris, &s.light_tris};
     for (int k = 0; k < 2; ++k) {
         im->tris[k].nodes = flatten_nodes(tr[k]->nodes);
         flatten_tris(tr[k]->prims, im->tris[k].ti, im->tris[k].ts);
-        build_fast_hierarchy(*tr[k], im->tris[k].fh);
+        im->tris[k].parent = parents_if_deep(tr[k]->nodes, tr[k]->depth);
+        // The fp32 hierarchy keeps up to three deferred children per 4-wide level on a 64-entry stack: a
+        // chain-like tree overflows it long before the exact walk needs its parent links.  Such a scene
+        // is rendered by the exact traversal (same image bit for bit, rt_render_accum), so the fp32
+        // structure is not built at all — its builder recurses once per level.
+        if (!im->tris[k].parent.empty() || tr[k]->depth + 2 > (uint32_t)kFastStackHost) im->fast_ok = false;
     }
+    for (int k = 0; k < 2 && im->fast_ok; ++k) {
+        build_fast_hierarchy(*tr[k], im->tris[k].fh);
+        if (im->tris[k].fh.depth + 2 > (uint32_t)kFastStackHost) im->fast_ok = false;
+    }
+    if (!im->fast_ok)
+        for (int k = 0; k < 2; ++k) im->tris[k].fh = FastHierarchy{};
     im->mats.resize(s.materials.size());
     for (size_t i = 0; i < im->mats.size(); ++i) {
         DMaterial m{};
@@ -220,9 +271,9 @@ std::shared_ptr<rt_device_image> make_image(const HostScene &s) {
     int ndev = 0;
     const bool cuda_ok = cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0;
     if (!cuda_ok) cudaGetLastError();
-    for (int k = 0; k < 4; ++k) { im->pin(im->shapes[k].nodes); im->pin(im->shapes[k].prims); }
+    for (int k = 0; k < 4; ++k) { im->pin(im->shapes[k].nodes); im->pin(im->shapes[k].prims); im->pin(im->shapes[k].parent); }
     im->pin(im->planes);
-    for (int k = 0; k < 2; ++k) { im->pin(im->tris[k].nodes); im->pin(im->tris[k].ti); im->pin(im->tris[k].ts); im->pin(im->tris[k].fh.nodes); im->pin(im->tris[k].fh.tris); }
+    for (int k = 0; k < 2; ++k) { im->pin(im->tris[k].parent); im->pin(im->tris[k].nodes); im->pin(im->tris[k].ti); im->pin(im->tris[k].ts); im->pin(im->tris[k].fh.nodes); im->pin(im->tris[k].fh.tris); }
     im->pin(im->mats);
     return im;
 }
@@ -237,6 +288,13 @@ int need_scene(rt_ctx *ctx) {
 int check_mode(rt_ctx *ctx, int mode) {
     if (mode != RT_MODE_EXACT && mode != RT_MODE_FAST) return set_err(ctx, RT_ERR_INVALID_ARG, "unknown mode");
     return RT_OK;
+}
+// FAST gives the EXACT results bit for bit; where its fp32 structures cannot be used — a hierarchy
+// deeper than the fp32 traversal's stack (the reference's sweep SAH has no depth bound,
+// src/bvh.rs:93-111), coordinates beyond the fp32 range (fast.cuh, kFastRange) — the exact traversal
+// answers the request instead of an error.
+bool fast_usable(const rt_ctx *ctx) {
+    return ctx->fast_ok && (ctx->dsc.tris.n_prims == 0 || ctx->dsc.ftris.bound <= kFastRange);
 }
 
 struct DevBuf {                         // scoped device allocation for the array-in / array-out calls
@@ -521,6 +579,7 @@ int rt_create(int device_id, rt_ctx **out) {
     // k_wf_plan only moves on when `batch` planes are complete, and at most ring - reserve (reserve <= 4)
     // planes are ever open: a larger batch would never be reached
     if (ctx->knob_batch > ctx->knob_ring - 4u) ctx->knob_batch = ctx->knob_ring - 4u;
+    if (const char *e = std::getenv("RT_WF_L2PERSIST")) { const int v = std::atoi(e); if (v >= 0 && v <= 4096) ctx->knob_l2_persist_mb = (uint32_t)v; }
     if (const char *e = std::getenv("RT_WF_SLOTS")) { const long long v = std::atoll(e); if (v >= 1024) ctx->wf_rt.slots_override = (uint64_t)v; }
     *out = ctx.release();
     return RT_OK;
@@ -541,10 +600,6 @@ const char *rt_last_error(const rt_ctx *ctx) { return ctx ? ctx->err.c_str() : g
 int rt_upload_scene(rt_ctx *ctx, const rt_scene *scene) {
     if (!ctx || !scene) return set_err(ctx, RT_ERR_INVALID_ARG, "null argument");
     const HostScene &s = scene->s;
-    const uint32_t depths[6] = {s.boxes.depth, s.ellipsoids.depth, s.tris.depth, s.light_boxes.depth, s.light_ellipsoids.depth, s.light_tris.depth};
-    for (uint32_t d : depths)
-        if (d > (uint32_t)kExactStackHost)
-            return set_err(ctx, RT_ERR_LIMIT, "BVH depth " + std::to_string(d) + " exceeds the traversal stack (" + std::to_string(kExactStackHost) + ")");
     return guarded(ctx, RT_ERR_INVALID_ARG, [&]() -> int {
         CK(ctx, cudaSetDevice(ctx->device));
         // built once per scene, whichever context (thread) uploads first: one host thread per GPU may
@@ -552,9 +607,6 @@ int rt_upload_scene(rt_ctx *ctx, const rt_scene *scene) {
         std::call_once(scene->image_once, [&]() { scene->image = make_image(s); });
         if (!scene->image) return set_err(ctx, RT_ERR_LIMIT, "the flattened scene image could not be built");
         const rt_device_image &im = *scene->image;
-        for (int k = 0; k < 2; ++k)
-            if (im.tris[k].fh.depth + 2 > (uint32_t)kFastStackHost)
-                return set_err(ctx, RT_ERR_LIMIT, "fp32 hierarchy depth " + std::to_string(im.tris[k].fh.depth) + " exceeds the traversal stack");
         CK(ctx, cudaStreamSynchronize(ctx->stream));
         const size_t n_px = (size_t)s.width * s.height;
         const bool keep = ctx->arena_cap >= im.total_bytes && ctx->n_px == n_px;
@@ -572,6 +624,7 @@ int rt_upload_scene(rt_ctx *ctx, const rt_scene *scene) {
         for (int k = 0; k < 4; ++k) {
             CK(ctx, upload(ctx, im.shapes[k].nodes, &sb[k]->nodes));
             CK(ctx, upload(ctx, im.shapes[k].prims, sp[k]));
+            CK(ctx, upload(ctx, im.shapes[k].parent, &sb[k]->parent));     // null unless the hierarchy is deeper than the stack
             sb[k]->n_nodes = (uint32_t)im.shapes[k].nodes.size();
             sb[k]->n_prims = (uint32_t)im.shapes[k].prims.size();
         }
@@ -585,6 +638,7 @@ int rt_upload_scene(rt_ctx *ctx, const rt_scene *scene) {
             CK(ctx, upload(ctx, im.tris[k].nodes, &tb[k]->nodes));
             CK(ctx, upload(ctx, im.tris[k].ti, ti[k]));
             CK(ctx, upload(ctx, im.tris[k].ts, ts[k]));
+            CK(ctx, upload(ctx, im.tris[k].parent, &tb[k]->parent));
             tb[k]->n_nodes = (uint32_t)im.tris[k].nodes.size();
             tb[k]->n_prims = (uint32_t)im.tris[k].ti.size();
             CK(ctx, upload(ctx, im.tris[k].fh.nodes, &fb[k]->nodes));
@@ -607,6 +661,8 @@ int rt_upload_scene(rt_ctx *ctx, const rt_scene *scene) {
         CK(ctx, cudaMemsetAsync(ctx->d_accum, 0, n_px * 3 * sizeof(double), ctx->stream));
         CK(ctx, cudaStreamSynchronize(ctx->stream));
         ctx->dsc = d;
+        ctx->fast_ok = im.fast_ok;
+        ctx->l2_window_set = false;
         ctx->samples = s.samples;
         ctx->scene_bytes = ctx->arena_used;
         ctx->has_scene = true;
@@ -631,7 +687,7 @@ int rt_trace_rays(rt_ctx *ctx, int mode, uint64_t n, const double *origins, cons
     CK(ctx, h.alloc(n * sizeof(rt_hit)));
     CK(ctx, cudaMemcpyAsync(o.p, origins, n * 24, cudaMemcpyHostToDevice, ctx->stream));
     CK(ctx, cudaMemcpyAsync(d.p, dirs, n * 24, cudaMemcpyHostToDevice, ctx->stream));
-    CK(ctx, launch_trace_rays(ctx->stream, ctx->dsc, mode, n, (const double *)o.p, (const double *)d.p, h.p, ctx->d_ctr));
+    CK(ctx, launch_trace_rays(ctx->stream, ctx->dsc, (mode == RT_MODE_FAST && !ctx->fast_ok) ? (int)RT_MODE_EXACT : mode, n, (const double *)o.p, (const double *)d.p, h.p, ctx->d_ctr));
     ++ctx->launches;
     CK(ctx, cudaMemcpyAsync(hits, h.p, n * sizeof(rt_hit), cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -643,7 +699,7 @@ int rt_trace_primary(rt_ctx *ctx, int mode, double jx, double jy, rt_hit *hits, 
     DevBuf h, rb;
     if (hits) CK(ctx, h.alloc(ctx->n_px * sizeof(rt_hit)));
     if (rays_out) CK(ctx, rb.alloc(ctx->n_px * 48));
-    CK(ctx, launch_trace_primary(ctx->stream, ctx->dsc, mode, jx, jy, h.p, (double *)rb.p, ctx->d_ctr));
+    CK(ctx, launch_trace_primary(ctx->stream, ctx->dsc, (mode == RT_MODE_FAST && !ctx->fast_ok) ? (int)RT_MODE_EXACT : mode, jx, jy, h.p, (double *)rb.p, ctx->d_ctr));
     ++ctx->launches;
     if (hits) CK(ctx, cudaMemcpyAsync(hits, h.p, ctx->n_px * sizeof(rt_hit), cudaMemcpyDeviceToHost, ctx->stream));
     if (rays_out) CK(ctx, cudaMemcpyAsync(rays_out, rb.p, ctx->n_px * 48, cudaMemcpyDeviceToHost, ctx->stream));
@@ -661,7 +717,7 @@ int rt_light_pdf(rt_ctx *ctx, int mode, uint64_t n, const double *pos, const dou
     CK(ctx, o.alloc(n * 8));
     CK(ctx, cudaMemcpyAsync(p.p, pos, n * 24, cudaMemcpyHostToDevice, ctx->stream));
     CK(ctx, cudaMemcpyAsync(d.p, dir, n * 24, cudaMemcpyHostToDevice, ctx->stream));
-    CK(ctx, launch_light_pdf(ctx->stream, ctx->dsc, mode, n, (const double *)p.p, (const double *)d.p, (double *)o.p, ctx->d_ctr));
+    CK(ctx, launch_light_pdf(ctx->stream, ctx->dsc, (mode == RT_MODE_FAST && !ctx->fast_ok) ? (int)RT_MODE_EXACT : mode, n, (const double *)p.p, (const double *)d.p, (double *)o.p, ctx->d_ctr));
     ++ctx->launches;
     CK(ctx, cudaMemcpyAsync(pdf, o.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -674,9 +730,10 @@ int rt_render_accum(rt_ctx *ctx, const rt_render_params *p) {
     rt_render_params resolved = *p;                     // RT_MODE_AUTO / RT_SCHED_AUTO -> what suits the scene
     const bool has_tris = ctx->dsc.tris.n_prims != 0;
     if (resolved.mode == RT_MODE_AUTO) resolved.mode = has_tris ? RT_MODE_FAST : RT_MODE_EXACT;
-    // A scene whose coordinates leave the range of the fp32 culling arithmetic (fast.cuh, kFastRange)
-    // is rendered by the exact traversal whatever was asked for: same image, bit for bit.
-    if (resolved.mode == RT_MODE_FAST && has_tris && !(ctx->dsc.ftris.bound <= kFastRange)) {
+    // A scene whose coordinates leave the range of the fp32 culling arithmetic (fast.cuh, kFastRange),
+    // or whose hierarchy is too deep for the fp32 traversal's stack, is rendered by the exact
+    // traversal whatever was asked for: same image, bit for bit.
+    if (resolved.mode == RT_MODE_FAST && !fast_usable(ctx)) {
         resolved.mode = RT_MODE_EXACT;
         resolved.sched = RT_SCHED_MEGAKERNEL;
     }
@@ -696,6 +753,7 @@ int rt_render_accum(rt_ctx *ctx, const rt_render_params *p) {
     if (p->sched == RT_SCHED_WAVEFRONT && ctx->dsc.ray_depth > 0) {
         if (p->mode != RT_MODE_FAST) return set_err(ctx, RT_ERR_INVALID_ARG, "the wavefront scheduler runs FAST mode only (EXACT is the megakernel parity anchor)");
         CK(ctx, ensure_wavefront(ctx));
+        if (!ctx->l2_window_set) { CK(ctx, apply_l2_window(ctx)); ctx->l2_window_set = true; }
         CK(ctx, launch_render_wavefront(ctx->stream, ctx->wf_rt, ctx->dsc, p->sample_begin, p->sample_count, p->seed, ctx->d_accum,
                                         ctx->d_ctr, ctx->wf, ctx->wf_blocks, &ctx->launches, rg));
         return RT_OK;

@@ -80,6 +80,8 @@ constexpr uint32_t kFastTopNodes = 85;      // 1 + 4 + 16 + 64: the levels stage
 
 struct DBvh {
     const DNode *nodes;
+    const uint32_t *parent;             // parent[node], uploaded ONLY for hierarchies deeper than the traversal stack
+                                        // (kExactStack): non-null selects the stackless walk of exact.cuh
     uint32_t n_nodes, n_prims;
 };
 

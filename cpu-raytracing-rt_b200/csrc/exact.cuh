@@ -9,7 +9,7 @@
 
 namespace rt {
 
-constexpr int kExactStack = 96;         // checked against the built tree depth at upload time
+constexpr int kExactStack = 96;         // deeper hierarchies are walked without a stack (DBvh::parent, closest_exact_walk<DEEP>)
 constexpr uint32_t kNoChild = 0xFFFFFFFFu;
 #define RT_D __device__ __forceinline__
 
@@ -213,15 +213,25 @@ struct Best {
     double t;
     uint32_t prim;
 };
-template <int KIND>
-RT_D Best closest_exact(const DBvh bvh, const void *prims, d3 o, d3 d, Cnt &c) {
+// DEEP = true is the same walk WITHOUT a stack, for hierarchies deeper than kExactStack (a sweep-SAH
+// tree that peels one primitive per level, reference src/bvh.rs:93-111, has no depth bound): nothing
+// is pushed, and when a subtree is finished the walk climbs parent links (DBvh::parent) and re-derives
+// what the stack would have held.  That is possible because a deferred entry is fully determined by
+// the ray: its distance is the sibling's box distance (the clamp at :161-163 never changes a value
+// that passes `< best`), the sibling is visited second exactly when its distance is below the best
+// hit AT THAT MOMENT (the pop re-check, :170 / :176 — and a sibling that was never pushed because it
+// was not below the older, larger best fails this test too), and which child went first is `tl < tr`
+// (:167, :173).  Two box tests per climbed level replace 12 bytes of stack; they are not counted
+// (the counters report the reference's calls).
+template <int KIND, bool DEEP>
+RT_D Best closest_exact_walk(const DBvh bvh, const void *prims, d3 o, d3 d, Cnt &c) {
     Best best{false, 0.0, 0u};
     if (bvh.n_prims == 0) return best;
     double tt;
     ++c.aabb;
     if (!node_aabb_exact(bvh.nodes, o, d, tt)) return best;
-    uint32_t stack_n[kExactStack];
-    double stack_t[kExactStack];
+    uint32_t stack_n[DEEP ? 1 : kExactStack];
+    double stack_t[DEEP ? 1 : kExactStack];
     int sp = 0;
     uint32_t node = 0;
     for (;;) {
@@ -252,8 +262,8 @@ RT_D Best closest_exact(const DBvh bvh, const void *prims, d3 o, d3 d, Cnt &c) {
             const double right = hr ? (tr < b ? tr : b) : b;
             if (left < b) {
                 if (right < b) {
-                    if (left < right) { stack_n[sp] = r; stack_t[sp] = right; ++sp; node = l; }
-                    else { stack_n[sp] = l; stack_t[sp] = left; ++sp; node = r; }
+                    if (left < right) { if (!DEEP) { stack_n[sp] = r; stack_t[sp] = right; ++sp; } node = l; }
+                    else { if (!DEEP) { stack_n[sp] = l; stack_t[sp] = left; ++sp; } node = r; }
                 } else {
                     node = l;
                 }
@@ -264,13 +274,40 @@ RT_D Best closest_exact(const DBvh bvh, const void *prims, d3 o, d3 d, Cnt &c) {
             }
         }
         if (descended) continue;
-        for (;;) {
-            if (sp == 0) return best;
-            --sp;
-            const double b = best.has ? best.t : dinf();
-            if (stack_t[sp] < b) { node = stack_n[sp]; break; }
+        if (!DEEP) {
+            for (;;) {
+                if (sp == 0) return best;
+                --sp;
+                const double b = best.has ? best.t : dinf();
+                if (stack_t[sp] < b) { node = stack_n[sp]; break; }
+            }
+        } else {
+            for (;;) {                                                      // climb until a pending sibling is found
+                if (node == 0) return best;
+                const uint32_t par = __ldg(bvh.parent + node);
+                const uint32_t l = par + 1, r = load_node_links(bvh.nodes + par).x;
+                double tl, tr;
+                const bool hl = node_aabb_exact(bvh.nodes + l, o, d, tl);
+                const bool hr = node_aabb_exact(bvh.nodes + r, o, d, tr);
+                const bool went_first = !(hl && hr) || node == (tl < tr ? l : r);
+                const bool other_hit = node == l ? hr : hl;
+                const double other_t = node == l ? tr : tl;
+                const uint32_t other = node == l ? r : l;
+                const double b = best.has ? best.t : dinf();
+                if (went_first && other_hit && other_t < b) { node = other; break; }
+                node = par;
+            }
         }
     }
+}
+template <int KIND>
+static __device__ __noinline__ Best closest_exact_deep(const DBvh bvh, const void *prims, d3 o, d3 d, Cnt &c) {
+    return closest_exact_walk<KIND, true>(bvh, prims, o, d, c);
+}
+template <int KIND>
+RT_D Best closest_exact(const DBvh bvh, const void *prims, d3 o, d3 d, Cnt &c) {
+    if (bvh.parent) return closest_exact_deep<KIND>(bvh, prims, o, d, c);      // uniform, cold: trees deeper than the stack
+    return closest_exact_walk<KIND, false>(bvh, prims, o, d, c);
 }
 
 // ---- intersections::intersect, reference src/intersections.rs:42-85 --------------------------
@@ -328,17 +365,24 @@ RT_D SceneHit intersect_exact(const DScene &sc, d3 o, d3 d, Cnt &c) {
 // ---- BVH::intersections / Node::intersections (all hits), reference src/bvh.rs:38-45, :188-210
 // + intersect_lights (src/intersections.rs:87-91) + Light::pdf (src/ray_sampler.rs:132-139)
 // + IntersectionProbability (src/intersection_probability.rs) + to_direction_probability.
-template <int KIND>
-RT_D void light_hits_exact(const DBvh bvh, const void *prims, const DTriS *tri_s, d3 o, d3 d, double &impact, Cnt &c) {
+// DEEP = true: no stack (see closest_exact_walk) — after a left subtree the walk climbs to the parent
+// and enters the right child if the ray touches its box, after a right subtree it keeps climbing.
+template <int KIND, bool DEEP>
+RT_D void light_hits_exact_walk(const DBvh bvh, const void *prims, const DTriS *tri_s, d3 o, d3 d, double &impact, Cnt &c) {
     if (bvh.n_prims == 0) return;
     double tt;
     ++c.laabb;
     if (!node_aabb_exact(bvh.nodes, o, d, tt)) return;
-    uint32_t stack_n[kExactStack];
+    uint32_t stack_n[DEEP ? 1 : kExactStack];
     int sp = 0;
     stack_n[sp++] = 0;
-    while (sp > 0) {
-        const uint32_t node = stack_n[--sp];
+    uint32_t node = 0;
+    for (;;) {
+        if (!DEEP) {
+            if (sp == 0) return;
+            node = stack_n[--sp];
+        }
+        bool descended = false;
         const uint4 links = load_node_links(bvh.nodes + node);
         if (links.x == kNoChild) {
             for (uint32_t i = links.y; i < links.y + links.z; ++i) {
@@ -385,10 +429,34 @@ RT_D void light_hits_exact(const DBvh bvh, const void *prims, const DTriS *tri_s
             c.laabb += 2;
             const bool hl = node_aabb_exact(bvh.nodes + l, o, d, tt);
             const bool hr = node_aabb_exact(bvh.nodes + r, o, d, tt);
-            if (hr) stack_n[sp++] = r;                     // left subtree completes before the right one
-            if (hl) stack_n[sp++] = l;
+            if (!DEEP) {
+                if (hr) stack_n[sp++] = r;                 // left subtree completes before the right one
+                if (hl) stack_n[sp++] = l;
+            } else if (hl || hr) {
+                node = hl ? l : r;
+                descended = true;
+            }
+        }
+        if (DEEP && !descended) {
+            for (;;) {
+                if (node == 0) return;
+                const uint32_t par = __ldg(bvh.parent + node);
+                const uint32_t r = load_node_links(bvh.nodes + par).x;
+                const bool from_left = node == par + 1;
+                node = par;
+                if (from_left && node_aabb_exact(bvh.nodes + r, o, d, tt)) { node = r; break; }
+            }
         }
     }
+}
+template <int KIND>
+static __device__ __noinline__ void light_hits_exact_deep(const DBvh bvh, const void *prims, const DTriS *tri_s, d3 o, d3 d, double &impact, Cnt &c) {
+    light_hits_exact_walk<KIND, true>(bvh, prims, tri_s, o, d, impact, c);
+}
+template <int KIND>
+RT_D void light_hits_exact(const DBvh bvh, const void *prims, const DTriS *tri_s, d3 o, d3 d, double &impact, Cnt &c) {
+    if (bvh.parent) { light_hits_exact_deep<KIND>(bvh, prims, tri_s, o, d, impact, c); return; }
+    light_hits_exact_walk<KIND, false>(bvh, prims, tri_s, o, d, impact, c);
 }
 // o = pos + EPSILON * dir (ray_sampler.rs:133) is formed by the caller
 RT_D double light_pdf_exact(const DScene &sc, d3 o, d3 dir, Cnt &c) {

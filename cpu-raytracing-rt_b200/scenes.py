@@ -252,3 +252,25 @@ def write_heightfield_gltf(path, nx=500, nz=1000, extent_x=100.0, extent_z=200.0
     with open(path, "w") as fh:
         json.dump(doc, fh)
     return n_tris
+
+
+def deep_chain_text(n=130, growth=13.0, width=32, height=24, spp=2, depth=4, lights=True):
+    """A text scene whose triangle hierarchy is a CHAIN: triangle k is `growth` times larger than
+    triangle k-1, so the surface-area cost of the reference's sweep SAH (src/bvh.rs:120-135) is
+    minimised by peeling the largest triangle off at every level (area ratio growth^2 > n) and the
+    tree is about n levels deep — deeper than any fixed traversal stack (SURVEY.md §7 hard part 5).
+    Triangles face the camera at increasing distance; every fourth one emits."""
+    lines = [f"DIMENSIONS {width} {height}", f"SAMPLES {spp}", f"RAY_DEPTH {depth}", "BG_COLOR 0.1 0.2 0.3",
+             "CAMERA_POSITION 0 0 -3", "CAMERA_FOV_X 1.2"]
+    s = 0.5
+    for k in range(n):
+        z = 2.0 * s
+        x0 = -0.3 * s if k % 2 else -0.7 * s
+        lines += ["NEW_PRIMITIVE", f"TRIANGLE {x0!r} {-0.4 * s!r} {z!r} {x0 + s!r} {-0.4 * s!r} {z!r} {x0!r} {0.6 * s!r} {z * 1.25!r}",
+                  f"COLOR {0.3 + 0.5 * (k % 3 == 0)} {0.3 + 0.5 * (k % 3 == 1)} {0.3 + 0.5 * (k % 3 == 2)}"]
+        if lights and k % 4 == 1:
+            lines.append("EMISSION 3 3 3")
+        if k % 5 == 2:
+            lines.append("METALLIC")
+        s *= growth
+    return "\n".join(lines) + "\n"

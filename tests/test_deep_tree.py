@@ -1,0 +1,111 @@
+"""Hierarchies deeper than the traversal stacks (SURVEY.md §7 hard part 5, VERDICT r01 missing #4).
+
+The reference's sweep SAH (src/bvh.rs:75-135) has no depth bound: primitives of geometrically growing
+size are peeled off one per level.  Such a scene used to be refused by rt_upload_scene
+(RT_ERR_LIMIT); now the exact traversal walks it WITHOUT a stack (parent links, exact.cuh
+closest_exact_walk<DEEP>) and FAST requests are answered by it, with the reference's results and the
+reference's numbers of box / primitive tests."""
+import os
+
+import numpy as np
+import pytest
+
+import rtb200
+import rtb200.ctypes_types as T
+from rtb200 import scenes
+from tests import helpers
+
+
+def _deep_pair(orc, tmp_path, **kw):
+    from oracle import loaders
+    path = helpers.write_text(tmp_path, scenes.deep_chain_text(**kw), "deep.txt")
+    return rtb200.Scene.load_text(path), orc.OracleScene(loaders.parse_text_scene(open(path).read()))
+
+
+def test_chain_scene_is_deeper_than_the_stacks_and_matches_the_oracle(orc, tmp_path):
+    prod, oracle = _deep_pair(orc, tmp_path)
+    assert prod.info.bvh_depth[T.BVH_TRIANGLES] > 96        # kExactStack
+    assert prod.info.bvh_prims[T.BVH_LIGHT_TRIANGLES] > 8
+    helpers.assert_scene_equal(prod, oracle)
+
+
+def test_sizes_overflowing_f64_areas_give_one_same_node_leaf(orc, tmp_path):
+    """Area sums overflow to +inf: no split beats the leaf cost (`SameNode`, src/bvh.rs:93-96) and the
+    whole set becomes ONE leaf of 200 triangles — unbounded leaf size, the other half of hard part 5."""
+    prod, oracle = _deep_pair(orc, tmp_path, n=200, growth=16.0)
+    assert prod.info.bvh_nodes[T.BVH_TRIANGLES] == 1 and prod.info.bvh_prims[T.BVH_TRIANGLES] == 200
+    helpers.assert_scene_equal(prod, oracle)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kw", [dict(), dict(n=200, growth=16.0)], ids=["chain127", "one_leaf_200"])
+def test_deep_or_wide_hierarchies_render_like_the_oracle(orc, tmp_path, kw):
+    prod, oracle = _deep_pair(orc, tmp_path, **kw)
+    ctx = rtb200.Context(0).upload(prod)                    # used to fail with RT_ERR_LIMIT
+    try:
+        ctx.reset_counters()
+        g_hits, g_rays = ctx.trace_primary(0.5, 0.5, T.MODE_EXACT, want_rays=True)
+        gc = ctx.counters()
+        c_hits, c_rays, cc = oracle.trace_primary(0.5, 0.5)
+        assert g_rays.tobytes() == c_rays.tobytes()
+        assert helpers.hits_equal(g_hits, c_hits) == 0
+        hit = c_hits["kind"] >= 0
+        assert hit.sum() > 0.2 * len(c_hits) and len(np.unique(c_hits["prim"][hit])) > 3
+        for f in ("t", "geometry_normal", "shading_normal"):
+            assert g_hits[f][hit].tobytes() == c_hits[f][hit].tobytes(), f
+        for k in ("segments", "aabb_tests", "prim_tests"):  # the stackless walk's re-derived box tests are not counted
+            assert gc[k] == cc[k], (k, gc[k], cc[k])
+        # a FAST request is answered by the exact traversal: same bits
+        f_hits, _ = ctx.trace_primary(0.5, 0.5, T.MODE_FAST)
+        assert helpers.hits_equal(f_hits, g_hits) == 0 and f_hits["t"][hit].tobytes() == g_hits["t"][hit].tobytes()
+        # bounce rays + Light::pdf (all-hits walk of the light hierarchy, depth 30: on the stack) and the full render
+        pos = c_rays[hit, :3] + c_rays[hit, 3:] * c_hits["t"][hit, None]
+        ld = oracle.light_sample(5, pos)
+        assert ctx.light_pdf(pos, ld, T.MODE_EXACT).tobytes() == oracle.light_pdf(pos, ld)[0].tobytes()
+        ctx.reset_counters()
+        ctx.render_accum(0, 2, 0xD1E, T.MODE_EXACT, clear=True)
+        got, gc = ctx.accum(), ctx.counters()
+        want, cc = oracle.render_accum(0, 2, 0xD1E)
+        for k in ("segments", "light_pdf_rays", "paths", "aabb_tests", "prim_tests", "light_aabb_tests", "light_prim_tests"):
+            assert gc[k] == cc[k], (k, gc[k], cc[k])
+        err = np.abs(got - want) / np.maximum(np.abs(want), 1e-300)
+        err[got == want] = 0.0
+        assert want.sum() > 0 and err.max() <= 1e-9, err.max()
+        for mode, sched in ((T.MODE_FAST, T.SCHED_WAVEFRONT), (T.MODE_AUTO, T.SCHED_AUTO)):
+            ctx.render_accum(0, 2, 0xD1E, mode, sched, clear=True)
+            assert ctx.accum().tobytes() == got.tobytes()
+    finally:
+        ctx.close()
+
+
+@pytest.mark.gpu
+def test_deep_light_hierarchy_all_hits_walk(orc, tmp_path):
+    """Every triangle emits: the LIGHT hierarchy is the deep one, so Light::pdf's all-hits traversal
+    (src/bvh.rs:188-210) runs stackless too, in the reference's left-then-right order (the sum is
+    order-dependent in the last bits)."""
+    from oracle import loaders
+    text = scenes.deep_chain_text(n=130, growth=13.0).replace("COLOR", "EMISSION 2 2 2\nCOLOR")
+    path = helpers.write_text(tmp_path, text, "deep_lights.txt")
+    prod, oracle = rtb200.Scene.load_text(path), orc.OracleScene(loaders.parse_text_scene(open(path).read()))
+    assert prod.info.bvh_depth[T.BVH_LIGHT_TRIANGLES] > 96
+    ctx = rtb200.Context(0).upload(prod)
+    try:
+        c_hits, c_rays, _ = oracle.trace_primary(0.5, 0.5)
+        hit = c_hits["kind"] >= 0
+        pos = c_rays[hit, :3] + c_rays[hit, 3:] * c_hits["t"][hit, None]
+        ld = oracle.light_sample(3, pos)
+        ctx.reset_counters()
+        g = ctx.light_pdf(pos, ld, T.MODE_EXACT)
+        gc = ctx.counters()
+        c, cc = oracle.light_pdf(pos, ld)
+        assert (c > 0).sum() > 0.2 * len(c)
+        assert g.tobytes() == c.tobytes()
+        assert gc["light_aabb_tests"] == cc["light_aabb_tests"] and gc["light_prim_tests"] == cc["light_prim_tests"]
+        ctx.render_accum(0, 2, 5, T.MODE_FAST, T.SCHED_WAVEFRONT, clear=True)
+        got = ctx.accum()
+        want, _ = oracle.render_accum(0, 2, 5)
+        err = np.abs(got - want) / np.maximum(np.abs(want), 1e-300)
+        err[got == want] = 0.0
+        assert err.max() <= 1e-9
+    finally:
+        ctx.close()

@@ -1,5 +1,5 @@
 """Aggregates an ncu source page (`--page source --csv --print-source cuda,sass`) per source line.
-usage: ncu_lines.py report.ncu-rep [top_n]"""
+usage: ncu_lines.py report.ncu-rep [top_n] [kernel-name-regex]"""
 import csv
 import subprocess
 import sys
@@ -7,7 +7,8 @@ from collections import defaultdict
 
 rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+kern = ["--kernel-name", "regex:" + sys.argv[3]] if len(sys.argv) > 3 else []
+txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"] + kern, capture_output=True, text=True).stdout
 rows = list(csv.reader(txt.splitlines()))
 cur_file, hdr = None, None
 agg = defaultdict(lambda: [0, 0, 0, ""])      # (file,line) -> [inst, thread_inst, samples, src]
