@@ -94,33 +94,6 @@ cudaError_t ensure_wavefront(rt_ctx *ctx) {
     return cudaSuccess;
 }
 
-// L2 residency of the fp32 culling structures.  The trace kernel's node and pre-test records
-// (FNode + FTri, contiguous in the arena: 93 MB on the 1 M-triangle scene) are re-read by every ray,
-// while each iteration also streams the whole path state (0.6 GB at 1080p) through the same 126 MB
-// L2.  An access-policy window marks the culling structures `persisting` on both streams (captured
-// kernel nodes inherit the stream's window), as much of them as the device lets persist.
-cudaError_t apply_l2_window(rt_ctx *ctx) {
-    const FBvh &f = ctx->dsc.ftris;
-    if (!ctx->knob_l2_persist_mb || !f.nodes || !ctx->wf_rt.side) return cudaSuccess;
-    int max_persist = 0, max_window = 0;
-    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
-    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
-    if (max_persist <= 0 || max_window <= 0) return cudaSuccess;
-    const size_t want = std::min<size_t>((size_t)ctx->knob_l2_persist_mb << 20, (size_t)max_persist);
-    cudaError_t e = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
-    if (e != cudaSuccess) return e;
-    const char *lo = (const char *)f.nodes, *hi = (const char *)ctx->arena + ctx->arena_used;     // FNode, FTri (scene), then the light set's
-    const size_t bytes = std::min<size_t>((size_t)(hi - lo), (size_t)max_window);
-    cudaStreamAttrValue v{};
-    v.accessPolicyWindow.base_ptr = (void *)lo;
-    v.accessPolicyWindow.num_bytes = bytes;
-    v.accessPolicyWindow.hitRatio = bytes <= want ? 1.0f : (float)((double)want / (double)bytes);
-    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    if ((e = cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &v)) != cudaSuccess) return e;
-    return cudaStreamSetAttribute(ctx->wf_rt.side, cudaStreamAttributeAccessPolicyWindow, &v);
-}
-
 void free_scene(rt_ctx *ctx, bool keep_arena) {
     if (!keep_arena) {
         free_wavefront(ctx);
@@ -579,7 +552,6 @@ int rt_create(int device_id, rt_ctx **out) {
     // k_wf_plan only moves on when `batch` planes are complete, and at most ring - reserve (reserve <= 4)
     // planes are ever open: a larger batch would never be reached
     if (ctx->knob_batch > ctx->knob_ring - 4u) ctx->knob_batch = ctx->knob_ring - 4u;
-    if (const char *e = std::getenv("RT_WF_L2PERSIST")) { const int v = std::atoi(e); if (v >= 0 && v <= 4096) ctx->knob_l2_persist_mb = (uint32_t)v; }
     if (const char *e = std::getenv("RT_WF_SLOTS")) { const long long v = std::atoll(e); if (v >= 1024) ctx->wf_rt.slots_override = (uint64_t)v; }
     *out = ctx.release();
     return RT_OK;
@@ -662,7 +634,6 @@ int rt_upload_scene(rt_ctx *ctx, const rt_scene *scene) {
         CK(ctx, cudaStreamSynchronize(ctx->stream));
         ctx->dsc = d;
         ctx->fast_ok = im.fast_ok;
-        ctx->l2_window_set = false;
         ctx->samples = s.samples;
         ctx->scene_bytes = ctx->arena_used;
         ctx->has_scene = true;
@@ -753,7 +724,6 @@ int rt_render_accum(rt_ctx *ctx, const rt_render_params *p) {
     if (p->sched == RT_SCHED_WAVEFRONT && ctx->dsc.ray_depth > 0) {
         if (p->mode != RT_MODE_FAST) return set_err(ctx, RT_ERR_INVALID_ARG, "the wavefront scheduler runs FAST mode only (EXACT is the megakernel parity anchor)");
         CK(ctx, ensure_wavefront(ctx));
-        if (!ctx->l2_window_set) { CK(ctx, apply_l2_window(ctx)); ctx->l2_window_set = true; }
         CK(ctx, launch_render_wavefront(ctx->stream, ctx->wf_rt, ctx->dsc, p->sample_begin, p->sample_count, p->seed, ctx->d_accum,
                                         ctx->d_ctr, ctx->wf, ctx->wf_blocks, &ctx->launches, rg));
         return RT_OK;

@@ -33,8 +33,6 @@ struct rt_ctx {
     // experiment knobs, read ONCE at rt_create (never on the render path)
     uint64_t knob_cap = 0;
     uint32_t knob_ring = rt::kWfRing, knob_batch = 4;
-    uint32_t knob_l2_persist_mb = 0;    // RT_WF_L2PERSIST: MB of L2 set aside for the fp32 culling structures (0 = off)
-    bool l2_window_set = false;         // the access-policy window of the current scene is on the streams
     rt_comm *comm = nullptr;            // set by rt_comm_init / rt_group_create, torn down in rt_destroy
 };
 

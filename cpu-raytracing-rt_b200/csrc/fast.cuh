@@ -141,25 +141,10 @@ struct FTriRec {
     d3 a;
     float bax, bay, baz, cax, cay, caz;
 };
-#ifndef RT_TRI_NOALLOC
-#define RT_TRI_NOALLOC 0        // 1: pre-test records bypass L1 allocation (they are touched once per leaf visit; nodes are re-read)
-#endif
-RT_D float4 ld_f4_noalloc(const float4 *p) {
-    float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-}
 RT_D FTriRec load_ftri(const FTri *t) {
-#if RT_TRI_NOALLOC
-    const float4 q0f = ld_f4_noalloc(reinterpret_cast<const float4 *>(t));
-    const double2 q0 = make_double2(__hiloint2double(__float_as_int(q0f.y), __float_as_int(q0f.x)), __hiloint2double(__float_as_int(q0f.w), __float_as_int(q0f.z)));
-    const float4 q1 = ld_f4_noalloc(reinterpret_cast<const float4 *>(t) + 1);
-    const float4 q2 = ld_f4_noalloc(reinterpret_cast<const float4 *>(t) + 2);
-#else
     const double2 q0 = __ldg(reinterpret_cast<const double2 *>(t));
     const float4 q1 = __ldg(reinterpret_cast<const float4 *>(t) + 1);
     const float4 q2 = __ldg(reinterpret_cast<const float4 *>(t) + 2);
-#endif
     FTriRec r;
     r.a = mk3(q0.x, q0.y, __hiloint2double(__float_as_int(q1.y), __float_as_int(q1.x)));
     r.bax = q1.z; r.bay = q1.w; r.baz = q2.x;

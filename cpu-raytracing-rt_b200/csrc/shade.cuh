@@ -11,7 +11,24 @@ namespace rt {
 // Here every (pixel, global sample) owns a Philox4x32-10 stream keyed by the render seed, so a
 // sample's path does not depend on which GPU, launch or thread computed it.  The transforms
 // below reproduce rand 0.8.5's distributions for each call site.
-struct Rng {
+// One Philox4x32-10 block of the stream (seed; pixel, sample): counter = (pixel, sample, block, 0).
+// The stream of u64 draws is  #2k = (c1:c0) of block k,  #2k+1 = (c3:c2) of block k.
+RT_D void philox_block(uint32_t k0, uint32_t k1, uint32_t pixel, uint32_t sample, uint32_t block,
+                       unsigned long long &first, unsigned long long &second) {
+    uint32_t c0 = pixel, c1 = sample, c2 = block, c3 = 0u, a = k0, b = k1;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        c0 = h1 ^ c1 ^ a; c1 = l1; c2 = h0 ^ c3 ^ b; c3 = l0;
+        a += 0x9E3779B9u; b += 0xBB67AE85u;
+    }
+    first = ((unsigned long long)c1 << 32) | c0;
+    second = ((unsigned long long)c3 << 32) | c2;
+}
+// Stream position kept as (next block, spare half): one block per two draws, computed where the draw
+// happens.  Used by the megakernel, whose lanes draw at different times anyway.
+struct RngSeq {
     uint32_t k0, k1, pixel, sample, block;
     uint32_t s0, s1;        // spare u64 of the current block
     bool have;
@@ -20,17 +37,48 @@ struct Rng {
     }
     RT_D unsigned long long next_u64() {
         if (have) { have = false; return ((unsigned long long)s1 << 32) | s0; }
-        uint32_t c0 = pixel, c1 = sample, c2 = block++, c3 = 0u, a = k0, b = k1;
-#pragma unroll
-        for (int r = 0; r < 10; ++r) {
-            const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
-            const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
-            c0 = h1 ^ c1 ^ a; c1 = l1; c2 = h0 ^ c3 ^ b; c3 = l0;
-            a += 0x9E3779B9u; b += 0xBB67AE85u;
-        }
-        s0 = c2; s1 = c3; have = true;
-        return ((unsigned long long)c1 << 32) | c0;
+        unsigned long long first, second;
+        philox_block(k0, k1, pixel, sample, block++, first, second);
+        s0 = (uint32_t)second; s1 = (uint32_t)(second >> 32); have = true;
+        return first;
     }
+};
+// The same stream addressed by the number of draws consumed (`pos`), with a WINDOW of draws computed
+// ahead: the wavefront kernels fill the window once per bounce while the whole warp is converged
+// (prefetch), instead of running the ten Philox rounds inside whichever divergent branch draws next
+// (ncu, round 1: a fifth of the shade kernel's instructions were Philox rounds at 5 of 32 lanes).
+// Draws beyond the window (rejection loops, the six draws of a box light) are computed in place.
+// The per-slot state is `pos` alone (4 bytes instead of block + spare + flag).
+struct RngWin {
+    uint32_t k0, k1, pixel, sample, pos;
+    uint32_t wbase, wn;                     // the window holds draws [wbase, wbase + wn), wbase even, wn <= 4
+    unsigned long long w0, w1, w2, w3;
+    RT_D void init(unsigned long long seed, uint32_t px, uint32_t smp, uint32_t at = 0u) {
+        k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32); pixel = px; sample = smp; pos = at; wbase = 0u; wn = 0u;
+        w0 = w1 = w2 = w3 = 0ull;
+    }
+    RT_D void prefetch(int blocks) {        // 1 or 2 blocks starting at the one that holds draw `pos`
+        wbase = pos & ~1u;
+        philox_block(k0, k1, pixel, sample, wbase >> 1, w0, w1);
+        wn = 2u;
+        if (blocks > 1) { philox_block(k0, k1, pixel, sample, (wbase >> 1) + 1u, w2, w3); wn = 4u; }
+    }
+    RT_D unsigned long long next_u64() {
+        const uint32_t i = pos - wbase;
+        ++pos;
+        if (i < wn) {
+            const unsigned long long lo = (i & 1u) ? w1 : w0, hi = (i & 1u) ? w3 : w2;
+            return (i & 2u) ? hi : lo;
+        }
+        unsigned long long first, second;
+        philox_block(k0, k1, pixel, sample, (pos - 1u) >> 1, first, second);
+        return ((pos - 1u) & 1u) ? second : first;
+    }
+};
+// rand 0.8.5's distributions over either core
+template <class CORE>
+struct RngT : CORE {
+    using CORE::next_u64;
     RT_D uint32_t next_u32() { return (uint32_t)(next_u64() >> 32); }
     RT_D double gen_f64() { return (double)(next_u64() >> 11) * (1.0 / 9007199254740992.0); }      // Standard
     RT_D static double one_two(unsigned long long u) { return __longlong_as_double((long long)((u >> 12) | 0x3FF0000000000000ull)); }
@@ -69,6 +117,8 @@ struct Rng {
         return next_u64() < p_int;
     }
 };
+using Rng = RngT<RngSeq>;
+using RngW = RngT<RngWin>;
 
 // ---- camera, reference src/camera.rs:48-55 + normalise (src/raytrace.rs:9) ---------------------
 RT_D void camera_ray(const DCamera &cam, uint32_t px_x, uint32_t px_y, double jx, double jy, d3 &o, d3 &d) {
@@ -81,11 +131,13 @@ RT_D void camera_ray(const DCamera &cam, uint32_t px_x, uint32_t px_y, double jx
 }
 
 // ---- samplers, reference src/ray_sampler.rs ------------------------------------------------
-RT_D d3 uniform_on_sphere(Rng &rng) {                       // :159-170 (cube-normalise: biased by design)
+template <class RNG>
+RT_D d3 uniform_on_sphere(RNG &rng) {                       // :159-170 (cube-normalise: biased by design)
     const double a0 = rng.gen_f64(), a1 = rng.gen_f64(), a2 = rng.gen_f64();
     return unit3(mk3(a0 * 2.0 - 1.0, a1 * 2.0 - 1.0, a2 * 2.0 - 1.0));
 }
-RT_D d3 cosine_sample(d3 n, Rng &rng) {                     // :68-76
+template <class RNG>
+RT_D d3 cosine_sample(d3 n, RNG &rng) {                     // :68-76
     const d3 dir = add(uniform_on_sphere(rng), n);
     const double eps = kEps * 16.0;
     if (fabs(dir.x) <= eps && fabs(dir.y) <= eps && fabs(dir.z) <= eps) return n;
@@ -95,7 +147,8 @@ RT_D double cosine_pdf(d3 n, d3 dir) {                      // :78-83
     const double c = dot3(n, dir);
     return c <= 0.0 ? 0.0 : c / kPi;
 }
-RT_D d3 uniform_on_box(d3 s, Rng &rng) {                    // :142-157
+template <class RNG>
+RT_D d3 uniform_on_box(d3 s, RNG &rng) {                    // :142-157
     const double w4x = s.y * s.z, w4y = s.x * s.z, w4z = s.x * s.y;
     const double choice = rng.range(0.0, w4x + w4y + w4z);
     const double sign = (double)(rng.range_i32_0_1() * 2 - 1);
@@ -108,8 +161,8 @@ RT_D d3 uniform_on_box(d3 s, Rng &rng) {                    // :142-157
     return mul3(p, s);
 }
 // SHAPES = false: the caller guarantees there are no box / ellipsoid lights (their code is dropped)
-template <bool SHAPES = true>
-RT_D d3 light_sample(const DScene &sc, d3 pos, Rng &rng) {  // :101-130
+template <bool SHAPES = true, class RNG = Rng>
+RT_D d3 light_sample(const DScene &sc, d3 pos, RNG &rng) {  // :101-130
     const uint32_t index = (uint32_t)rng.range_usize(sc.n_lights);
     const uint32_t nb = SHAPES ? sc.lboxes.n_prims : 0u, ne = SHAPES ? sc.lellipsoids.n_prims : 0u;
     d3 world;
@@ -157,8 +210,8 @@ struct Pending {
     double cos_pdf;     // Cosine::pdf
 };
 enum { kPathEnd = 0, kPathContinue = 1, kPathPendingPdf = 2 };
-template <bool SHAPES = true>
-RT_D int shade_hit(const DScene &sc, const SceneHit &h, d3 &o, d3 &d, d3 &T, d3 &L, Rng &rng, Pending &pd) {
+template <bool SHAPES = true, class RNG = Rng>
+RT_D int shade_hit(const DScene &sc, const SceneHit &h, d3 &o, d3 &d, d3 &T, d3 &L, RNG &rng, Pending &pd) {
     if (h.kind < 0) { L = add(L, mul3(T, sc.bg)); return kPathEnd; }         // :14
     const double2 *mp = reinterpret_cast<const double2 *>(sc.materials + h.material);
     const double2 m0 = __ldg(mp), m1 = __ldg(mp + 1), m2 = __ldg(mp + 2);

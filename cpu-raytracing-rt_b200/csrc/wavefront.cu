@@ -44,23 +44,6 @@ constexpr uint32_t kOverflowClosest = 0x10000u, kOverflowLight = 0x20000u;
 constexpr uint32_t kNoShape = 0xFFFFFFFFu;
 
 RT_D d3 ld_soa(const double *base, uint32_t n, uint32_t i) { return mk3(base[i], base[n + i], base[2u * n + i]); }
-#ifndef WF_HINTS
-#define WF_HINTS 0              // 1: the trace kernel reads ray state / writes candidates with the streaming policy (evict-first)
-#endif
-RT_D d3 ld_soa_cs(const double *base, uint32_t n, uint32_t i) {
-#if WF_HINTS
-    return mk3(__ldcs(base + i), __ldcs(base + n + i), __ldcs(base + 2u * n + i));
-#else
-    return ld_soa(base, n, i);
-#endif
-}
-RT_D void st_u32_cs(uint32_t *p, uint32_t v) {
-#if WF_HINTS
-    __stcs(p, v);
-#else
-    *p = v;
-#endif
-}
 RT_D void st_soa(double *base, uint32_t n, uint32_t i, d3 v) { base[i] = v.x; base[n + i] = v.y; base[2u * n + i] = v.z; }
 
 __device__ __forceinline__ void flush_counters_wf(const Cnt &c, DCounters *out) {
@@ -610,7 +593,7 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
                     cur = sc.fltris.root; cur_t = 0.0f;
                     WF_ENTER_LEAF()
                 } else {                                                            // publish, go idle
-                    st_u32_cs(&b.ncand[slot], nc | (nl << 8) | over);
+                    b.ncand[slot] = nc | (nl << 8) | over;
                     has = false;
                 }
             }
@@ -628,7 +611,7 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
                     if (idx < n) {
                         const uint32_t slot_new = ll.at(idx);
                         slot = slot_new;
-                        const d3 o = ld_soa_cs(b.ro, N, slot_new), dd = ld_soa_cs(b.rd, N, slot_new);
+                        const d3 o = ld_soa(b.ro, N, slot_new), dd = ld_soa(b.rd, N, slot_new);
                         my_ray[0] = o.x; my_ray[128] = o.y; my_ray[256] = o.z;
                         my_ray[384] = dd.x; my_ray[512] = dd.y; my_ray[640] = dd.z;
                         r = make_fray(o, dd);
@@ -718,14 +701,14 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
                     if (closest) {
                         if (cls == 2) tmax = fminf(tmax, thi);
                         if (nc < (uint32_t)kWfCand) {
-                            st_u32_cs(&b.cand[nc * N + slot], tri_i);
+                            b.cand[nc * N + slot] = tri_i;
                             ++nc;
                         } else {
                             over |= kOverflowClosest;           // rare: the shade kernel redoes this search
                             WF_INC(n_over)
                         }
                     } else {
-                        if (nl < (uint32_t)kWfCand) { st_u32_cs(&b.lcand[nl * N + slot], tri_i); ++nl; }
+                        if (nl < (uint32_t)kWfCand) { b.lcand[nl * N + slot] = tri_i; ++nl; }
                         else { over |= kOverflowLight; WF_INC(n_over) }
                     }
                 }

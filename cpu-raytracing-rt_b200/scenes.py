@@ -264,9 +264,11 @@ def deep_chain_text(n=130, growth=13.0, width=32, height=24, spp=2, depth=4, lig
              "CAMERA_POSITION 0 0 -3", "CAMERA_FOV_X 1.2"]
     s = 0.5
     for k in range(n):
+        # distance and size grow together, so every triangle has the same angular size; a 6 x 4 grid of
+        # directions keeps two dozen of them visible side by side instead of one hiding the rest
         z = 2.0 * s
-        x0 = -0.3 * s if k % 2 else -0.7 * s
-        lines += ["NEW_PRIMITIVE", f"TRIANGLE {x0!r} {-0.4 * s!r} {z!r} {x0 + s!r} {-0.4 * s!r} {z!r} {x0!r} {0.6 * s!r} {z * 1.25!r}",
+        x0, y0 = (-1.1 + 0.36 * (k % 6)) * s, (-0.75 + 0.36 * ((k // 6) % 4)) * s
+        lines += ["NEW_PRIMITIVE", f"TRIANGLE {x0!r} {y0!r} {z!r} {x0 + 0.33 * s!r} {y0!r} {z!r} {x0!r} {y0 + 0.33 * s!r} {z * 1.05!r}",
                   f"COLOR {0.3 + 0.5 * (k % 3 == 0)} {0.3 + 0.5 * (k % 3 == 1)} {0.3 + 0.5 * (k % 3 == 2)}"]
         if lights and k % 4 == 1:
             lines.append("EMISSION 3 3 3")
