@@ -54,7 +54,7 @@ cudaError_t ensure_wavefront(rt_ctx *ctx) {
     const uint32_t n = (uint32_t)cap;
     if (ctx->wf_arena && ctx->wf.n == n && ctx->wf.n_px_cap == n_img) return cudaSuccess;
     free_wavefront(ctx);
-    const size_t per = (wf_bytes_per_slot() + 15) & ~(size_t)15;
+    const size_t per = wf_bytes_per_slot();
     const uint32_t ring = ctx->knob_ring, batch = ctx->knob_batch;
     const size_t total = per * n + (size_t)n_img * 24 * ring + 65536 + 64 * 256;
     cudaError_t e = cudaMalloc(&ctx->wf_arena, total);
@@ -63,34 +63,23 @@ cudaError_t ensure_wavefront(rt_ctx *ctx) {
     auto take = [&](size_t bytes) { char *r = p; p += (bytes + 255) & ~(size_t)255; return r; };
     WfBuf &b = ctx->wf;
     b.n = n;
-    double **d3s[5] = {&b.ro, &b.rd, &b.T, &b.L, &b.pv};
-    for (double **q : d3s) *q = (double *)take((size_t)n * 24);
-    double **d1s[3] = {&b.pcos, &b.pimp, &b.sh_t};
-    for (double **q : d1s) *q = (double *)take((size_t)n * 8);
-    uint32_t **u1s[7] = {&b.sh_id, &b.rng_block, &b.rng_s0, &b.rng_s1, &b.sample, &b.flags, &b.ncand};
-    for (uint32_t **q : u1s) *q = (uint32_t *)take((size_t)n * 4);
-    b.cand = (uint32_t *)take((size_t)n * 4 * kWfCand);
-    b.lcand = (uint32_t *)take((size_t)n * 4 * kWfCand);
-    double **res[4] = {&b.res_t, &b.res_u, &b.res_v, &b.lres};
-    for (double **q : res) *q = (double *)take((size_t)n * 8);
-    b.live[0] = (uint32_t *)take((size_t)n * 4);
-    b.live[1] = (uint32_t *)take((size_t)n * 4);
-    b.n_live = (uint32_t *)take(32);                    // [0..3] the two lists, [4] cursor, [5] n_x: words 2..5 are cleared together
+    b.slot = (WfSlot *)take((size_t)n * sizeof(WfSlot));
+    b.aux = (WfAux *)take((size_t)n * sizeof(WfAux));
+    b.live = (uint32_t *)take((size_t)n * 4);
+    b.hit_list = (uint32_t *)take((size_t)n * 4);
+    b.regen_list = (uint32_t *)take((size_t)n * 4);
+    b.xlist = (uint32_t *)take((size_t)n * 4);
+    b.counts = (uint32_t *)take(32);
     b.ring = ring;
     b.batch = batch;
-    b.pix = (uint32_t *)take((size_t)n * 4);
-    b.ord = (uint32_t *)take((size_t)n * 4);
     b.side = (double *)take((size_t)n_img * 24 * ring);
     b.n_px_cap = n_img;
     b.item = (unsigned long long *)take(24);
     b.plane = (uint32_t *)take(16);
-    b.cursor = b.n_live + 4;
-    b.n_x = b.n_live + 5;
     b.call = (WfCall *)take(sizeof(WfCall));
-    b.xlist = (uint32_t *)take((size_t)n * 4);
     if ((size_t)(p - ctx->wf_arena) > total) return cudaErrorMemoryAllocation;
     if (!ctx->wf_rt.side && (e = wf_runtime_init(ctx->wf_rt)) != cudaSuccess) return e;
-    ctx->wf_blocks = wf_trace_blocks(ctx->device);
+    ctx->wf_blocks = wf_trace_blocks(ctx->device, ctx->wf_rt.smem_top);
     return cudaSuccess;
 }
 
@@ -552,6 +541,7 @@ int rt_create(int device_id, rt_ctx **out) {
     // k_wf_plan only moves on when `batch` planes are complete, and at most ring - reserve (reserve <= 4)
     // planes are ever open: a larger batch would never be reached
     if (ctx->knob_batch > ctx->knob_ring - 4u) ctx->knob_batch = ctx->knob_ring - 4u;
+    if (const char *e = std::getenv("RT_WF_SMEM_TOP")) ctx->wf_rt.smem_top = std::atoi(e) != 0;
     if (const char *e = std::getenv("RT_WF_SLOTS")) { const long long v = std::atoll(e); if (v >= 1024) ctx->wf_rt.slots_override = (uint64_t)v; }
     *out = ctx.release();
     return RT_OK;

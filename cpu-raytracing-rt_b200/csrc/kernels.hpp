@@ -27,26 +27,45 @@ struct WfCall {
     unsigned long long seed;
     DRegion rg;
 };
-struct WfBuf {                          // path slots, structure of arrays; n = width * height = capacity of every array
-    uint32_t n;
-    double *ro, *rd, *T, *L, *pv;       // 3 * n: ray origin / direction, throughput, radiance, pending weight
-    double *pcos, *pimp, *sh_t;         // n: Cosine::pdf, light impact of analytic lights, shapes' best t
-    uint32_t *sh_id, *rng_block, *rng_s0, *rng_s1, *sample, *flags, *ncand;    // n
-    uint32_t *cand, *lcand;             // kWfCand * n: triangle candidates (scene / lights) that survived the fp32 pre-test
-    double *res_t, *res_u, *res_v;      // n: exact (t, u, v) of the nearest confirmed triangle (k_wf_confirm / k_wf_exact), valid when ncand = 1
-    double *lres;                       // n: complete Light::pdf impact of the ray in flight (analytic lights + emissive triangles)
-    uint32_t *live[2];                  // n each: compacted indices of slots with work
-    uint32_t *n_live;                   // [4]: per list, entries filled from the front / from the back (8-byte aligned pairs)
-    uint32_t *cursor;                   // trace kernel's fetch position in the live list (= n_live + 4: one memset clears list 1, cursor and n_x)
+// Everything a path carries from one kernel to the next is ONE 128-byte record per slot (a cache line:
+// any kernel that touches a slot — in whatever order a compacted list hands slots out — moves whole
+// lines, never a sector for 8 useful bytes), plus a second line with what only some slots or some
+// kernels need: the pending diffuse weight, the confirmed hit, the candidate lists.
+struct __align__(16) WfSlot {           // 128 B
+    double o[3], d[3];                  // the ray to trace / just traced
+    double T[3], L[3];                  // throughput, radiance so far
+    uint32_t flags, sh_id, ncand, hit_prim;     // one 16-byte vector: what the trace and confirm kernels read
+                                        // flags: alive / ended / pending Light::pdf / deferred to k_wf_exact | depth left << 8
+                                        // sh_id: nearest analytic shape (kind << 28 | index) or 0xFFFFFFFF
+                                        // ncand: trace -> confirm: #scene | #light << 8 | overflow bits; confirm -> shade: 0 / 1
+                                        // hit_prim: nearest confirmed triangle
+    uint32_t sample, pix, ord, rng_pos; // the item in flight (sample of the call, pixel, ordinal in the region), RNG draws consumed
+};
+static_assert(sizeof(WfSlot) == 128, "WfSlot must be one cache line");
+struct __align__(16) WfAux {            // 128 B
+    double pv[3], pcos;                 // pending diffuse bounce: dot * color / PI, Cosine::pdf
+    double pimp, lres;                  // Light::pdf impact: the analytic lights' part, the complete sum
+    double res_t, res_u, res_v;         // exact (t, u, v) of hit_prim
+    double sh_t;                        // distance of sh_id
+    uint32_t cand[kWfCand], lcand[kWfCand];     // triangles that survived the fp32 pre-test (scene / light hierarchy)
+};
+static_assert(sizeof(WfAux) == 128, "WfAux must be one cache line");
+struct WfBuf {
+    uint32_t n;                         // slots allocated
+    WfSlot *slot;
+    WfAux *aux;
+    uint32_t *live;                     // n: the trace list, filled from both ends (front: fresh camera rays, back: bounced rays)
+    uint32_t *hit_list, *regen_list;    // n each: slots whose ray hit something (k_wf_shade_hit) / slots that need a new path (k_wf_regen)
+    uint32_t *counts;                   // [0] trace list front, [1] back, [2] trace fetch cursor, [3] slots deferred to k_wf_exact,
+                                        // [4] hit list, [5] regen list — cleared together at the start of an iteration
+    uint32_t *xlist;                    // n: slots deferred to k_wf_exact in this iteration
     uint32_t batch;                     // planes added to the image per k_wf_sum pass (amortises the read-modify-write)
     uint32_t ring;                      // planes in the ring of finished samples
     uint32_t n_px_cap;                  // pixels the side planes were allocated for (width * height)
     WfCall *call;                       // device: the parameters of the render call in flight (written by k_wf_init)
-    uint32_t *pix, *ord;                // n: pixel (index in the image) / ordinal (in the region's tile order) a slot works on
-    double *side;                       // ring * 3 * n: radiance of finished samples: plane (sample % ring), component, ordinal
+    double *side;                       // ring * 3 * n_px: radiance of finished samples: plane (sample % ring), component, ordinal
     unsigned long long *item;           // [0] next unclaimed item, [1] claim limit, [2] items of this call
     uint32_t *plane;                    // [0] planes added to accum, [1] oldest sample in flight, [2] ring, [3] planes complete
-    uint32_t *xlist, *n_x;              // slots deferred to k_wf_exact in this iteration (n entries), their count (= cursor + 1)
 };
 size_t wf_bytes_per_slot();
 // Slots a render of n_px pixels uses: twice the pixels for small images (fewer, fuller iterations: the
@@ -57,7 +76,7 @@ inline uint64_t wf_slots_for(uint64_t n_px) {
     const uint64_t twice = 2 * n_px, most = n_px > (1u << 21) ? n_px : (1u << 21);
     return twice < most ? twice : most;
 }
-int wf_trace_blocks(int device);
+int wf_trace_blocks(int device, bool smem_top);
 // Host state a context keeps between render calls: the forked stream, the events and the
 // instantiated graph of four iterations, re-captured only when a kernel argument changes (another
 // scene, other buffers).
@@ -72,8 +91,9 @@ struct WfRuntime {
     double *key_accum = nullptr;
     DCounters *key_ctr = nullptr;
     int key_blocks = 0;
-    volatile uint32_t *host_live = nullptr;     // pinned, 4 words: what the host polls
+    volatile uint32_t *host_live = nullptr;     // pinned, 6 words: what the host polls (counts[0..3], next item)
     uint64_t slots_override = 0;        // RT_WF_SLOTS (experiments), read once at rt_create
+    bool smem_top = false;              // RT_WF_SMEM_TOP=1: the trace kernel stages the top levels of the hierarchy in shared memory
     uint64_t graph_builds = 0;          // diagnostics: how often the graph was (re)instantiated
 };
 cudaError_t wf_runtime_init(WfRuntime &rt);

@@ -1,31 +1,38 @@
 // wavefront.cu — the wavefront scheduler of generate_image (reference src/main.rs:94-103).
 //
-// A pool of SLOTS, each holding one path in flight (ray, throughput, RNG stream position, pending
-// diffuse weight), and a queue of ITEMS: item j = sample (j / n_px) of the pixel with ordinal
-// (j % n_px).  A slot whose path has ended takes the next item, whichever pixel it belongs to, so
-// all slots stay busy until the last sample of the call has been started.  An iteration:
+// A pool of SLOTS, each holding one path in flight in a 128-byte record (ray, throughput, radiance,
+// RNG stream position; kernels.hpp WfSlot / WfAux), and a queue of ITEMS: item j = sample (j / n_px)
+// of the pixel with ordinal (j % n_px).  A slot whose path has ended takes the next item, whichever
+// pixel it belongs to, so all slots stay busy until the last sample of the call has been started.
+// One iteration — every kernel after the first walks a COMPACTED LIST, so its warps are full of
+// lanes that all do the same thing:
 //
-//   k_wf_confirm  the exact f64 triangle test of the candidates the previous trace found, one
-//                 (ray, candidate) pair per thread, folded per ray; proves that the reference
-//                 reaches the same hit or hands the ray to
-//   k_wf_exact    (forked branch) the reference's own traversal for those few rays;
-//   k_wf_shade    one thread per slot, f64: finishes the pending Light::pdf weight, runs one bounce
-//                 of raytrace_impl (src/raytrace.rs:12-60); a finished sample's radiance is parked
-//                 in the plane of its sample index and the slot claims the next item; slots with a
-//                 ray are appended to the trace list with a warp ballot + prefix-sum (stream
-//                 compaction of live paths), fresh camera rays at the front;
+//   k_wf_confirm    one (ray, candidate) pair per thread: the exact f64 triangle test of the
+//                   candidates the previous trace found, folded per ray; proves that the reference
+//                   reaches the same hit or hands the ray to k_wf_exact.  Then sorts every slot into
+//                   the HIT list (its ray hit something), the REGEN list (its ray escaped, or the slot
+//                   is empty) or neither (deferred to k_wf_exact);
+//   k_wf_exact      (forked branch) the reference's own traversal for the few deferred rays;
+//   k_wf_shade_hit  hit list, f64: finishes the pending Light::pdf weight and runs one bounce of
+//                   raytrace_impl (src/raytrace.rs:12-60); the RNG draws of the bounce are computed
+//                   ahead while the warp is converged.  Paths that go on are appended to the back of
+//                   the trace list, paths that end to the regen list;
+//   k_wf_regen      regen list: adds the background to escaped paths, parks the finished sample's
+//                   radiance in the plane of its sample index, claims the next item and starts its
+//                   camera ray (front of the trace list, runs of neighbouring pixels);
 //   k_wf_plan / k_wf_sum  complete sample planes are added to the accumulation buffer in sample
-//                 order — main.rs:100-103's order, so the sum is the megakernel's bit for bit;
-//   k_wf_trace    persistent warps, fp32 only.  Each lane walks the culling hierarchy for one ray
-//                 (closest-hit search and, for a pending diffuse bounce, the all-hits search of
-//                 the light hierarchy along the same ray) and writes candidate lists.  A lane that
-//                 finishes its ray does not wait for the slowest ray of its warp: when too few
-//                 lanes remain busy the warp refills the idle ones from the trace list.
+//                   order — main.rs:100-103's order, so the sum is the megakernel's bit for bit;
+//   k_wf_trace      persistent warps, fp32 only.  Each lane walks the culling hierarchy for one ray
+//                   (closest-hit search and, for a pending diffuse bounce, the all-hits search of
+//                   the light hierarchy along the same ray) and writes candidate lists.  A lane that
+//                   finishes its ray does not wait for the slowest ray of its warp: when too few
+//                   lanes remain busy the warp refills the idle ones from the trace list.
 //
-// In a megakernel every lane waits for the slowest of its 32 rays at every bounce (ncu: 7 of 32
-// lanes active in the traversal loop); here the traversal loop stays full and the ~400-instruction
-// f64 confirmation runs with most lanes of a warp at once.  Arithmetic per path is identical to
-// the megakernel in FAST mode, so both schedulers produce bitwise the same accumulation buffer.
+// Round 1 ran confirm's successor as ONE kernel over all slots in static order: a warp held hits next
+// to misses next to empty slots and executed each of those code paths with a third of its lanes
+// (ncu: 12.4 of 32 lanes per instruction, a fifth of all instructions Philox rounds at 5 lanes).
+// Arithmetic per path is identical to the megakernel in FAST mode, so both schedulers produce
+// bitwise the same accumulation buffer, whatever slot or kernel a sample passed through.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -38,13 +45,53 @@
 namespace rt {
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
-constexpr uint32_t kFlagAlive = 1u, kFlagRngHave = 2u, kFlagPendLight = 4u;
-constexpr uint32_t kFlagExactPending = 16u;   // handed to k_wf_exact in this iteration: not shaded, not traced; cleared by the next confirm pass
+constexpr uint32_t kFlagAlive = 1u;           // the slot holds a path whose ray is being / was traced
+constexpr uint32_t kFlagEnded = 2u;           // k_wf_shade_hit ended the path: L is final, k_wf_regen parks it
+constexpr uint32_t kFlagPendLight = 4u;       // the weight of the last diffuse bounce waits for Light::pdf of the ray in flight
+constexpr uint32_t kFlagExactPending = 16u;   // handed to k_wf_exact in this iteration; cleared by the next confirm pass
 constexpr uint32_t kOverflowClosest = 0x10000u, kOverflowLight = 0x20000u;
 constexpr uint32_t kNoShape = 0xFFFFFFFFu;
+enum { kCntFront = 0, kCntBack = 1, kCntCursor = 2, kCntExact = 3, kCntHit = 4, kCntRegen = 5, kCntWords = 6 };
 
-RT_D d3 ld_soa(const double *base, uint32_t n, uint32_t i) { return mk3(base[i], base[n + i], base[2u * n + i]); }
-RT_D void st_soa(double *base, uint32_t n, uint32_t i, d3 v) { base[i] = v.x; base[n + i] = v.y; base[2u * n + i] = v.z; }
+// ---- slot records: 16-byte vector access ---------------------------------------------------------
+// WfSlot as double2[6] + uint4[2]: (o.x o.y) (o.z d.x) (d.y d.z) (T.x T.y) (T.z L.x) (L.y L.z) | head | item
+RT_D void ld_ray(const WfSlot *s, d3 &o, d3 &d) {
+    const double2 *p = reinterpret_cast<const double2 *>(s);
+    const double2 q0 = p[0], q1 = p[1], q2 = p[2];
+    o = mk3(q0.x, q0.y, q1.x);
+    d = mk3(q1.y, q2.x, q2.y);
+}
+RT_D void st_ray(WfSlot *s, d3 o, d3 d) {
+    double2 *p = reinterpret_cast<double2 *>(s);
+    p[0] = make_double2(o.x, o.y); p[1] = make_double2(o.z, d.x); p[2] = make_double2(d.y, d.z);
+}
+RT_D void ld_TL(const WfSlot *s, d3 &T, d3 &L) {
+    const double2 *p = reinterpret_cast<const double2 *>(s);
+    const double2 q3 = p[3], q4 = p[4], q5 = p[5];
+    T = mk3(q3.x, q3.y, q4.x);
+    L = mk3(q4.y, q5.x, q5.y);
+}
+RT_D void st_TL(WfSlot *s, d3 T, d3 L) {
+    double2 *p = reinterpret_cast<double2 *>(s);
+    p[3] = make_double2(T.x, T.y); p[4] = make_double2(T.z, L.x); p[5] = make_double2(L.y, L.z);
+}
+RT_D uint4 ld_head(const WfSlot *s) { return reinterpret_cast<const uint4 *>(s)[6]; }      // flags, sh_id, ncand, hit_prim
+RT_D void st_head(WfSlot *s, uint4 h) { reinterpret_cast<uint4 *>(s)[6] = h; }
+RT_D uint4 ld_item(const WfSlot *s) { return reinterpret_cast<const uint4 *>(s)[7]; }      // sample, pix, ord, rng_pos
+RT_D void st_item(WfSlot *s, uint4 v) { reinterpret_cast<uint4 *>(s)[7] = v; }
+// WfAux as double2[5] + candidates: (pv.x pv.y) (pv.z pcos) (pimp lres) (res_t res_u) (res_v sh_t)
+RT_D void ld_pending(const WfAux *a, Pending &pd, double &lres) {
+    const double2 *p = reinterpret_cast<const double2 *>(a);
+    const double2 q0 = p[0], q1 = p[1];
+    pd.v = mk3(q0.x, q0.y, q1.x);
+    pd.cos_pdf = q1.y;
+    lres = a->lres;
+}
+RT_D void st_pending(WfAux *a, const Pending &pd, double pimp) {
+    double2 *p = reinterpret_cast<double2 *>(a);
+    p[0] = make_double2(pd.v.x, pd.v.y); p[1] = make_double2(pd.v.z, pd.cos_pdf);
+    a->pimp = pimp;
+}
 
 __device__ __forceinline__ void flush_counters_wf(const Cnt &c, DCounters *out) {
     constexpr int kN = 4;
@@ -58,25 +105,38 @@ __device__ __forceinline__ void flush_counters_wf(const Cnt &c, DCounters *out) 
         if (lane == 0 && s) atomicAdd(dst[k], s);
     }
 }
+// Stream compaction: ballot + prefix sum inside the warp, one atomic per warp reserves the room.
+// Called by all 32 lanes.  Entries of one warp stay together and in lane order.
+RT_D void warp_append(uint32_t *list, uint32_t *count, bool pred, uint32_t value, int lane) {
+    const unsigned m = __ballot_sync(kFull, pred);
+    if (!m) return;
+    const int leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(count, (uint32_t)__popc(m));
+    base = __shfl_sync(kFull, base, leader);
+    if (pred) list[base + __popc(m & ((1u << lane) - 1u))] = value;
+}
+// the oldest sample still in flight: every plane before it is complete (k_wf_plan)
+RT_D void note_oldest_sample(const WfBuf &b, bool in_flight, uint32_t smp, int lane) {
+    uint32_t m = in_flight ? smp : 0xFFFFFFFFu;
+    for (int off = 16; off > 0; off >>= 1) m = min(m, __shfl_xor_sync(kFull, m, off));
+    if (lane == 0 && m != 0xFFFFFFFFu) atomicMin(&b.plane[1], m);
+}
 
-// A slot IS a pixel of the whole image (state arrays, RNG key and accumulation index all use it);
-// a render call restricted to a region simply starts with a live list that holds the region's
-// pixels only, so the other kernels do not know about regions at all.
-// A live list is filled from BOTH ends: slots whose ray is a fresh camera ray go to the front,
-// slots in the middle of a path to the back.  Consumers walk front then back, so the warps of
-// the trace kernel get runs of neighbouring primary rays (which visit the same nodes) instead of
-// a mixture of primary and bounced rays, and the shade kernel's warps see similar hits.
-// n_live[2 * list] = entries at the front, n_live[2 * list + 1] = entries at the back.
+// The trace list is filled from BOTH ends: slots whose ray is a fresh camera ray go to the front,
+// slots in the middle of a path to the back.  The trace kernel walks front then back, so its warps
+// get runs of neighbouring primary rays (which visit the same nodes) instead of a mixture of primary
+// and bounced rays.  counts[kCntFront] = entries at the front, counts[kCntBack] = entries at the back.
 struct LiveList {
     const uint32_t *p;
     uint32_t nf, n, last;
     RT_D uint32_t at(uint32_t i) const { return p[i < nf ? i : last - (i - nf)]; }
 };
-RT_D LiveList live_list(const WfBuf &b, int list) {
+RT_D LiveList live_list(const WfBuf &b) {
     LiveList l;
-    l.p = b.live[list];
-    l.nf = b.n_live[2 * list];
-    l.n = l.nf + b.n_live[2 * list + 1];
+    l.p = b.live;
+    l.nf = b.counts[kCntFront];
+    l.n = l.nf + b.counts[kCntBack];
     l.last = b.n - 1u;
     return l;
 }
@@ -93,15 +153,10 @@ RT_D uint32_t region_tile_pixel(const DRegion &rg, uint32_t width, uint32_t i) {
 __global__ void k_wf_init(WfBuf b, WfCall cl, uint32_t sample_count) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_px = cl.n_px;
-    if (i < cl.n_slots) {
-        b.flags[i] = 0;
-        b.sample[i] = 0;
-        b.live[0][i] = i;                               // the static list of all slots (k_wf_confirm)
-    }
+    if (i < cl.n_slots) st_head(b.slot + i, make_uint4(0u, kNoShape, 0u, 0u));      // an empty slot: the first confirm pass sends it to k_wf_regen
     if (i == 0) {
         *b.call = cl;                                   // what the kernels of this call read instead of arguments
-        b.n_live[0] = cl.n_slots; b.n_live[1] = 0; b.n_live[2] = 0; b.n_live[3] = 0;
-        b.cursor[0] = 0; b.cursor[1] = 0;
+        for (int k = 0; k < kCntWords; ++k) b.counts[k] = 0;
         const unsigned long long total = (unsigned long long)n_px * sample_count, first = (unsigned long long)(b.ring - cl.reserve) * n_px;
         b.item[0] = 0; b.item[1] = first < total ? first : total; b.item[2] = total;
         b.plane[0] = 0; b.plane[1] = 0xFFFFFFFFu; b.plane[2] = b.ring; b.plane[3] = 0;
@@ -115,47 +170,53 @@ __global__ void k_wf_init(WfBuf b, WfCall cl, uint32_t sample_count) {
 // candidates, so a loop per ray runs with a third of the lanes; here a block gathers the pairs of
 // its 128 rays with a prefix sum and deals them out evenly.
 // Phase 2, one ray per thread: fold the pair results into what the shade kernel needs — the
-// nearest confirmed triangle (slot entry 0 of cand / res_t / res_u / res_v, ncand = 0 or 1) and the
-// complete Light::pdf impact (lres entry 0: the analytic lights' part + the terms in list order =
-// the reference's DFS order, bvh.rs:188-210) — and decide whether the proof that the reference
-// finds the same hits holds (hit_fragile, tie_margin).  If not the slot goes to k_wf_exact.
+// nearest confirmed triangle (hit_prim, res_t / res_u / res_v, ncand = 0 or 1) and the complete
+// Light::pdf impact (lres: the analytic lights' part + the terms in list order = the reference's DFS
+// order, bvh.rs:188-210) — and decide whether the proof that the reference finds the same hits holds
+// (hit_fragile, tie_margin).  If not the slot goes to k_wf_exact.
+// Phase 3: every slot of the block is sorted into the hit list, the regen list or neither.
 #ifndef WF_CONFIRM_MINB
 #define WF_CONFIRM_MINB 8
 #endif
 // pair results a block keeps in shared memory between the two phases (0.9 pairs per ray on C3: 128
 // rays need ~115); the rays of a block whose pairs do not fit are answered by k_wf_exact
 constexpr uint32_t kConfirmPairs = 448;
-__global__ void __launch_bounds__(128, WF_CONFIRM_MINB) k_wf_confirm(DScene sc, WfBuf b, int list, DCounters *ctr) {
-    __shared__ uint32_t s_slot[128];
+__global__ void __launch_bounds__(128, WF_CONFIRM_MINB) k_wf_confirm(DScene sc, WfBuf b, DCounters *ctr) {
     __shared__ uint16_t s_pair[128 * 2 * kWfCand];
     __shared__ uint32_t s_warp[4];
     __shared__ double s_ray[6][128];
     __shared__ double s_t[kConfirmPairs], s_u[kConfirmPairs], s_v[kConfirmPairs];   // phase 1 -> phase 2
-    const uint32_t tid = threadIdx.x, i = blockIdx.x * 128 + tid, lane = tid & 31, wid = tid >> 5;
-    const LiveList ll = live_list(b, list);
-    const uint32_t N = b.n;
-    uint32_t slot = 0, nc = 0, nl = 0, flags = 0, nc_all = 0;
+    const uint32_t tid = threadIdx.x, slot0 = blockIdx.x * 128, i = slot0 + tid, lane = tid & 31, wid = tid >> 5;
+    const uint32_t n_slots = b.call->n_slots;
+    if (slot0 >= n_slots) return;                       // the grid covers the buffer's capacity
+    WfSlot *const sp = b.slot + i;
+    WfAux *const ap = b.aux + i;
+    uint32_t nc = 0, nl = 0, flags = 0, nc_all = 0, sh_id = kNoShape;
     bool mine = false;                                  // this thread's slot has results to fold
-    if (i < ll.n) {
-        slot = ll.at(i);
-        flags = b.flags[slot];
+    int cls = 0;                                        // 1: hit list, 2: regen list
+    if (i < n_slots) {
+        const uint4 h = ld_head(sp);
+        flags = h.x; sh_id = h.y; nc_all = h.z;
         if (flags & kFlagExactPending) {
             // k_wf_exact answered this slot during the last iteration (the graph joined since):
             // its results are final, the shade kernel takes them in this iteration
-            b.flags[slot] = flags & ~kFlagExactPending;
-        } else if (flags & kFlagAlive) {                // not alive: nothing was traced for this slot
+            flags &= ~kFlagExactPending;
+            sp->flags = flags;
+            cls = ((nc_all & 0xFFu) || sh_id != kNoShape) ? 1 : 2;
+        } else if (flags & kFlagAlive) {
             mine = true;
-            nc_all = b.ncand[slot];
-            nc = (nc_all & kOverflowClosest) ? 0u : (nc_all & 0xFFu);       // overflowed lists: the shade kernel redoes the search
+            nc = (nc_all & kOverflowClosest) ? 0u : (nc_all & 0xFFu);       // overflowed lists: the exact traversal redoes the search
             nl = ((nc_all & kOverflowLight) || !(flags & kFlagPendLight)) ? 0u : ((nc_all >> 8) & 0xFFu);
             if (nc + nl) {
-                const d3 o = ld_soa(b.ro, N, slot), d = ld_soa(b.rd, N, slot);
+                d3 o, d;
+                ld_ray(sp, o, d);
                 s_ray[0][tid] = o.x; s_ray[1][tid] = o.y; s_ray[2][tid] = o.z;
                 s_ray[3][tid] = d.x; s_ray[4][tid] = d.y; s_ray[5][tid] = d.z;
             }
+        } else {
+            cls = 2;                                    // no path: wants the next item
         }
     }
-    s_slot[tid] = slot;
     // exclusive prefix sum of the pair counts over the block
     uint32_t incl = nc + nl;
 #pragma unroll
@@ -179,10 +240,10 @@ __global__ void __launch_bounds__(128, WF_CONFIRM_MINB) k_wf_confirm(DScene sc, 
     for (uint32_t e = tid; e < min(total, kConfirmPairs); e += 128) {
         const uint32_t pr = s_pair[e], owner = pr & 127u, k = (pr >> 7) & 7u;
         const bool light = (pr & 0x400u) != 0;
-        const size_t at = (size_t)k * N + s_slot[owner];
+        const WfAux *oa = b.aux + slot0 + owner;
         const d3 o = mk3(s_ray[0][owner], s_ray[1][owner], s_ray[2][owner]);
         const d3 d = mk3(s_ray[3][owner], s_ray[4][owner], s_ray[5][owner]);
-        const uint32_t prim = light ? b.lcand[at] : b.cand[at];
+        const uint32_t prim = light ? oa->lcand[k] : oa->cand[k];
         double t, u, v;
         const DTriI *tp = (light ? sc.ltri_i : sc.tri_i) + prim;
         const bool hit = tri_exact(tp, o, d, t, u, v);
@@ -208,138 +269,214 @@ __global__ void __launch_bounds__(128, WF_CONFIRM_MINB) k_wf_confirm(DScene sc, 
         // is not worth a second fp32 search: the exact traversal answers the ray
         bool need_exact = (nc_all & (kOverflowClosest | kOverflowLight)) != 0 || base + nl + nc > kConfirmPairs;
         if ((flags & kFlagPendLight) && !need_exact) {
-            double impact = b.pimp[slot];
+            double impact = ap->pimp;
             for (uint32_t k = 0; k < nl; ++k) {
                 const double term = s_t[base + k];
                 if (term == -2.0) need_exact = true;
                 else if (term != -1.0) impact += term;
             }
-            b.lres[slot] = impact;
+            ap->lres = impact;
         }
+        bool tri_hit = false;
         if (!need_exact) {
             FBest fb;
             fbest_clear(fb);
             for (uint32_t k = 0; k < nc; ++k) {
                 const uint32_t e = base + nl + k;
                 const double u = s_u[e];
-                if (u != -1.0) fbest_take(fb, s_t[e], u, s_v[e], b.cand[(size_t)k * N + slot], u == -2.0);
+                if (u != -1.0) fbest_take(fb, s_t[e], u, s_v[e], ap->cand[k], u == -2.0);
             }
             if (fb.has) {
                 const d3 o = mk3(s_ray[0][tid], s_ray[1][tid], s_ray[2][tid]), d = mk3(s_ray[3][tid], s_ray[4][tid], s_ray[5][tid]);
-                need_exact = need_exact || fbest_needs_exact(fb, o, d, (double)sc.ftris.bound);
-                b.cand[slot] = fb.prim;
-                b.res_t[slot] = fb.t; b.res_u[slot] = fb.u; b.res_v[slot] = fb.v;
+                need_exact = fbest_needs_exact(fb, o, d, (double)sc.ftris.bound);
+                ap->res_t = fb.t; ap->res_u = fb.u; ap->res_v = fb.v;
             }
-            b.ncand[slot] = fb.has ? 1u : 0u;
+            if (!need_exact) {
+                sp->ncand = fb.has ? 1u : 0u;
+                sp->hit_prim = fb.prim;
+                tri_hit = fb.has;
+            }
         }
         if (need_exact) {
-            b.flags[slot] = flags | kFlagExactPending;
-            b.xlist[atomicAdd(b.n_x, 1u)] = slot;
+            // Nothing is shaded or traced for the slot in this iteration: k_wf_exact answers both searches
+            // with the reference's own traversal meanwhile, the next confirm pass picks the slot up.
+            sp->flags = flags | kFlagExactPending;
+            b.xlist[atomicAdd(&b.counts[kCntExact], 1u)] = i;
             atomicAdd(&ctr->exact_fallbacks, 1ull);     // rare
+            atomicMin(&b.plane[1], sp->sample);         // still in flight
+        } else {
+            cls = (tri_hit || sh_id != kNoShape) ? 1 : 2;
         }
     }
+    // ---- phase 3: the lists the next two kernels walk
+    warp_append(b.hit_list, &b.counts[kCntHit], cls == 1, i, (int)lane);
+    warp_append(b.regen_list, &b.counts[kCntRegen], cls == 2, i, (int)lane);
 }
 
-// ---- shade -------------------------------------------------------------------------------------
+// ---- shade: the slots whose ray hit something ----------------------------------------------------
 #ifndef WF_SHADE_MINB
-#define WF_SHADE_MINB 6        // glTF variant: 80 registers, no spills to speak of; measured 4 / 5 / 6 / 7 / 8 -> 1240 / 1270 / 1282 / 1276 / 1275 Mseg/s
+#define WF_SHADE_MINB 6
 #endif
 template <bool SHAPES>
-__global__ void __launch_bounds__(128, SHAPES ? 4 : WF_SHADE_MINB) k_wf_shade(DScene sc, WfBuf b, DCounters *ctr) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const WfCall cl = *b.call;                          // uniform: one broadcast load
-    const DRegion rg = cl.rg;
-    const uint32_t sample_begin = cl.sample_begin;
-    const unsigned long long seed = cl.seed;
-    const uint32_t N = b.n, n_px = cl.n_px;
+__global__ void __launch_bounds__(128, SHAPES ? 4 : WF_SHADE_MINB) k_wf_shade_hit(DScene sc, WfBuf b, DCounters *ctr) {
+    const uint32_t n = b.counts[kCntHit];
+    if (blockIdx.x * 128u >= n) return;                 // the grid covers the buffer's capacity
+    const uint32_t i = blockIdx.x * 128u + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    uint32_t *__restrict__ next_live = b.live[1];
+    const bool on = i < n;
     Cnt c;
-    bool keep = false, fresh = false, in_range = i < cl.n_slots, want = false, alive = false, defer = false, pend_light = false;
-    const uint32_t slot = i;                            // slots are walked in index order; which PIXEL a slot works on changes
-    uint32_t smp = 0, pix = 0, ord = 0, left = 0;
-    Rng rng;
-    rng.init(seed, 0u, 0u);
-    d3 o = mk3(0.0, 0.0, 0.0), d = o, T = o, L = o;
-    Pending pd;
-    pd.v = o; pd.cos_pdf = 0.0;
-    if (in_range) {
-        const uint32_t flags = b.flags[slot];
-        smp = b.sample[slot];
-        left = (flags >> 8) & 0xFFu;
-        defer = (flags & kFlagExactPending) != 0;
-        alive = (flags & kFlagAlive) != 0 && !defer;
-        bool ended = false;
-        if (alive) {
-            pix = b.pix[slot];
-            rng.init(seed, pix, sample_begin + smp);
-            rng.block = b.rng_block[slot]; rng.s0 = b.rng_s0[slot]; rng.s1 = b.rng_s1[slot];
-            rng.have = (flags & kFlagRngHave) != 0;
-            o = ld_soa(b.ro, N, slot); d = ld_soa(b.rd, N, slot);
-            T = ld_soa(b.T, N, slot); L = ld_soa(b.L, N, slot);
-            const uint32_t nc_all = b.ncand[slot];
-            if (flags & kFlagPendLight) {               // finish the previous diffuse bounce: Light::pdf of THIS ray
-                const double impact = b.lres[slot];     // folded by k_wf_confirm or answered by k_wf_exact
-                pd.v = ld_soa(b.pv, N, slot);
-                pd.cos_pdf = b.pcos[slot];
-                if (!apply_pending(pd, impact / (double)sc.n_lights, T)) ended = true;
+    bool go_on = false, ended = false;
+    uint32_t slot = 0, smp = 0;
+    if (on) {
+        slot = b.hit_list[i];
+        WfSlot *const sp = b.slot + slot;
+        WfAux *const ap = b.aux + slot;
+        d3 o, d, T, L;
+        ld_ray(sp, o, d);
+        ld_TL(sp, T, L);
+        const uint4 h = ld_head(sp), it = ld_item(sp);
+        const uint32_t flags = h.x;
+        smp = it.x;
+        uint32_t left = (flags >> 8) & 0xFFu;
+        // the draws of this bounce (a diffuse bounce takes four), computed while every lane of the warp is here
+        RngW rng;
+        rng.init(b.call->seed, it.y, b.call->sample_begin + smp, it.w);
+        rng.prefetch(2);
+        Pending pd;
+        pd.v = mk3(0.0, 0.0, 0.0); pd.cos_pdf = 0.0;
+        bool pend_light = false;
+        if (flags & kFlagPendLight) {                   // finish the previous diffuse bounce: Light::pdf of THIS ray
+            double impact;                              // folded by k_wf_confirm or answered by k_wf_exact
+            ld_pending(ap, pd, impact);
+            if (!apply_pending(pd, impact / (double)sc.n_lights, T)) ended = true;
+        }
+        if (!ended) {
+            ShapeBest sb;
+            sb.has = SHAPES && h.y != kNoShape; sb.kind = sb.has ? (int)(h.y >> 28) : -1; sb.prim = h.y & 0x0FFFFFFFu;
+            sb.t = sb.has ? ap->sh_t : 0.0;
+            FBest fb;
+            fbest_clear(fb);
+            bool skip;
+            (void)shapes_tmax(sb, skip);
+            if (!skip && (h.z & 0xFFu)) {               // the nearest confirmed triangle, folded by k_wf_confirm
+                const double2 r = reinterpret_cast<const double2 *>(ap)[3];
+                fb.has = true; fb.prim = h.w;
+                fb.t = r.x; fb.u = r.y; fb.v = ap->res_v;
             }
-            if (!ended) {
-                ShapeBest sb;
-                const uint32_t sid = b.sh_id[slot];
-                sb.has = sid != kNoShape; sb.kind = sb.has ? (int)(sid >> 28) : -1; sb.prim = sid & 0x0FFFFFFFu; sb.t = b.sh_t[slot];
-                FBest fb;
-                fbest_clear(fb);
-                bool skip;
-                const float tmax = shapes_tmax(sb, skip);
-                (void)tmax;
-                if (!skip && (nc_all & 0xFFu)) {        // the nearest confirmed triangle, folded by k_wf_confirm
-                    fb.has = true; fb.prim = b.cand[slot];
-                    fb.t = b.res_t[slot]; fb.u = b.res_u[slot]; fb.v = b.res_v[slot];
-                }
-                ++c.seg;
-                const SceneHit h = finish_hit<SHAPES>(sc, o, d, sb, fb);
-                const int r = shade_hit<SHAPES>(sc, h, o, d, T, L, rng, pd);
-                --left;
-                if (r == kPathEnd) {
-                    ended = true;
-                } else if (left == 0) {
-                    // the reference evaluates Light::pdf before recursing into a depth-0 call
-                    // that returns at once (raytrace.rs:27-32, :13): count it, nothing to trace
-                    if (r == kPathPendingPdf) ++c.lray;
-                    ended = true;
-                } else {
-                    pend_light = r == kPathPendingPdf;
-                }
-            }
-            if (ended) {
-                // The finished sample's radiance goes to the plane of its sample index; k_wf_sum
-                // adds the planes to the accumulation buffer in sample order (main.rs:102), whatever
-                // slot computed them and whenever.
-                const uint32_t od = b.ord[slot];
-                double *sp = b.side + (size_t)(smp % b.ring) * 3u * n_px + od;
-                sp[0] = L.x; sp[n_px] = L.y; sp[2u * (size_t)n_px] = L.z;
-                alive = false;
+            ++c.seg;
+            const SceneHit hit = finish_hit<SHAPES>(sc, o, d, sb, fb);
+            const int r = shade_hit<SHAPES>(sc, hit, o, d, T, L, rng, pd);
+            --left;
+            if (r == kPathEnd) {
+                ended = true;
+            } else if (left == 0) {
+                // the reference evaluates Light::pdf before recursing into a depth-0 call
+                // that returns at once (raytrace.rs:27-32, :13): count it, nothing to trace
+                if (r == kPathPendingPdf) ++c.lray;
+                ended = true;
+            } else {
+                pend_light = r == kPathPendingPdf;
             }
         }
-        // A slot without a path (k_wf_exact's slots excepted) takes the next item of the queue.
-        want = !alive && !defer;
+        if (ended) {
+            // k_wf_regen parks the radiance in the plane of the sample and gives the slot its next item
+            st_TL(sp, T, L);
+            sp->flags = kFlagEnded;
+        } else {                                        // hand the ray to the trace kernel
+            uint32_t sh_id = kNoShape;
+            if (SHAPES) {
+                const ShapeBest nb = shapes_closest(sc, o, d, c);
+                sh_id = nb.has ? (((uint32_t)nb.kind << 28) | nb.prim) : kNoShape;
+                if (nb.has) ap->sh_t = nb.t;
+            }
+            if (pend_light) {
+                ++c.lray;
+                st_pending(ap, pd, SHAPES ? light_shapes_impact(sc, o, d, c) : 0.0);
+            }
+            st_ray(sp, o, d);
+            st_TL(sp, T, L);
+            st_head(sp, make_uint4(kFlagAlive | (pend_light ? kFlagPendLight : 0u) | (left << 8), sh_id, 0u, 0u));
+            sp->rng_pos = rng.pos;
+            go_on = true;
+        }
+    }
+    // bounced rays go to the BACK of the trace list
+    {
+        const unsigned m = __ballot_sync(kFull, go_on);
+        if (m) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&b.counts[kCntBack], (uint32_t)__popc(m));
+            base = __shfl_sync(kFull, base, 0);
+            if (go_on) b.live[b.n - 1u - (base + __popc(m & ((1u << lane) - 1u)))] = slot;
+        }
+    }
+    warp_append(b.regen_list, &b.counts[kCntRegen], ended, slot, lane);
+    note_oldest_sample(b, go_on, smp, lane);
+    flush_counters_wf(c, ctr);
+}
+
+// ---- regen: escaped rays, ended paths, empty slots -> the next item -----------------------------
+// Slots are not tied to pixels: a slot takes whatever item is next, so all slots stay busy until
+// the last sample of the call has been started, however unevenly path lengths are spread over the
+// image.  What keeps the result the megakernel's bit for bit is the ORDER of the additions: every
+// finished sample is parked in the plane of its sample index, and complete planes are added to the
+// accumulation buffer one after the other, sample 0 first (main.rs:100-103).
+template <bool SHAPES>
+__global__ void __launch_bounds__(128, SHAPES ? 4 : 8) k_wf_regen(DScene sc, WfBuf b, DCounters *ctr) {
+    const uint32_t n = b.counts[kCntRegen];
+    if (blockIdx.x * 128u >= n) return;
+    const uint32_t i = blockIdx.x * 128u + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool on = i < n;
+    const WfCall cl = *b.call;                          // uniform: one broadcast load
+    const uint32_t n_px = cl.n_px;
+    Cnt c;
+    uint32_t slot = 0, old_flags = 0;
+    WfSlot *sp = nullptr;
+    if (on) {
+        slot = b.regen_list[i];
+        sp = b.slot + slot;
+        const uint4 h = ld_head(sp);
+        old_flags = h.x;
+        if (old_flags & (kFlagAlive | kFlagEnded)) {
+            const uint4 it = ld_item(sp);
+            d3 T, L;
+            ld_TL(sp, T, L);
+            if (old_flags & kFlagAlive) {               // the ray escaped: raytrace_impl returns bg_color (raytrace.rs:14)
+                bool counts_as_segment = true;
+                if (old_flags & kFlagPendLight) {       // ... once the weight of the bounce that shot it is known
+                    Pending pd;
+                    double impact;
+                    ld_pending(b.aux + slot, pd, impact);
+                    counts_as_segment = apply_pending(pd, impact / (double)sc.n_lights, T);
+                }
+                if (counts_as_segment) {
+                    ++c.seg;
+                    L = add(L, mul3(T, sc.bg));
+                }
+            }
+            // The finished sample's radiance goes to the plane of its sample index; k_wf_sum adds the
+            // planes to the accumulation buffer in sample order (main.rs:102), whatever slot computed
+            // them and whenever.
+            double *side = b.side + (size_t)(it.x % b.ring) * 3u * n_px + it.z;
+            side[0] = L.x; side[n_px] = L.y; side[2u * (size_t)n_px] = L.z;
+        }
     }
     // ---- claim: item j = sample (j / n_px) of the pixel with ordinal (j % n_px) in the region's
-    // tile order.  One compare-and-swap per warp hands out a run of consecutive items — the lanes
-    // of a warp that start a path together get neighbouring pixels — and never passes the limit
-    // (the planes of the ring that are still being filled).
-    __syncwarp();
-    const unsigned mw = __ballot_sync(kFull, want);
-    if (mw) {
-        const int leader = __ffs(mw) - 1;
+    // tile order.  One atomicAdd per warp hands out a run of consecutive items — the lanes of a warp
+    // that start a path together get neighbouring pixels — and the claims never pass the limit (the
+    // planes of the ring that are still being filled) by more than one item per slot.
+    bool fresh = false;
+    uint32_t smp = 0;
+    const unsigned mw = __ballot_sync(kFull, on);
+    {
         unsigned long long first = 0;
         uint32_t got = 0, s0 = 0, o0 = 0;
-        if (lane == leader) {
-            // One atomicAdd per warp, no retry loop (a compare-and-swap on this one address from
-            // 65 000 warps at once does not scale).  The limit is checked on a plain read first, so
-            // all the warps of one launch together can overshoot it by at most one item per slot =
-            // one plane (n_slots <= n_px): k_wf_plan keeps two planes of the ring in reserve.
+        if (lane == 0 && mw) {
+            // no retry loop (a compare-and-swap on this one address from 65 000 warps at once does not
+            // scale).  The limit is checked on a plain read first, so all the warps of one launch
+            // together can overshoot it by at most one item per slot = one plane (n_slots <= n_px):
+            // k_wf_plan keeps two planes of the ring in reserve.
             const unsigned long long limit = b.item[1], total = b.item[2];
             const uint32_t cnt = (uint32_t)__popc(mw);
             if (*(volatile unsigned long long *)b.item < limit) {
@@ -349,91 +486,46 @@ __global__ void __launch_bounds__(128, SHAPES ? 4 : WF_SHADE_MINB) k_wf_shade(DS
             s0 = (uint32_t)(first / n_px);
             o0 = (uint32_t)(first - (unsigned long long)s0 * n_px);
         }
-        got = __shfl_sync(kFull, got, leader);
-        s0 = __shfl_sync(kFull, s0, leader);
-        o0 = __shfl_sync(kFull, o0, leader);
+        got = __shfl_sync(kFull, got, 0);
+        s0 = __shfl_sync(kFull, s0, 0);
+        o0 = __shfl_sync(kFull, o0, 0);
         const uint32_t rank = __popc(mw & ((1u << lane) - 1u));
-        if (want && rank < got) {
+        if (on && rank < got) {
             smp = s0;
             unsigned long long oo = (unsigned long long)o0 + rank;
             while (oo >= n_px) { oo -= n_px; ++smp; }
-            ord = (uint32_t)oo;
-            pix = region_tile_pixel(rg, sc.width, ord);
-            rng.init(seed, pix, sample_begin + smp);
+            const uint32_t ord = (uint32_t)oo;
+            const uint32_t pix = region_tile_pixel(cl.rg, sc.width, ord);
+            RngW rng;
+            rng.init(cl.seed, pix, cl.sample_begin + smp);
+            rng.prefetch(1);
             const double jx = rng.range(0.0, 1.0), jy = rng.range(0.0, 1.0);       // camera.rs:49-50
+            d3 o, d;
             camera_ray(sc.cam, pix % sc.width, pix / sc.width, jx, jy, o, d);
             ++c.paths;
-            T = mk3(1.0, 1.0, 1.0);
-            L = mk3(0.0, 0.0, 0.0);
-            left = sc.ray_depth;
-            pend_light = false;
-            fresh = true;
-            alive = true;
-        }
-    }
-    if (in_range) {
-        if (defer) {
-            // k_wf_confirm could not prove that the reference finds the same hits for this ray
-            // (hit_fragile / a tie): k_wf_exact is answering both searches with the reference's own
-            // traversal while this kernel runs.  Nothing is shaded, stored or traced for the slot
-            // in this iteration; it stays in the list and is picked up in the next one.
-            keep = true;
-        } else if (alive) {                             // hand the ray to the trace kernel
+            uint32_t sh_id = kNoShape;
             if (SHAPES) {
-                const ShapeBest sb = shapes_closest(sc, o, d, c);
-                b.sh_id[slot] = sb.has ? (((uint32_t)sb.kind << 28) | sb.prim) : kNoShape;
-                b.sh_t[slot] = sb.t;
-            } else {
-                b.sh_id[slot] = kNoShape;
-                b.sh_t[slot] = 0.0;
+                const ShapeBest nb = shapes_closest(sc, o, d, c);
+                sh_id = nb.has ? (((uint32_t)nb.kind << 28) | nb.prim) : kNoShape;
+                if (nb.has) b.aux[slot].sh_t = nb.t;
             }
-            if (pend_light) {
-                ++c.lray;
-                b.pimp[slot] = SHAPES ? light_shapes_impact(sc, o, d, c) : 0.0;
-                st_soa(b.pv, N, slot, pd.v);
-                b.pcos[slot] = pd.cos_pdf;
-            }
-            st_soa(b.ro, N, slot, o); st_soa(b.rd, N, slot, d);
-            st_soa(b.T, N, slot, T); st_soa(b.L, N, slot, L);
-            b.rng_block[slot] = rng.block; b.rng_s0[slot] = rng.s0; b.rng_s1[slot] = rng.s1;
-            if (fresh) { b.sample[slot] = smp; b.pix[slot] = pix; b.ord[slot] = ord; }
-            b.flags[slot] = kFlagAlive | (rng.have ? kFlagRngHave : 0u) | (pend_light ? kFlagPendLight : 0u) | (left << 8);
-            keep = true;
-        } else {
-            b.flags[slot] = 0;
+            st_ray(sp, o, d);
+            st_TL(sp, mk3(1.0, 1.0, 1.0), mk3(0.0, 0.0, 0.0));
+            st_head(sp, make_uint4(kFlagAlive | ((uint32_t)sc.ray_depth << 8), sh_id, 0u, 0u));
+            st_item(sp, make_uint4(smp, pix, ord, rng.pos));
+            fresh = true;
+        } else if (on && old_flags != 0u) {
+            sp->flags = 0u;                             // nothing to claim right now: an empty slot, asks again in the next iteration
         }
     }
-    // the oldest sample still in flight: every plane before it is complete (k_wf_plan)
-    {
-        uint32_t m = (in_range && (alive || defer)) ? smp : 0xFFFFFFFFu;
-        for (int off = 16; off > 0; off >>= 1) m = min(m, __shfl_xor_sync(kFull, m, off));
-        if (lane == 0 && m != 0xFFFFFFFFu) atomicMin(&b.plane[1], m);
-    }
-    // stream compaction of the live slots: ballot + prefix sum inside the warp, one 64-bit atomic
-    // per warp reserves room at both ends of the trace list (front: fresh camera rays, back: the rest)
-    const unsigned mf = __ballot_sync(kFull, keep && fresh), mb = __ballot_sync(kFull, keep && !fresh);
-    if (mf | mb) {
-        unsigned long long base = 0;
-        if (lane == 0)
-            base = atomicAdd(reinterpret_cast<unsigned long long *>(b.n_live + 2),
-                             (unsigned long long)__popc(mf) | ((unsigned long long)__popc(mb) << 32));
-        base = __shfl_sync(kFull, base, 0);
-        const unsigned below = (1u << lane) - 1u;
-        if (keep) {
-            if (fresh) next_live[(uint32_t)base + __popc(mf & below)] = slot;
-            else next_live[N - 1u - ((uint32_t)(base >> 32) + __popc(mb & below))] = slot;
-        }
-    }
+    // fresh camera rays go to the FRONT of the trace list, in claim order
+    warp_append(b.live, &b.counts[kCntFront], fresh, slot, lane);
+    note_oldest_sample(b, fresh, smp, lane);
     flush_counters_wf(c, ctr);
 }
 
 // ---- sum -----------------------------------------------------------------------------------------
-// Slots are not tied to pixels: a slot takes whatever item is next, so all slots stay busy until
-// the last sample of the call has been started, however unevenly path lengths are spread over the
-// image.  What keeps the result the megakernel's bit for bit is the ORDER of the additions: every
-// finished sample is parked in the plane of its sample index, and complete planes are added to the
-// accumulation buffer one after the other, sample 0 first (main.rs:100-103).
-// k_wf_plan (one thread, after the shade kernel): planes [summed, upto) are complete — fully
+// k_wf_plan (one thread, after the regen kernel): planes [summed, upto) are complete — fully
 // claimed and older than the oldest sample still in flight — and the claim limit moves on.
 __global__ void k_wf_plan(WfBuf b) {
     const uint32_t n_px = b.call->n_px, reserve = b.call->reserve;
@@ -473,29 +565,32 @@ __global__ void __launch_bounds__(256) k_wf_sum(WfBuf b, uint32_t width, double 
 // The slots k_wf_confirm could not vouch for (normally a few dozen per iteration: paths leaving a
 // flat light, rays through a mesh vertex): both searches of the ray redone with the reference's
 // own traversal (exact.cuh) and written back in the form k_wf_confirm leaves its results in — the
-// nearest triangle in entry 0, the complete light impact.  The slot's flag stays set for the whole
-// iteration (the next confirm pass clears it), so whether this kernel is early or late changes nothing.  One such traversal is a long serial chain, so this kernel runs on a forked
-// branch of the graph, next to the shade and trace kernels, which skip these slots meanwhile.
+// nearest triangle, the complete light impact.  The slot's flag stays set for the whole iteration
+// (the next confirm pass clears it) and the slot is in none of the lists, so whether this kernel is
+// early or late changes nothing.  One such traversal is a long serial chain, so this kernel runs on a
+// forked branch of the graph, next to the shade, regen and trace kernels.
 __global__ void __launch_bounds__(128) k_wf_exact(DScene sc, WfBuf b) {
-    const uint32_t n = *b.n_x, N = b.n;
+    const uint32_t n = b.counts[kCntExact];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t slot = b.xlist[i];
-        const uint32_t flags = b.flags[slot];
-        const d3 o = ld_soa(b.ro, N, slot), d = ld_soa(b.rd, N, slot);
+        WfSlot *const sp = b.slot + slot;
+        WfAux *const ap = b.aux + slot;
+        d3 o, d;
+        ld_ray(sp, o, d);
         Cnt scratch;
-        if (flags & kFlagPendLight) {
-            double impact = b.pimp[slot];               // the analytic lights' part (shade kernel), then the triangles
+        if (sp->flags & kFlagPendLight) {
+            double impact = ap->pimp;                   // the analytic lights' part (shade kernel), then the triangles
             light_hits_exact<3>(sc.ltris, sc.ltri_i, sc.ltri_s, o, d, impact, scratch);
-            b.lres[slot] = impact;
+            ap->lres = impact;
         }
         const Best bt = closest_exact<3>(sc.tris, sc.tri_i, o, d, scratch);
         if (bt.has) {
             double t, u, v;
             tri_exact(sc.tri_i + bt.prim, o, d, t, u, v);
-            b.cand[slot] = bt.prim;
-            b.res_t[slot] = t; b.res_u[slot] = u; b.res_v[slot] = v;
+            sp->hit_prim = bt.prim;
+            ap->res_t = t; ap->res_u = u; ap->res_v = v;
         }
-        b.ncand[slot] = bt.has ? 1u : 0u;               // no overflow: nothing left for the shade kernel to search
+        sp->ncand = bt.has ? 1u : 0u;                   // no overflow: nothing left to search
     }
 }
 
@@ -507,9 +602,10 @@ __global__ void __launch_bounds__(128) k_wf_exact(DScene sc, WfBuf b) {
 // finished lane is refilled from the live list as soon as enough lanes are idle — no lane waits
 // for the slowest ray of its warp.  The closest-hit search of the scene hierarchy and the all-hits
 // search of the light hierarchy use the same two steps with per-lane node / triangle pointers.
-#ifndef WF_SMEM_TOP
-#define WF_SMEM_TOP 0      // measured on B200 (C3): 947 Mseg/s with staging vs 1015 without — L1 hits cost the same as shared memory
-#endif
+// Refills take 16 lanes at a time (measured on B200, Mseg/s on C3: 4 / 8 / 12 / 16 / 20 / 24 / 32 lanes
+// -> 1325 / 1340 / 1366 / 1419 / 1426 / 1421 / 1331): rays that start at the root TOGETHER stay in
+// step through the top of the hierarchy and fetch the same nodes; handing rays out a few at a time
+// from a run claimed per warp loses that, however early the idle lanes get back to work.
 #ifndef WF_COUNT
 #define WF_COUNT 0           // 1: count fp32 node visits / pre-tests / candidates / overflows (diagnostics)
 #endif
@@ -525,25 +621,30 @@ __global__ void __launch_bounds__(128) k_wf_exact(DScene sc, WfBuf b) {
 #endif
 constexpr int kRefillLanes = WF_REFILL;  // refill once this many lanes are idle
 
-__global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, WfBuf b, int list, DCounters *ctr) {
-    const LiveList ll = live_list(b, list);
-    const uint32_t n = ll.n, N = b.n;
+// SMEM_TOP: the top levels of the scene hierarchy (nodes [0, top), breadth-first: every ray starts
+// there) are staged in shared memory, one contiguous copy per block.  Measured on B200 (C3): 947
+// Mseg/s with staging against 1015 without at the time — an L1 hit costs what a shared-memory read
+// costs, and the per-lane choice between the two address spaces is extra work in the hottest loop —
+// so the default is off; RT_WF_SMEM_TOP=1 (read at rt_create) selects this instantiation.
+template <bool SMEM_TOP>
+__global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, WfBuf b, DCounters *ctr) {
+    const LiveList ll = live_list(b);
+    const uint32_t n = ll.n;
     const int lane = threadIdx.x & 31;
     const float inf = __int_as_float(0x7F800000);
-#if WF_SMEM_TOP
-    // shared-memory staging of the top levels of the scene hierarchy (every ray starts there):
-    // nodes [0, top) are its first levels in breadth-first order, one contiguous copy per block
-    __shared__ float4 s_top[kFastTopNodes * 8];
-    const uint32_t top_n = sc.ftris.root >= 0 ? (sc.ftris.top < kFastTopNodes ? sc.ftris.top : kFastTopNodes) : 0u;
-    for (uint32_t k = threadIdx.x; k < top_n * 8; k += blockDim.x) s_top[k] = __ldg(reinterpret_cast<const float4 *>(sc.ftris.nodes) + k);
-    __syncthreads();
-#endif
+    __shared__ float4 s_top[SMEM_TOP ? kFastTopNodes * 8 : 1];
+    uint32_t top_n = 0;
+    if (SMEM_TOP) {
+        top_n = sc.ftris.root >= 0 ? (sc.ftris.top < kFastTopNodes ? sc.ftris.top : kFastTopNodes) : 0u;
+        for (uint32_t k = threadIdx.x; k < top_n * 8; k += blockDim.x) s_top[k] = __ldg(reinterpret_cast<const float4 *>(sc.ftris.nodes) + k);
+        __syncthreads();
+    }
     bool has = false, drained = false, closest = true, want_light = false;
     uint32_t nc = 0, nl = 0, over = 0, tri_i = 0, tri_end = 0;
     // per-lane values that are written at refill and read only when a candidate is stored or the ray
     // is published live in shared memory, not in registers (the kernel runs at 64 registers, 8 blocks per SM)
     __shared__ uint32_t s_slot[128];
-#define slot s_slot[threadIdx.x]
+#define my_slot s_slot[threadIdx.x]
 #if WF_COUNT
     uint32_t n_inner = 0, n_tri = 0, n_cand = 0, n_over = 0;
 #define WF_INC(X) ++X;
@@ -593,7 +694,7 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
                     cur = sc.fltris.root; cur_t = 0.0f;
                     WF_ENTER_LEAF()
                 } else {                                                            // publish, go idle
-                    b.ncand[slot] = nc | (nl << 8) | over;
+                    b.slot[my_slot].ncand = nc | (nl << 8) | over;
                     has = false;
                 }
             }
@@ -602,7 +703,7 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
             if (!drained && __popc(idle) >= kRefillLanes) {
                 const int leader = __ffs(idle) - 1;
                 uint32_t base = 0;
-                if (lane == leader) base = atomicAdd(b.cursor, (uint32_t)__popc(idle));
+                if (lane == leader) base = atomicAdd(&b.counts[kCntCursor], (uint32_t)__popc(idle));
                 base = __shfl_sync(kFull, base, leader);
                 // the highest index handed out in this refill tells whether the list ran out
                 if (base + (uint32_t)__popc(idle) >= n) drained = true;
@@ -610,17 +711,19 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
                     const uint32_t idx = base + __popc(idle & ((1u << lane) - 1u));
                     if (idx < n) {
                         const uint32_t slot_new = ll.at(idx);
-                        slot = slot_new;
-                        const d3 o = ld_soa(b.ro, N, slot_new), dd = ld_soa(b.rd, N, slot_new);
+                        my_slot = slot_new;
+                        const WfSlot *rec = b.slot + slot_new;
+                        d3 o, dd;
+                        ld_ray(rec, o, dd);
+                        const uint4 h = ld_head(rec);
                         my_ray[0] = o.x; my_ray[128] = o.y; my_ray[256] = o.z;
                         my_ray[384] = dd.x; my_ray[512] = dd.y; my_ray[640] = dd.z;
                         r = make_fray(o, dd);
-                        const uint32_t sid = b.sh_id[slot_new];
-                        const double st = b.sh_t[slot_new];
+                        const uint32_t sid = h.y;
+                        const double st = sid != kNoShape ? b.aux[slot_new].sh_t : 0.0;
                         bool skip = (sid != kNoShape && st != st) || ray_is_nan(o, dd);
                         tmax = (sid != kNoShape && !skip) ? up_f32(st) : inf;
-                        const uint32_t fl = b.flags[slot_new];
-                        want_light = (fl & kFlagPendLight) != 0;
+                        want_light = (h.x & kFlagPendLight) != 0;
                         nc = 0; nl = 0; over = 0; sp = 0;
                         const float range_bound = fmaxf(sc.ftris.bound, sc.fltris.bound);
                         s_wpad[threadIdx.x] = fast_wpad(o, range_bound);
@@ -634,7 +737,7 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
                         closest = true;
                         cur = skip ? kFastEmpty : sc.ftris.root; cur_t = 0.0f;
                         WF_ENTER_LEAF()
-                        has = !(fl & kFlagExactPending);        // k_wf_exact is answering this ray: not traced
+                        has = true;
                     }
                 }
             }
@@ -648,12 +751,13 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
         if (WF_VOTE_I * ni >= WF_VOTE_T * nt) {
             if (wi) {                                           // INNER step: one 4-wide node
                 WF_INC(n_inner)
-#if WF_SMEM_TOP
-                const FNode *np = (closest && (uint32_t)cur < top_n) ? reinterpret_cast<const FNode *>(s_top) + cur : (closest ? sc.ftris.nodes : sc.fltris.nodes) + cur;
-                Visit4 v = visit4<true>(np, r, tmax);
-#else
-                Visit4 v = visit4((closest ? sc.ftris.nodes : sc.fltris.nodes) + cur, r, tmax);
-#endif
+                Visit4 v;
+                if (SMEM_TOP) {
+                    const FNode *np = (closest && (uint32_t)cur < top_n) ? reinterpret_cast<const FNode *>(s_top) + cur : (closest ? sc.ftris.nodes : sc.fltris.nodes) + cur;
+                    v = visit4<true>(np, r, tmax);
+                } else {
+                    v = visit4((closest ? sc.ftris.nodes : sc.fltris.nodes) + cur, r, tmax);
+                }
                 // Nearest hit child becomes `cur`; the other hit children are deferred in child
                 // order.  The child index rides in the two low mantissa bits of the (positive) entry
                 // distance — cleared bits round it DOWN, so it stays a lower bound — and an integer
@@ -701,14 +805,14 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
                     if (closest) {
                         if (cls == 2) tmax = fminf(tmax, thi);
                         if (nc < (uint32_t)kWfCand) {
-                            b.cand[nc * N + slot] = tri_i;
+                            b.aux[my_slot].cand[nc] = tri_i;
                             ++nc;
                         } else {
-                            over |= kOverflowClosest;           // rare: the shade kernel redoes this search
+                            over |= kOverflowClosest;           // rare: k_wf_exact redoes this search
                             WF_INC(n_over)
                         }
                     } else {
-                        if (nl < (uint32_t)kWfCand) { b.lcand[nl * N + slot] = tri_i; ++nl; }
+                        if (nl < (uint32_t)kWfCand) { b.aux[my_slot].lcand[nl] = tri_i; ++nl; }
                         else { over |= kOverflowLight; WF_INC(n_over) }
                     }
                 }
@@ -716,7 +820,7 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
             WF_POP()
         }
     }
-#undef slot
+#undef my_slot
 #undef WF_ENTER_LEAF
 #undef WF_POP
 #undef WF_INC
@@ -736,11 +840,13 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
 }
 
 // ---- host loop -----------------------------------------------------------------------------------
-size_t wf_bytes_per_slot() { return 15 * 8 + 3 * 8 + 7 * 4 + kWfCand * 8 + 4 * 8 + 3 * 4 + 2 * 4; }      // + kWfRing * 24 per PIXEL for the side planes
-int wf_trace_blocks(int device) {
+size_t wf_bytes_per_slot() { return sizeof(WfSlot) + sizeof(WfAux) + 4 * sizeof(uint32_t); }      // + ring * 24 per PIXEL for the side planes
+int wf_trace_blocks(int device, bool smem_top) {
     int sms = 148, per_sm = 4;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wf_trace, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+    const cudaError_t e = smem_top ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wf_trace<true>, 128, 0)
+                                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wf_trace<false>, 128, 0);
+    if (e != cudaSuccess || per_sm < 1) per_sm = 4;
     return sms * per_sm;
 }
 cudaError_t wf_runtime_init(WfRuntime &rt) {
@@ -750,7 +856,7 @@ cudaError_t wf_runtime_init(WfRuntime &rt) {
     for (cudaEvent_t *ev : evs)
         if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return e;
     uint32_t *host = nullptr;
-    if ((e = cudaHostAlloc((void **)&host, 4 * sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess) return e;
+    if ((e = cudaHostAlloc((void **)&host, 8 * sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess) return e;
     rt.host_live = host;
     return cudaSuccess;
 }
@@ -769,7 +875,7 @@ void wf_runtime_destroy(WfRuntime &rt) {
 }
 
 constexpr int kGraphIters = 4;              // iterations per graph launch
-constexpr int kLaunchesPerIter = 6;         // confirm, exact, shade, plan, sum, trace
+constexpr int kLaunchesPerIter = 7;         // confirm, exact, shade_hit, regen, plan, sum, trace
 
 cudaError_t launch_render_wavefront(cudaStream_t st, WfRuntime &rt, const DScene &sc, uint32_t sample_begin, uint32_t sample_count,
                                     uint64_t seed, double *accum, DCounters *ctr, const WfBuf &b, int trace_blocks,
@@ -792,36 +898,42 @@ cudaError_t launch_render_wavefront(cudaStream_t st, WfRuntime &rt, const DScene
     cl.n_px = n_px;
     cl.seed = seed;
     cl.rg = rg;
-    // The grids cover the buffer's CAPACITY (threads past n_slots leave at once), so the launch
-    // configuration does not depend on the call either.
+    // The grids cover the buffer's CAPACITY (blocks past the slots in use, or past the end of a
+    // list, leave at once), so the launch configuration does not depend on the call either.
     const unsigned blocks = (b.n + 127) / 128;
     k_wf_init<<<(cl.n_slots + 127) / 128, 128, 0, st>>>(b, cl, sample_count);
     ++*launches;
     // a segment takes one iteration, two when it is deferred to k_wf_exact; an item can wait for
     // a free plane of the ring: generous bound, reaching it is reported as an error
     const uint64_t max_iters = 4 * ((uint64_t)sample_count * n_px / cl.n_slots + 1) * (sc.ray_depth ? sc.ray_depth : 1) + 64;
-    // scenes without planes / boxes / ellipsoids (every glTF scene) run the kernel compiled without them
+    // scenes without planes / boxes / ellipsoids (every glTF scene) run the kernels compiled without them
     const bool shapes = sc.n_planes || sc.boxes.n_prims || sc.ellipsoids.n_prims || sc.lboxes.n_prims || sc.lellipsoids.n_prims;
     const unsigned sum_blocks = (unsigned)std::min<uint64_t>(((uint64_t)b.n_px_cap + 255) / 256, 148 * 8);
-    // One iteration: confirm -> shade -> trace on the main stream; on the forked stream k_wf_exact
-    // (after confirm) and the one-thread k_wf_plan + k_wf_sum (after shade, next to the trace
-    // kernel), joined before the next iteration.  Four iterations are captured ONCE per (scene,
+    // One iteration: confirm -> shade_hit -> regen -> trace on the main stream; on the forked stream
+    // k_wf_exact (after confirm) and the one-thread k_wf_plan + k_wf_sum (after regen, next to the
+    // trace kernel), joined before the next iteration.  Four iterations are captured ONCE per (scene,
     // buffers) into a CUDA graph and replayed by every call: the inner loop is launch-bound on small
     // images and at the end of every render.
     auto issue_iteration = [&]() {
-        cudaMemsetAsync(&b.n_live[2], 0, 4 * sizeof(uint32_t), st);         // the trace list starts empty; trace fetch position; deferred-slot count
-        k_wf_confirm<<<blocks, 128, 0, st>>>(sc, b, 0, ctr);
+        cudaMemsetAsync(b.counts, 0, kCntWords * sizeof(uint32_t), st);     // the lists start empty; trace fetch position; deferred-slot count
+        k_wf_confirm<<<blocks, 128, 0, st>>>(sc, b, ctr);
         cudaEventRecord(rt.ev_fork, st);
         cudaStreamWaitEvent(rt.side, rt.ev_fork, 0);
         k_wf_exact<<<64, 128, 0, rt.side>>>(sc, b);
-        if (shapes) k_wf_shade<true><<<blocks, 128, 0, st>>>(sc, b, ctr);
-        else k_wf_shade<false><<<blocks, 128, 0, st>>>(sc, b, ctr);
+        if (shapes) {
+            k_wf_shade_hit<true><<<blocks, 128, 0, st>>>(sc, b, ctr);
+            k_wf_regen<true><<<blocks, 128, 0, st>>>(sc, b, ctr);
+        } else {
+            k_wf_shade_hit<false><<<blocks, 128, 0, st>>>(sc, b, ctr);
+            k_wf_regen<false><<<blocks, 128, 0, st>>>(sc, b, ctr);
+        }
         cudaEventRecord(rt.ev_shade, st);
         cudaStreamWaitEvent(rt.side, rt.ev_shade, 0);
         k_wf_plan<<<1, 1, 0, rt.side>>>(b);
         k_wf_sum<<<sum_blocks, 256, 0, rt.side>>>(b, sc.width, accum);
         cudaEventRecord(rt.ev_join, rt.side);
-        k_wf_trace<<<trace_blocks, 128, 0, st>>>(sc, b, 1, ctr);
+        if (rt.smem_top) k_wf_trace<true><<<trace_blocks, 128, 0, st>>>(sc, b, ctr);
+        else k_wf_trace<false><<<trace_blocks, 128, 0, st>>>(sc, b, ctr);
         cudaStreamWaitEvent(st, rt.ev_join, 0);
     };
     const bool same_key = rt.tried_graph && std::memcmp(&rt.key_sc, &sc, sizeof sc) == 0 && std::memcmp(&rt.key_b, &b, sizeof b) == 0 &&
@@ -852,16 +964,16 @@ cudaError_t launch_render_wavefront(cudaStream_t st, WfRuntime &rt, const DScene
             for (int k = 0; k < kGraphIters; ++k) issue_iteration();
         }
         *launches += kGraphIters * kLaunchesPerIter;
-        // poll the state after the PREVIOUS group of four without stalling the stream: nothing in
-        // flight and nothing left to claim means the call is done
+        // poll the state after the PREVIOUS group of four without stalling the stream: nothing
+        // traced, nothing deferred and nothing left to claim means the call is done
         if (poll_pending) {
             result = cudaEventSynchronize(rt.ev_poll);
             if (result != cudaSuccess) break;
-            const unsigned long long next = (unsigned long long)host_live[2] | ((unsigned long long)host_live[3] << 32);
-            if (host_live[0] + host_live[1] == 0 && next >= total_items) { finished = true; break; }
+            const unsigned long long next = (unsigned long long)host_live[4] | ((unsigned long long)host_live[5] << 32);
+            if (host_live[kCntFront] + host_live[kCntBack] + host_live[kCntExact] == 0 && next >= total_items) { finished = true; break; }
         }
-        cudaMemcpyAsync((void *)host_live, &b.n_live[2], 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync((void *)(host_live + 2), b.item, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync((void *)host_live, b.counts, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync((void *)(host_live + 4), b.item, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
         cudaEventRecord(rt.ev_poll, st);
         poll_pending = true;
     }
