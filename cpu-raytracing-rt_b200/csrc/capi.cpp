@@ -63,22 +63,27 @@ cudaError_t ensure_wavefront(rt_ctx *ctx) {
     auto take = [&](size_t bytes) { char *r = p; p += (bytes + 255) & ~(size_t)255; return r; };
     WfBuf &b = ctx->wf;
     b.n = n;
-    b.slot = (WfSlot *)take((size_t)n * sizeof(WfSlot));
-    b.aux = (WfAux *)take((size_t)n * sizeof(WfAux));
+    b.head = (uint4 *)take((size_t)n * sizeof(uint4));
+    b.ray = (WfRay *)take((size_t)n * sizeof(WfRay));
+    b.tl = (WfTL *)take((size_t)n * sizeof(WfTL));
+    b.pend = (WfPend *)take((size_t)n * sizeof(WfPend));
+    b.res = (WfRes *)take((size_t)n * sizeof(WfRes));
+    b.cand = (WfCand *)take((size_t)n * sizeof(WfCand));
     b.live = (uint32_t *)take((size_t)n * 4);
     b.hit_list = (uint32_t *)take((size_t)n * 4);
-    b.regen_list = (uint32_t *)take((size_t)n * 4);
+    b.regen_list[0] = (uint32_t *)take((size_t)n * 4);
+    b.regen_list[1] = (uint32_t *)take((size_t)n * 4);
     b.xlist = (uint32_t *)take((size_t)n * 4);
     b.counts = (uint32_t *)take(32);
     b.ring = ring;
     b.batch = batch;
     b.side = (double *)take((size_t)n_img * 24 * ring);
     b.n_px_cap = n_img;
-    b.item = (unsigned long long *)take(24);
+    b.item = (unsigned long long *)take(32);
     b.plane = (uint32_t *)take(16);
     b.call = (WfCall *)take(sizeof(WfCall));
     if ((size_t)(p - ctx->wf_arena) > total) return cudaErrorMemoryAllocation;
-    if (!ctx->wf_rt.side && (e = wf_runtime_init(ctx->wf_rt)) != cudaSuccess) return e;
+    if (!ctx->wf_rt.side && (e = wf_runtime_init(ctx->wf_rt, ctx->device)) != cudaSuccess) return e;
     ctx->wf_blocks = wf_trace_blocks(ctx->device, ctx->wf_rt.smem_top);
     return cudaSuccess;
 }
@@ -541,6 +546,8 @@ int rt_create(int device_id, rt_ctx **out) {
     // k_wf_plan only moves on when `batch` planes are complete, and at most ring - reserve (reserve <= 4)
     // planes are ever open: a larger batch would never be reached
     if (ctx->knob_batch > ctx->knob_ring - 4u) ctx->knob_batch = ctx->knob_ring - 4u;
+    if (const char *e = std::getenv("RT_WF_SHADE_BLOCKS")) { const int v = std::atoi(e); if (v >= 1 && v <= 32) ctx->wf_rt.shade_blocks = 148u * (unsigned)v; }
+    if (const char *e = std::getenv("RT_WF_REGEN_BLOCKS")) { const int v = std::atoi(e); if (v >= 1 && v <= 32) ctx->wf_rt.regen_blocks = 148u * (unsigned)v; }
     if (const char *e = std::getenv("RT_WF_SMEM_TOP")) ctx->wf_rt.smem_top = std::atoi(e) != 0;
     if (const char *e = std::getenv("RT_WF_SLOTS")) { const long long v = std::atoll(e); if (v >= 1024) ctx->wf_rt.slots_override = (uint64_t)v; }
     *out = ctx.release();

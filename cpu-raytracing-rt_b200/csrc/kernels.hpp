@@ -27,44 +27,58 @@ struct WfCall {
     unsigned long long seed;
     DRegion rg;
 };
-// Everything a path carries from one kernel to the next is ONE 128-byte record per slot (a cache line:
-// any kernel that touches a slot — in whatever order a compacted list hands slots out — moves whole
-// lines, never a sector for 8 useful bytes), plus a second line with what only some slots or some
-// kernels need: the pending diffuse weight, the confirmed hit, the candidate lists.
-struct __align__(16) WfSlot {           // 128 B
+// Path state, grouped by WHO touches it.  The confirm kernel walks the slots in index order, the other
+// kernels walk compacted lists (a gather): every group is a record of whole 32-byte sectors that its
+// readers need in full, so a gather never moves a sector for eight useful bytes, and the one group every
+// kernel reads (`head`, 16 bytes) is a plain array that the index-order walk reads coalesced.
+//   head[slot]  uint4: flags, sh_id, ncand, hit_prim
+//                 flags: alive / ended / pending Light::pdf / deferred to k_wf_exact | depth left << 8
+//                 sh_id: nearest analytic shape (kind << 28 | index) or 0xFFFFFFFF
+//                 ncand: trace -> confirm: #scene | #light << 8 | overflow bits; confirm -> shade: 0 / 1
+//                 hit_prim: nearest confirmed triangle
+struct __align__(16) WfRay {            // 64 B: trace (gather), confirm, shade_hit, regen
     double o[3], d[3];                  // the ray to trace / just traced
-    double T[3], L[3];                  // throughput, radiance so far
-    uint32_t flags, sh_id, ncand, hit_prim;     // one 16-byte vector: what the trace and confirm kernels read
-                                        // flags: alive / ended / pending Light::pdf / deferred to k_wf_exact | depth left << 8
-                                        // sh_id: nearest analytic shape (kind << 28 | index) or 0xFFFFFFFF
-                                        // ncand: trace -> confirm: #scene | #light << 8 | overflow bits; confirm -> shade: 0 / 1
-                                        // hit_prim: nearest confirmed triangle
     uint32_t sample, pix, ord, rng_pos; // the item in flight (sample of the call, pixel, ordinal in the region), RNG draws consumed
 };
-static_assert(sizeof(WfSlot) == 128, "WfSlot must be one cache line");
-struct __align__(16) WfAux {            // 128 B
-    double pv[3], pcos;                 // pending diffuse bounce: dot * color / PI, Cosine::pdf
-    double pimp, lres;                  // Light::pdf impact: the analytic lights' part, the complete sum
-    double res_t, res_u, res_v;         // exact (t, u, v) of hit_prim
-    double sh_t;                        // distance of sh_id
-    uint32_t cand[kWfCand], lcand[kWfCand];     // triangles that survived the fp32 pre-test (scene / light hierarchy)
+struct __align__(16) WfTL {             // 64 B: shade_hit, regen
+    double T[3], L[3];                  // throughput, radiance so far
+    double _spare[2];
 };
-static_assert(sizeof(WfAux) == 128, "WfAux must be one cache line");
+struct __align__(16) WfPend {           // 64 B: only slots with a pending diffuse bounce
+    double pv[3], pcos;                 // dot * color / PI, Cosine::pdf
+    double pimp, lres;                  // Light::pdf impact: the analytic lights' part, the complete sum
+    double _spare[2];
+};
+struct __align__(16) WfRes {            // 32 B: confirm / exact -> shade_hit
+    double t, u, v;                     // exact (t, u, v) of hit_prim
+    double sh_t;                        // distance of sh_id
+};
+struct __align__(16) WfCand {           // 64 B: trace -> confirm
+    uint32_t cand[kWfCand], lcand[kWfCand];     // triangles that survived the fp32 pre-test (scene / light hierarchy)
+    uint32_t _spare[4];
+};
+static_assert(sizeof(WfRay) == 64 && sizeof(WfTL) == 64 && sizeof(WfPend) == 64 && sizeof(WfRes) == 32 && sizeof(WfCand) == 64, "slot records are whole sectors");
 struct WfBuf {
     uint32_t n;                         // slots allocated
-    WfSlot *slot;
-    WfAux *aux;
+    uint4 *head;
+    WfRay *ray;
+    WfTL *tl;
+    WfPend *pend;
+    WfRes *res;
+    WfCand *cand;
     uint32_t *live;                     // n: the trace list, filled from both ends (front: fresh camera rays, back: bounced rays)
-    uint32_t *hit_list, *regen_list;    // n each: slots whose ray hit something (k_wf_shade_hit) / slots that need a new path (k_wf_regen)
+    uint32_t *hit_list;                 // n: slots whose ray hit something (k_wf_shade_hit)
+    uint32_t *regen_list[2];            // n each: slots that need a new path — [0] found by k_wf_confirm (ray escaped, or no path),
+                                        // [1] paths k_wf_shade_hit ended
     uint32_t *counts;                   // [0] trace list front, [1] back, [2] trace fetch cursor, [3] slots deferred to k_wf_exact,
-                                        // [4] hit list, [5] regen list — cleared together at the start of an iteration
+                                        // [4] hit list, [5] regen list 0, [6] regen list 1 — cleared together at the start of an iteration
     uint32_t *xlist;                    // n: slots deferred to k_wf_exact in this iteration
     uint32_t batch;                     // planes added to the image per k_wf_sum pass (amortises the read-modify-write)
     uint32_t ring;                      // planes in the ring of finished samples
     uint32_t n_px_cap;                  // pixels the side planes were allocated for (width * height)
     WfCall *call;                       // device: the parameters of the render call in flight (written by k_wf_init)
     double *side;                       // ring * 3 * n_px: radiance of finished samples: plane (sample % ring), component, ordinal
-    unsigned long long *item;           // [0] next unclaimed item, [1] claim limit, [2] items of this call
+    unsigned long long *item;           // [0] next unclaimed item, [1] claim limit, [2] items of this call, [3] items taken in this iteration
     uint32_t *plane;                    // [0] planes added to accum, [1] oldest sample in flight, [2] ring, [3] planes complete
 };
 size_t wf_bytes_per_slot();
@@ -81,8 +95,8 @@ int wf_trace_blocks(int device, bool smem_top);
 // instantiated graph of four iterations, re-captured only when a kernel argument changes (another
 // scene, other buffers).
 struct WfRuntime {
-    cudaStream_t side = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_shade = nullptr, ev_join = nullptr, ev_poll = nullptr;
+    cudaStream_t side = nullptr, side2 = nullptr;       // forked branches of an iteration: k_wf_exact + plan / sum; k_wf_regen next to k_wf_shade_hit
+    cudaEvent_t ev_fork = nullptr, ev_shade = nullptr, ev_join = nullptr, ev_poll = nullptr, ev_regen = nullptr;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     bool tried_graph = false;           // capture failed once for this key: plain launches from then on
@@ -91,12 +105,14 @@ struct WfRuntime {
     double *key_accum = nullptr;
     DCounters *key_ctr = nullptr;
     int key_blocks = 0;
+    unsigned key_grid[2] = {0, 0};
+    unsigned shade_blocks = 0, regen_blocks = 0;       // grids of k_wf_shade_hit / k_wf_regen (RT_WF_SHADE_BLOCKS / RT_WF_REGEN_BLOCKS per SM override, experiments)
     volatile uint32_t *host_live = nullptr;     // pinned, 6 words: what the host polls (counts[0..3], next item)
     uint64_t slots_override = 0;        // RT_WF_SLOTS (experiments), read once at rt_create
     bool smem_top = false;              // RT_WF_SMEM_TOP=1: the trace kernel stages the top levels of the hierarchy in shared memory
     uint64_t graph_builds = 0;          // diagnostics: how often the graph was (re)instantiated
 };
-cudaError_t wf_runtime_init(WfRuntime &rt);
+cudaError_t wf_runtime_init(WfRuntime &rt, int device);
 void wf_runtime_destroy(WfRuntime &rt);
 cudaError_t launch_render_wavefront(cudaStream_t st, WfRuntime &rt, const DScene &sc, uint32_t sample_begin, uint32_t sample_count,
                                     uint64_t seed, double *accum, DCounters *ctr, const WfBuf &b, int trace_blocks,

@@ -1,7 +1,7 @@
 // wavefront.cu — the wavefront scheduler of generate_image (reference src/main.rs:94-103).
 //
-// A pool of SLOTS, each holding one path in flight in a 128-byte record (ray, throughput, radiance,
-// RNG stream position; kernels.hpp WfSlot / WfAux), and a queue of ITEMS: item j = sample (j / n_px)
+// A pool of SLOTS, each holding one path in flight (ray, throughput, radiance, RNG stream position:
+// records of whole sectors grouped by the kernels that touch them, kernels.hpp), and a queue of ITEMS: item j = sample (j / n_px)
 // of the pixel with ordinal (j % n_px).  A slot whose path has ended takes the next item, whichever
 // pixel it belongs to, so all slots stay busy until the last sample of the call has been started.
 // One iteration — every kernel after the first walks a COMPACTED LIST, so its warps are full of
@@ -17,9 +17,12 @@
 //                   raytrace_impl (src/raytrace.rs:12-60); the RNG draws of the bounce are computed
 //                   ahead while the warp is converged.  Paths that go on are appended to the back of
 //                   the trace list, paths that end to the regen list;
-//   k_wf_regen      regen list: adds the background to escaped paths, parks the finished sample's
-//                   radiance in the plane of its sample index, claims the next item and starts its
-//                   camera ray (front of the trace list, runs of neighbouring pixels);
+//   k_wf_regen      regen lists: adds the background to escaped paths, parks the finished sample's
+//                   radiance in the plane of its sample index, takes the next item and starts its
+//                   camera ray (front of the trace list, runs of neighbouring pixels).  Runs twice: for
+//                   the slots k_wf_confirm found (on a forked branch, NEXT TO k_wf_shade_hit — both
+//                   kernels wait for memory most of the time) and then for the paths the shade kernel
+//                   ended.  Items are handed out by position in the list: no atomic operation;
 //   k_wf_plan / k_wf_sum  complete sample planes are added to the accumulation buffer in sample
 //                   order — main.rs:100-103's order, so the sum is the megakernel's bit for bit;
 //   k_wf_trace      persistent warps, fp32 only.  Each lane walks the culling hierarchy for one ray
@@ -51,76 +54,102 @@ constexpr uint32_t kFlagPendLight = 4u;       // the weight of the last diffuse 
 constexpr uint32_t kFlagExactPending = 16u;   // handed to k_wf_exact in this iteration; cleared by the next confirm pass
 constexpr uint32_t kOverflowClosest = 0x10000u, kOverflowLight = 0x20000u;
 constexpr uint32_t kNoShape = 0xFFFFFFFFu;
-enum { kCntFront = 0, kCntBack = 1, kCntCursor = 2, kCntExact = 3, kCntHit = 4, kCntRegen = 5, kCntWords = 6 };
+enum { kCntFront = 0, kCntBack = 1, kCntCursor = 2, kCntExact = 3, kCntHit = 4, kCntRegen = 5 /* and 6: the two regen lists */, kCntWords = 8 };
 
 // ---- slot records: 16-byte vector access ---------------------------------------------------------
-// WfSlot as double2[6] + uint4[2]: (o.x o.y) (o.z d.x) (d.y d.z) (T.x T.y) (T.z L.x) (L.y L.z) | head | item
-RT_D void ld_ray(const WfSlot *s, d3 &o, d3 &d) {
+// WfRay as double2[3] + uint4: (o.x o.y) (o.z d.x) (d.y d.z) | sample, pix, ord, rng_pos
+RT_D void ld_ray(const WfRay *s, d3 &o, d3 &d) {
     const double2 *p = reinterpret_cast<const double2 *>(s);
     const double2 q0 = p[0], q1 = p[1], q2 = p[2];
     o = mk3(q0.x, q0.y, q1.x);
     d = mk3(q1.y, q2.x, q2.y);
 }
-RT_D void st_ray(WfSlot *s, d3 o, d3 d) {
+RT_D void st_ray(WfRay *s, d3 o, d3 d) {
     double2 *p = reinterpret_cast<double2 *>(s);
     p[0] = make_double2(o.x, o.y); p[1] = make_double2(o.z, d.x); p[2] = make_double2(d.y, d.z);
 }
-RT_D void ld_TL(const WfSlot *s, d3 &T, d3 &L) {
+RT_D uint4 ld_item(const WfRay *s) { return reinterpret_cast<const uint4 *>(s)[3]; }       // sample, pix, ord, rng_pos
+RT_D void st_item(WfRay *s, uint4 v) { reinterpret_cast<uint4 *>(s)[3] = v; }
+// WfTL as double2[3]: (T.x T.y) (T.z L.x) (L.y L.z)
+RT_D void ld_TL(const WfTL *s, d3 &T, d3 &L) {
     const double2 *p = reinterpret_cast<const double2 *>(s);
-    const double2 q3 = p[3], q4 = p[4], q5 = p[5];
-    T = mk3(q3.x, q3.y, q4.x);
-    L = mk3(q4.y, q5.x, q5.y);
+    const double2 q0 = p[0], q1 = p[1], q2 = p[2];
+    T = mk3(q0.x, q0.y, q1.x);
+    L = mk3(q1.y, q2.x, q2.y);
 }
-RT_D void st_TL(WfSlot *s, d3 T, d3 L) {
+RT_D void st_TL(WfTL *s, d3 T, d3 L) {
     double2 *p = reinterpret_cast<double2 *>(s);
-    p[3] = make_double2(T.x, T.y); p[4] = make_double2(T.z, L.x); p[5] = make_double2(L.y, L.z);
+    p[0] = make_double2(T.x, T.y); p[1] = make_double2(T.z, L.x); p[2] = make_double2(L.y, L.z);
 }
-RT_D uint4 ld_head(const WfSlot *s) { return reinterpret_cast<const uint4 *>(s)[6]; }      // flags, sh_id, ncand, hit_prim
-RT_D void st_head(WfSlot *s, uint4 h) { reinterpret_cast<uint4 *>(s)[6] = h; }
-RT_D uint4 ld_item(const WfSlot *s) { return reinterpret_cast<const uint4 *>(s)[7]; }      // sample, pix, ord, rng_pos
-RT_D void st_item(WfSlot *s, uint4 v) { reinterpret_cast<uint4 *>(s)[7] = v; }
-// WfAux as double2[5] + candidates: (pv.x pv.y) (pv.z pcos) (pimp lres) (res_t res_u) (res_v sh_t)
-RT_D void ld_pending(const WfAux *a, Pending &pd, double &lres) {
+// WfPend as double2[3]: (pv.x pv.y) (pv.z pcos) (pimp lres)
+RT_D void ld_pending(const WfPend *a, Pending &pd, double &lres) {
     const double2 *p = reinterpret_cast<const double2 *>(a);
     const double2 q0 = p[0], q1 = p[1];
     pd.v = mk3(q0.x, q0.y, q1.x);
     pd.cos_pdf = q1.y;
     lres = a->lres;
 }
-RT_D void st_pending(WfAux *a, const Pending &pd, double pimp) {
+RT_D void st_pending(WfPend *a, const Pending &pd, double pimp) {
     double2 *p = reinterpret_cast<double2 *>(a);
     p[0] = make_double2(pd.v.x, pd.v.y); p[1] = make_double2(pd.v.z, pd.cos_pdf);
     a->pimp = pimp;
 }
+// fields of head[slot]
+RT_D uint32_t *head_flags(uint4 *h) { return &h->x; }
+RT_D uint32_t *head_ncand(uint4 *h) { return &h->z; }
+RT_D uint32_t *head_hit_prim(uint4 *h) { return &h->w; }
 
-__device__ __forceinline__ void flush_counters_wf(const Cnt &c, DCounters *out) {
-    constexpr int kN = 4;
-    unsigned long long v[kN] = {c.seg, c.lray, c.paths, c.xf};
-    unsigned long long *dst[kN] = {&out->segments, &out->light_pdf_rays, &out->paths, &out->exact_fallbacks};
+// Per-block event counters and list appends: one global atomic per BLOCK and per counter.  (Per warp,
+// the 65 000 warps of a kernel that does little else queue up on a handful of addresses.)
+struct BlockShared {
+    unsigned long long ctr[4];          // segments, light-pdf rays, paths, exact fallbacks
+    uint32_t cnt[2][4], base[2];        // two lists: entries per warp, position of the block's run
+    uint32_t oldest;
+};
+RT_D void block_shared_init(BlockShared &s) {
+    if (threadIdx.x < 4) s.ctr[threadIdx.x] = 0ull;
+    if (threadIdx.x == 4) s.oldest = 0xFFFFFFFFu;
+    __syncthreads();
+}
+// warp-level sum into shared memory; block_shared_flush publishes after the last one
+RT_D void block_count(BlockShared &s, const Cnt &c) {
+    unsigned long long v[4] = {c.seg, c.lray, c.paths, c.xf};
     const int lane = threadIdx.x & 31;
 #pragma unroll
-    for (int k = 0; k < kN; ++k) {
-        unsigned long long s = v[k];
-        for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(kFull, s, off);
-        if (lane == 0 && s) atomicAdd(dst[k], s);
+    for (int k = 0; k < 4; ++k) {
+        unsigned long long x = v[k];
+        for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xFFFFFFFFu, x, off);
+        if (lane == 0 && x) atomicAdd(&s.ctr[k], x);
     }
 }
-// Stream compaction: ballot + prefix sum inside the warp, one atomic per warp reserves the room.
-// Called by all 32 lanes.  Entries of one warp stay together and in lane order.
-RT_D void warp_append(uint32_t *list, uint32_t *count, bool pred, uint32_t value, int lane) {
-    const unsigned m = __ballot_sync(kFull, pred);
-    if (!m) return;
-    const int leader = __ffs(m) - 1;
-    uint32_t base = 0;
-    if (lane == leader) base = atomicAdd(count, (uint32_t)__popc(m));
-    base = __shfl_sync(kFull, base, leader);
-    if (pred) list[base + __popc(m & ((1u << lane) - 1u))] = value;
-}
-// the oldest sample still in flight: every plane before it is complete (k_wf_plan)
-RT_D void note_oldest_sample(const WfBuf &b, bool in_flight, uint32_t smp, int lane) {
+RT_D void block_note_oldest(BlockShared &s, bool in_flight, uint32_t smp) {
     uint32_t m = in_flight ? smp : 0xFFFFFFFFu;
-    for (int off = 16; off > 0; off >>= 1) m = min(m, __shfl_xor_sync(kFull, m, off));
-    if (lane == 0 && m != 0xFFFFFFFFu) atomicMin(&b.plane[1], m);
+    for (int off = 16; off > 0; off >>= 1) m = min(m, __shfl_xor_sync(0xFFFFFFFFu, m, off));
+    if ((threadIdx.x & 31) == 0 && m != 0xFFFFFFFFu) atomicMin(&s.oldest, m);
+}
+RT_D void block_shared_flush(BlockShared &s, DCounters *out, uint32_t *oldest) {
+    __syncthreads();
+    unsigned long long *dst[4] = {&out->segments, &out->light_pdf_rays, &out->paths, &out->exact_fallbacks};
+    if (threadIdx.x < 4 && s.ctr[threadIdx.x]) atomicAdd(dst[threadIdx.x], s.ctr[threadIdx.x]);
+    if (threadIdx.x == 4 && s.oldest != 0xFFFFFFFFu) atomicMin(oldest, s.oldest);      // the oldest sample still in flight (k_wf_plan)
+}
+// Stream compaction into two lists at once: ballots + prefix sums, one atomic per block and list.
+// Called by every thread of the block; pos = where this thread's entry goes (meaningful when its
+// predicate holds).  Entries of a block stay together, in thread order.
+RT_D void block_append2(BlockShared &s, uint32_t *count_a, bool pa, uint32_t &pos_a, uint32_t *count_b, bool pb, uint32_t &pos_b) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned ma = __ballot_sync(0xFFFFFFFFu, pa), mb = __ballot_sync(0xFFFFFFFFu, pb);
+    if (lane == 0) { s.cnt[0][wid] = __popc(ma); s.cnt[1][wid] = __popc(mb); }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        const uint32_t tot = s.cnt[threadIdx.x][0] + s.cnt[threadIdx.x][1] + s.cnt[threadIdx.x][2] + s.cnt[threadIdx.x][3];
+        s.base[threadIdx.x] = tot ? atomicAdd(threadIdx.x ? count_b : count_a, tot) : 0u;
+    }
+    __syncthreads();
+    pos_a = s.base[0]; pos_b = s.base[1];
+    for (int w = 0; w < wid; ++w) { pos_a += s.cnt[0][w]; pos_b += s.cnt[1][w]; }
+    const unsigned below = (1u << lane) - 1u;
+    pos_a += __popc(ma & below); pos_b += __popc(mb & below);
 }
 
 // The trace list is filled from BOTH ends: slots whose ray is a fresh camera ray go to the front,
@@ -153,12 +182,12 @@ RT_D uint32_t region_tile_pixel(const DRegion &rg, uint32_t width, uint32_t i) {
 __global__ void k_wf_init(WfBuf b, WfCall cl, uint32_t sample_count) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_px = cl.n_px;
-    if (i < cl.n_slots) st_head(b.slot + i, make_uint4(0u, kNoShape, 0u, 0u));      // an empty slot: the first confirm pass sends it to k_wf_regen
+    if (i < cl.n_slots) b.head[i] = make_uint4(0u, kNoShape, 0u, 0u);      // an empty slot: the first confirm pass sends it to k_wf_regen
     if (i == 0) {
         *b.call = cl;                                   // what the kernels of this call read instead of arguments
         for (int k = 0; k < kCntWords; ++k) b.counts[k] = 0;
         const unsigned long long total = (unsigned long long)n_px * sample_count, first = (unsigned long long)(b.ring - cl.reserve) * n_px;
-        b.item[0] = 0; b.item[1] = first < total ? first : total; b.item[2] = total;
+        b.item[0] = 0; b.item[1] = first < total ? first : total; b.item[2] = total; b.item[3] = 0;
         b.plane[0] = 0; b.plane[1] = 0xFFFFFFFFu; b.plane[2] = b.ring; b.plane[3] = 0;
     }
 }
@@ -186,22 +215,21 @@ __global__ void __launch_bounds__(128, WF_CONFIRM_MINB) k_wf_confirm(DScene sc, 
     __shared__ uint32_t s_warp[4];
     __shared__ double s_ray[6][128];
     __shared__ double s_t[kConfirmPairs], s_u[kConfirmPairs], s_v[kConfirmPairs];   // phase 1 -> phase 2
+    __shared__ BlockShared s_blk;
     const uint32_t tid = threadIdx.x, slot0 = blockIdx.x * 128, i = slot0 + tid, lane = tid & 31, wid = tid >> 5;
     const uint32_t n_slots = b.call->n_slots;
     if (slot0 >= n_slots) return;                       // the grid covers the buffer's capacity
-    WfSlot *const sp = b.slot + i;
-    WfAux *const ap = b.aux + i;
     uint32_t nc = 0, nl = 0, flags = 0, nc_all = 0, sh_id = kNoShape;
     bool mine = false;                                  // this thread's slot has results to fold
     int cls = 0;                                        // 1: hit list, 2: regen list
     if (i < n_slots) {
-        const uint4 h = ld_head(sp);
+        const uint4 h = b.head[i];
         flags = h.x; sh_id = h.y; nc_all = h.z;
         if (flags & kFlagExactPending) {
             // k_wf_exact answered this slot during the last iteration (the graph joined since):
             // its results are final, the shade kernel takes them in this iteration
             flags &= ~kFlagExactPending;
-            sp->flags = flags;
+            *head_flags(b.head + i) = flags;
             cls = ((nc_all & 0xFFu) || sh_id != kNoShape) ? 1 : 2;
         } else if (flags & kFlagAlive) {
             mine = true;
@@ -209,7 +237,7 @@ __global__ void __launch_bounds__(128, WF_CONFIRM_MINB) k_wf_confirm(DScene sc, 
             nl = ((nc_all & kOverflowLight) || !(flags & kFlagPendLight)) ? 0u : ((nc_all >> 8) & 0xFFu);
             if (nc + nl) {
                 d3 o, d;
-                ld_ray(sp, o, d);
+                ld_ray(b.ray + i, o, d);
                 s_ray[0][tid] = o.x; s_ray[1][tid] = o.y; s_ray[2][tid] = o.z;
                 s_ray[3][tid] = d.x; s_ray[4][tid] = d.y; s_ray[5][tid] = d.z;
             }
@@ -240,10 +268,10 @@ __global__ void __launch_bounds__(128, WF_CONFIRM_MINB) k_wf_confirm(DScene sc, 
     for (uint32_t e = tid; e < min(total, kConfirmPairs); e += 128) {
         const uint32_t pr = s_pair[e], owner = pr & 127u, k = (pr >> 7) & 7u;
         const bool light = (pr & 0x400u) != 0;
-        const WfAux *oa = b.aux + slot0 + owner;
+        const WfCand *oc = b.cand + slot0 + owner;
         const d3 o = mk3(s_ray[0][owner], s_ray[1][owner], s_ray[2][owner]);
         const d3 d = mk3(s_ray[3][owner], s_ray[4][owner], s_ray[5][owner]);
-        const uint32_t prim = light ? oa->lcand[k] : oa->cand[k];
+        const uint32_t prim = light ? oc->lcand[k] : oc->cand[k];
         double t, u, v;
         const DTriI *tp = (light ? sc.ltri_i : sc.tri_i) + prim;
         const bool hit = tri_exact(tp, o, d, t, u, v);
@@ -269,13 +297,13 @@ __global__ void __launch_bounds__(128, WF_CONFIRM_MINB) k_wf_confirm(DScene sc, 
         // is not worth a second fp32 search: the exact traversal answers the ray
         bool need_exact = (nc_all & (kOverflowClosest | kOverflowLight)) != 0 || base + nl + nc > kConfirmPairs;
         if ((flags & kFlagPendLight) && !need_exact) {
-            double impact = ap->pimp;
+            double impact = b.pend[i].pimp;
             for (uint32_t k = 0; k < nl; ++k) {
                 const double term = s_t[base + k];
                 if (term == -2.0) need_exact = true;
                 else if (term != -1.0) impact += term;
             }
-            ap->lres = impact;
+            b.pend[i].lres = impact;
         }
         bool tri_hit = false;
         if (!need_exact) {
@@ -284,33 +312,35 @@ __global__ void __launch_bounds__(128, WF_CONFIRM_MINB) k_wf_confirm(DScene sc, 
             for (uint32_t k = 0; k < nc; ++k) {
                 const uint32_t e = base + nl + k;
                 const double u = s_u[e];
-                if (u != -1.0) fbest_take(fb, s_t[e], u, s_v[e], ap->cand[k], u == -2.0);
+                if (u != -1.0) fbest_take(fb, s_t[e], u, s_v[e], b.cand[i].cand[k], u == -2.0);
             }
             if (fb.has) {
                 const d3 o = mk3(s_ray[0][tid], s_ray[1][tid], s_ray[2][tid]), d = mk3(s_ray[3][tid], s_ray[4][tid], s_ray[5][tid]);
                 need_exact = fbest_needs_exact(fb, o, d, (double)sc.ftris.bound);
-                ap->res_t = fb.t; ap->res_u = fb.u; ap->res_v = fb.v;
+                b.res[i].t = fb.t; b.res[i].u = fb.u; b.res[i].v = fb.v;
             }
             if (!need_exact) {
-                sp->ncand = fb.has ? 1u : 0u;
-                sp->hit_prim = fb.prim;
+                // ncand and hit_prim are neighbours: one 8-byte store
+                *reinterpret_cast<uint2 *>(head_ncand(b.head + i)) = make_uint2(fb.has ? 1u : 0u, fb.prim);
                 tri_hit = fb.has;
             }
         }
         if (need_exact) {
             // Nothing is shaded or traced for the slot in this iteration: k_wf_exact answers both searches
             // with the reference's own traversal meanwhile, the next confirm pass picks the slot up.
-            sp->flags = flags | kFlagExactPending;
+            *head_flags(b.head + i) = flags | kFlagExactPending;
             b.xlist[atomicAdd(&b.counts[kCntExact], 1u)] = i;
             atomicAdd(&ctr->exact_fallbacks, 1ull);     // rare
-            atomicMin(&b.plane[1], sp->sample);         // still in flight
+            atomicMin(&b.plane[1], b.ray[i].sample);    // still in flight
         } else {
             cls = (tri_hit || sh_id != kNoShape) ? 1 : 2;
         }
     }
-    // ---- phase 3: the lists the next two kernels walk
-    warp_append(b.hit_list, &b.counts[kCntHit], cls == 1, i, (int)lane);
-    warp_append(b.regen_list, &b.counts[kCntRegen], cls == 2, i, (int)lane);
+    // ---- phase 3: the lists the next kernels walk
+    uint32_t pos_hit, pos_regen;
+    block_append2(s_blk, &b.counts[kCntHit], cls == 1, pos_hit, &b.counts[kCntRegen], cls == 2, pos_regen);
+    if (cls == 1) b.hit_list[pos_hit] = i;
+    if (cls == 2) b.regen_list[0][pos_regen] = i;
 }
 
 // ---- shade: the slots whose ray hit something ----------------------------------------------------
@@ -319,22 +349,30 @@ __global__ void __launch_bounds__(128, WF_CONFIRM_MINB) k_wf_confirm(DScene sc, 
 #endif
 template <bool SHAPES>
 __global__ void __launch_bounds__(128, SHAPES ? 4 : WF_SHADE_MINB) k_wf_shade_hit(DScene sc, WfBuf b, DCounters *ctr) {
+    // the list in chunks of 128 entries (one chunk per block unless RT_WF_SHADE_BLOCKS bounds the grid)
     const uint32_t n = b.counts[kCntHit];
-    if (blockIdx.x * 128u >= n) return;                 // the grid covers the buffer's capacity
-    const uint32_t i = blockIdx.x * 128u + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    const bool on = i < n;
+    if (blockIdx.x * 128u >= n) return;
+    __shared__ BlockShared s_blk;
+    block_shared_init(s_blk);
     Cnt c;
+    for (uint32_t chunk = blockIdx.x * 128u; chunk < n; chunk += gridDim.x * 128u) {
+    const uint32_t i = chunk + threadIdx.x;
+    const bool on = i < n;
+    // The lanes of a warp part ways twice — a pending weight or none, light sampling or cosine sampling —
+    // and left to itself the compiler keeps the four groups apart until the end of the kernel (ncu: 12.5 of
+    // 32 lanes with every lane holding a hit).  Warp barriers over the lanes that hold an entry bring them
+    // back together after each of the two.
+    const unsigned mon = __ballot_sync(kFull, on);
     bool go_on = false, ended = false;
     uint32_t slot = 0, smp = 0;
     if (on) {
         slot = b.hit_list[i];
-        WfSlot *const sp = b.slot + slot;
-        WfAux *const ap = b.aux + slot;
+        WfRay *const rp = b.ray + slot;
+        WfTL *const tp = b.tl + slot;
         d3 o, d, T, L;
-        ld_ray(sp, o, d);
-        ld_TL(sp, T, L);
-        const uint4 h = ld_head(sp), it = ld_item(sp);
+        ld_ray(rp, o, d);
+        ld_TL(tp, T, L);
+        const uint4 h = b.head[slot], it = ld_item(rp);
         const uint32_t flags = h.x;
         smp = it.x;
         uint32_t left = (flags >> 8) & 0xFFu;
@@ -347,21 +385,22 @@ __global__ void __launch_bounds__(128, SHAPES ? 4 : WF_SHADE_MINB) k_wf_shade_hi
         bool pend_light = false;
         if (flags & kFlagPendLight) {                   // finish the previous diffuse bounce: Light::pdf of THIS ray
             double impact;                              // folded by k_wf_confirm or answered by k_wf_exact
-            ld_pending(ap, pd, impact);
+            ld_pending(b.pend + slot, pd, impact);
             if (!apply_pending(pd, impact / (double)sc.n_lights, T)) ended = true;
         }
+        __syncwarp(mon);
         if (!ended) {
             ShapeBest sb;
             sb.has = SHAPES && h.y != kNoShape; sb.kind = sb.has ? (int)(h.y >> 28) : -1; sb.prim = h.y & 0x0FFFFFFFu;
-            sb.t = sb.has ? ap->sh_t : 0.0;
+            sb.t = sb.has ? b.res[slot].sh_t : 0.0;
             FBest fb;
             fbest_clear(fb);
             bool skip;
             (void)shapes_tmax(sb, skip);
             if (!skip && (h.z & 0xFFu)) {               // the nearest confirmed triangle, folded by k_wf_confirm
-                const double2 r = reinterpret_cast<const double2 *>(ap)[3];
+                const double2 r = reinterpret_cast<const double2 *>(b.res + slot)[0];
                 fb.has = true; fb.prim = h.w;
-                fb.t = r.x; fb.u = r.y; fb.v = ap->res_v;
+                fb.t = r.x; fb.u = r.y; fb.v = b.res[slot].v;
             }
             ++c.seg;
             const SceneHit hit = finish_hit<SHAPES>(sc, o, d, sb, fb);
@@ -378,41 +417,39 @@ __global__ void __launch_bounds__(128, SHAPES ? 4 : WF_SHADE_MINB) k_wf_shade_hi
                 pend_light = r == kPathPendingPdf;
             }
         }
+        __syncwarp(mon);
         if (ended) {
-            // k_wf_regen parks the radiance in the plane of the sample and gives the slot its next item
-            st_TL(sp, T, L);
-            sp->flags = kFlagEnded;
+            // the second k_wf_regen pass parks the radiance in the plane of the sample and gives the slot its next item
+            st_TL(tp, T, L);
+            *head_flags(b.head + slot) = kFlagEnded;
         } else {                                        // hand the ray to the trace kernel
             uint32_t sh_id = kNoShape;
             if (SHAPES) {
                 const ShapeBest nb = shapes_closest(sc, o, d, c);
                 sh_id = nb.has ? (((uint32_t)nb.kind << 28) | nb.prim) : kNoShape;
-                if (nb.has) ap->sh_t = nb.t;
+                if (nb.has) b.res[slot].sh_t = nb.t;
             }
             if (pend_light) {
                 ++c.lray;
-                st_pending(ap, pd, SHAPES ? light_shapes_impact(sc, o, d, c) : 0.0);
+                st_pending(b.pend + slot, pd, SHAPES ? light_shapes_impact(sc, o, d, c) : 0.0);
             }
-            st_ray(sp, o, d);
-            st_TL(sp, T, L);
-            st_head(sp, make_uint4(kFlagAlive | (pend_light ? kFlagPendLight : 0u) | (left << 8), sh_id, 0u, 0u));
-            sp->rng_pos = rng.pos;
+            st_ray(rp, o, d);
+            rp->rng_pos = rng.pos;
+            st_TL(tp, T, L);
+            b.head[slot] = make_uint4(kFlagAlive | (pend_light ? kFlagPendLight : 0u) | (left << 8), sh_id, 0u, 0u);
             go_on = true;
         }
     }
-    // bounced rays go to the BACK of the trace list
-    {
-        const unsigned m = __ballot_sync(kFull, go_on);
-        if (m) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(&b.counts[kCntBack], (uint32_t)__popc(m));
-            base = __shfl_sync(kFull, base, 0);
-            if (go_on) b.live[b.n - 1u - (base + __popc(m & ((1u << lane) - 1u)))] = slot;
-        }
+    // bounced rays go to the BACK of the trace list, ended paths to the second regen list
+    uint32_t pos_back, pos_regen;
+    block_append2(s_blk, &b.counts[kCntBack], go_on, pos_back, &b.counts[kCntRegen + 1], ended, pos_regen);
+    if (go_on) b.live[b.n - 1u - pos_back] = slot;
+    if (ended) b.regen_list[1][pos_regen] = slot;
+    block_note_oldest(s_blk, go_on, smp);
+    __syncthreads();                                    // block_append2's shared words are reused by the next chunk
     }
-    warp_append(b.regen_list, &b.counts[kCntRegen], ended, slot, lane);
-    note_oldest_sample(b, go_on, smp, lane);
-    flush_counters_wf(c, ctr);
+    block_count(s_blk, c);
+    block_shared_flush(s_blk, ctr, &b.plane[1]);
 }
 
 // ---- regen: escaped rays, ended paths, empty slots -> the next item -----------------------------
@@ -421,33 +458,64 @@ __global__ void __launch_bounds__(128, SHAPES ? 4 : WF_SHADE_MINB) k_wf_shade_hi
 // image.  What keeps the result the megakernel's bit for bit is the ORDER of the additions: every
 // finished sample is parked in the plane of its sample index, and complete planes are added to the
 // accumulation buffer one after the other, sample 0 first (main.rs:100-103).
+// Items are handed out BY POSITION: entry i of regen list 0 takes item next + i, entry i of list 1
+// item next + |list 0| + i, as far as the claim limit (the planes of the ring still being filled)
+// allows; the fresh camera ray goes to the same position of the trace list's front.  Every thread
+// derives this from the list lengths — no atomic operation, and the camera rays of neighbouring
+// threads are neighbouring pixels (8x4 tiles).  k_wf_plan moves `next` on afterwards.
+struct RegenPlan {
+    unsigned long long first;           // first item of this pass
+    uint32_t grant, front;              // items this pass may take; trace-list position of its first camera ray
+    uint32_t granted_so_far;            // grant of both passes up to and including this one
+};
+RT_D RegenPlan regen_plan(const WfBuf &b, int pass) {
+    const unsigned long long next = b.item[0], limit = b.item[1];
+    const unsigned long long room = limit > next ? limit - next : 0ull;
+    const uint32_t n0 = b.counts[kCntRegen], g0 = (uint32_t)min((unsigned long long)n0, room);
+    RegenPlan p;
+    if (pass == 0) { p.first = next; p.grant = g0; p.front = 0u; p.granted_so_far = g0; return p; }
+    const uint32_t n1 = b.counts[kCntRegen + 1], g1 = (uint32_t)min((unsigned long long)n1, room - g0);
+    p.first = next + g0; p.grant = g1; p.front = g0; p.granted_so_far = g0 + g1;
+    return p;
+}
 template <bool SHAPES>
-__global__ void __launch_bounds__(128, SHAPES ? 4 : 8) k_wf_regen(DScene sc, WfBuf b, DCounters *ctr) {
-    const uint32_t n = b.counts[kCntRegen];
+__global__ void __launch_bounds__(128, SHAPES ? 4 : 8) k_wf_regen(DScene sc, WfBuf b, DCounters *ctr, int pass) {
+    const uint32_t n = b.counts[kCntRegen + pass];
+    const RegenPlan plan = regen_plan(b, pass);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && pass == 1) {
+        // the bookkeeping of the whole iteration's claims (this block always runs, whatever the list lengths)
+        b.item[3] = plan.granted_so_far;                // k_wf_plan adds it to `next`
+        b.counts[kCntFront] = plan.granted_so_far;      // the trace list's front is complete
+        if (plan.granted_so_far) {
+            atomicAdd(&ctr->paths, (unsigned long long)plan.granted_so_far);
+            atomicMin(&b.plane[1], (uint32_t)(b.item[0] / b.call->n_px));      // the oldest of the samples just started
+        }
+    }
     if (blockIdx.x * 128u >= n) return;
-    const uint32_t i = blockIdx.x * 128u + threadIdx.x;
+    __shared__ BlockShared s_blk;
+    block_shared_init(s_blk);
     const int lane = threadIdx.x & 31;
-    const bool on = i < n;
     const WfCall cl = *b.call;                          // uniform: one broadcast load
     const uint32_t n_px = cl.n_px;
     Cnt c;
-    uint32_t slot = 0, old_flags = 0;
-    WfSlot *sp = nullptr;
+    for (uint32_t chunk = blockIdx.x * 128u; chunk < n; chunk += gridDim.x * 128u) {
+    const uint32_t i = chunk + threadIdx.x;
+    const bool on = i < n;
     if (on) {
-        slot = b.regen_list[i];
-        sp = b.slot + slot;
-        const uint4 h = ld_head(sp);
-        old_flags = h.x;
+        const uint32_t slot = b.regen_list[pass][i];
+        WfRay *const rp = b.ray + slot;
+        WfTL *const tp = b.tl + slot;
+        const uint32_t old_flags = b.head[slot].x;
         if (old_flags & (kFlagAlive | kFlagEnded)) {
-            const uint4 it = ld_item(sp);
+            const uint4 it = ld_item(rp);
             d3 T, L;
-            ld_TL(sp, T, L);
+            ld_TL(tp, T, L);
             if (old_flags & kFlagAlive) {               // the ray escaped: raytrace_impl returns bg_color (raytrace.rs:14)
                 bool counts_as_segment = true;
                 if (old_flags & kFlagPendLight) {       // ... once the weight of the bounce that shot it is known
                     Pending pd;
                     double impact;
-                    ld_pending(b.aux + slot, pd, impact);
+                    ld_pending(b.pend + slot, pd, impact);
                     counts_as_segment = apply_pending(pd, impact / (double)sc.n_lights, T);
                 }
                 if (counts_as_segment) {
@@ -461,38 +529,12 @@ __global__ void __launch_bounds__(128, SHAPES ? 4 : 8) k_wf_regen(DScene sc, WfB
             double *side = b.side + (size_t)(it.x % b.ring) * 3u * n_px + it.z;
             side[0] = L.x; side[n_px] = L.y; side[2u * (size_t)n_px] = L.z;
         }
-    }
-    // ---- claim: item j = sample (j / n_px) of the pixel with ordinal (j % n_px) in the region's
-    // tile order.  One atomicAdd per warp hands out a run of consecutive items — the lanes of a warp
-    // that start a path together get neighbouring pixels — and the claims never pass the limit (the
-    // planes of the ring that are still being filled) by more than one item per slot.
-    bool fresh = false;
-    uint32_t smp = 0;
-    const unsigned mw = __ballot_sync(kFull, on);
-    {
-        unsigned long long first = 0;
-        uint32_t got = 0, s0 = 0, o0 = 0;
-        if (lane == 0 && mw) {
-            // no retry loop (a compare-and-swap on this one address from 65 000 warps at once does not
-            // scale).  The limit is checked on a plain read first, so all the warps of one launch
-            // together can overshoot it by at most one item per slot = one plane (n_slots <= n_px):
-            // k_wf_plan keeps two planes of the ring in reserve.
-            const unsigned long long limit = b.item[1], total = b.item[2];
-            const uint32_t cnt = (uint32_t)__popc(mw);
-            if (*(volatile unsigned long long *)b.item < limit) {
-                first = atomicAdd(b.item, (unsigned long long)cnt);
-                got = first < total ? (uint32_t)min((unsigned long long)cnt, total - first) : 0u;
-            }
-            s0 = (uint32_t)(first / n_px);
-            o0 = (uint32_t)(first - (unsigned long long)s0 * n_px);
-        }
-        got = __shfl_sync(kFull, got, 0);
-        s0 = __shfl_sync(kFull, s0, 0);
-        o0 = __shfl_sync(kFull, o0, 0);
-        const uint32_t rank = __popc(mw & ((1u << lane) - 1u));
-        if (on && rank < got) {
-            smp = s0;
-            unsigned long long oo = (unsigned long long)o0 + rank;
+        if (i < plan.grant) {
+            // item j = sample (j / n_px) of the pixel with ordinal (j % n_px) in the region's tile order;
+            // one 64-bit division per warp, the lanes count on from its first lane
+            const unsigned long long j0 = plan.first + (i - (uint32_t)lane);
+            uint32_t smp = (uint32_t)(j0 / n_px);
+            unsigned long long oo = j0 - (unsigned long long)smp * n_px + (uint32_t)lane;
             while (oo >= n_px) { oo -= n_px; ++smp; }
             const uint32_t ord = (uint32_t)oo;
             const uint32_t pix = region_tile_pixel(cl.rg, sc.width, ord);
@@ -502,35 +544,35 @@ __global__ void __launch_bounds__(128, SHAPES ? 4 : 8) k_wf_regen(DScene sc, WfB
             const double jx = rng.range(0.0, 1.0), jy = rng.range(0.0, 1.0);       // camera.rs:49-50
             d3 o, d;
             camera_ray(sc.cam, pix % sc.width, pix / sc.width, jx, jy, o, d);
-            ++c.paths;
             uint32_t sh_id = kNoShape;
             if (SHAPES) {
                 const ShapeBest nb = shapes_closest(sc, o, d, c);
                 sh_id = nb.has ? (((uint32_t)nb.kind << 28) | nb.prim) : kNoShape;
-                if (nb.has) b.aux[slot].sh_t = nb.t;
+                if (nb.has) b.res[slot].sh_t = nb.t;
             }
-            st_ray(sp, o, d);
-            st_TL(sp, mk3(1.0, 1.0, 1.0), mk3(0.0, 0.0, 0.0));
-            st_head(sp, make_uint4(kFlagAlive | ((uint32_t)sc.ray_depth << 8), sh_id, 0u, 0u));
-            st_item(sp, make_uint4(smp, pix, ord, rng.pos));
-            fresh = true;
-        } else if (on && old_flags != 0u) {
-            sp->flags = 0u;                             // nothing to claim right now: an empty slot, asks again in the next iteration
+            st_ray(rp, o, d);
+            st_item(rp, make_uint4(smp, pix, ord, rng.pos));
+            st_TL(tp, mk3(1.0, 1.0, 1.0), mk3(0.0, 0.0, 0.0));
+            b.head[slot] = make_uint4(kFlagAlive | ((uint32_t)sc.ray_depth << 8), sh_id, 0u, 0u);
+            b.live[plan.front + i] = slot;              // fresh camera rays: the FRONT of the trace list, in item order
+        } else if (old_flags != 0u) {
+            *head_flags(b.head + slot) = 0u;            // nothing to take right now: an empty slot, asks again in the next iteration
         }
     }
-    // fresh camera rays go to the FRONT of the trace list, in claim order
-    warp_append(b.live, &b.counts[kCntFront], fresh, slot, lane);
-    note_oldest_sample(b, fresh, smp, lane);
-    flush_counters_wf(c, ctr);
+    }
+    block_count(s_blk, c);
+    block_shared_flush(s_blk, ctr, &b.plane[1]);
 }
 
 // ---- sum -----------------------------------------------------------------------------------------
-// k_wf_plan (one thread, after the regen kernel): planes [summed, upto) are complete — fully
+// k_wf_plan (one thread, after the regen passes): planes [summed, upto) are complete — fully
 // claimed and older than the oldest sample still in flight — and the claim limit moves on.
 __global__ void k_wf_plan(WfBuf b) {
     const uint32_t n_px = b.call->n_px, reserve = b.call->reserve;
     const uint32_t summed = b.plane[3];                 // the sum kernel of the last iteration has run
     b.plane[0] = summed;
+    b.item[0] += b.item[3];                             // the items the regen passes of this iteration took
+    b.item[3] = 0;
     const unsigned long long total = b.item[2], next = min(b.item[0], total);
     const unsigned long long claimed = next / n_px;     // planes whose items have all been handed out
     const uint32_t oldest = b.plane[1];
@@ -540,7 +582,7 @@ __global__ void k_wf_plan(WfBuf b) {
     if (upto < summed + b.batch && next < total) upto = summed;
     if (upto < summed) upto = summed;
     b.plane[3] = upto;
-    // b.reserve planes of the ring stay free: the claims of one launch can pass the limit by one item per slot
+    // b.reserve planes of the ring stay free (headroom; the regen passes never take an item past the limit)
     const unsigned long long limit = ((unsigned long long)upto + b.ring - reserve) * n_px;
     b.item[1] = limit < total ? limit : total;
     b.plane[1] = 0xFFFFFFFFu;
@@ -573,24 +615,22 @@ __global__ void __launch_bounds__(128) k_wf_exact(DScene sc, WfBuf b) {
     const uint32_t n = b.counts[kCntExact];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint32_t slot = b.xlist[i];
-        WfSlot *const sp = b.slot + slot;
-        WfAux *const ap = b.aux + slot;
         d3 o, d;
-        ld_ray(sp, o, d);
+        ld_ray(b.ray + slot, o, d);
         Cnt scratch;
-        if (sp->flags & kFlagPendLight) {
-            double impact = ap->pimp;                   // the analytic lights' part (shade kernel), then the triangles
+        if (b.head[slot].x & kFlagPendLight) {
+            double impact = b.pend[slot].pimp;          // the analytic lights' part (shade kernel), then the triangles
             light_hits_exact<3>(sc.ltris, sc.ltri_i, sc.ltri_s, o, d, impact, scratch);
-            ap->lres = impact;
+            b.pend[slot].lres = impact;
         }
         const Best bt = closest_exact<3>(sc.tris, sc.tri_i, o, d, scratch);
         if (bt.has) {
             double t, u, v;
             tri_exact(sc.tri_i + bt.prim, o, d, t, u, v);
-            sp->hit_prim = bt.prim;
-            ap->res_t = t; ap->res_u = u; ap->res_v = v;
+            *head_hit_prim(b.head + slot) = bt.prim;
+            b.res[slot].t = t; b.res[slot].u = u; b.res[slot].v = v;
         }
-        sp->ncand = bt.has ? 1u : 0u;                   // no overflow: nothing left to search
+        *head_ncand(b.head + slot) = bt.has ? 1u : 0u;  // no overflow: nothing left to search
     }
 }
 
@@ -694,7 +734,7 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
                     cur = sc.fltris.root; cur_t = 0.0f;
                     WF_ENTER_LEAF()
                 } else {                                                            // publish, go idle
-                    b.slot[my_slot].ncand = nc | (nl << 8) | over;
+                    *head_ncand(b.head + my_slot) = nc | (nl << 8) | over;
                     has = false;
                 }
             }
@@ -712,15 +752,14 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
                     if (idx < n) {
                         const uint32_t slot_new = ll.at(idx);
                         my_slot = slot_new;
-                        const WfSlot *rec = b.slot + slot_new;
                         d3 o, dd;
-                        ld_ray(rec, o, dd);
-                        const uint4 h = ld_head(rec);
+                        ld_ray(b.ray + slot_new, o, dd);
+                        const uint4 h = b.head[slot_new];
                         my_ray[0] = o.x; my_ray[128] = o.y; my_ray[256] = o.z;
                         my_ray[384] = dd.x; my_ray[512] = dd.y; my_ray[640] = dd.z;
                         r = make_fray(o, dd);
                         const uint32_t sid = h.y;
-                        const double st = sid != kNoShape ? b.aux[slot_new].sh_t : 0.0;
+                        const double st = sid != kNoShape ? b.res[slot_new].sh_t : 0.0;
                         bool skip = (sid != kNoShape && st != st) || ray_is_nan(o, dd);
                         tmax = (sid != kNoShape && !skip) ? up_f32(st) : inf;
                         want_light = (h.x & kFlagPendLight) != 0;
@@ -805,14 +844,14 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
                     if (closest) {
                         if (cls == 2) tmax = fminf(tmax, thi);
                         if (nc < (uint32_t)kWfCand) {
-                            b.aux[my_slot].cand[nc] = tri_i;
+                            b.cand[my_slot].cand[nc] = tri_i;
                             ++nc;
                         } else {
                             over |= kOverflowClosest;           // rare: k_wf_exact redoes this search
                             WF_INC(n_over)
                         }
                     } else {
-                        if (nl < (uint32_t)kWfCand) { b.aux[my_slot].lcand[nl] = tri_i; ++nl; }
+                        if (nl < (uint32_t)kWfCand) { b.cand[my_slot].lcand[nl] = tri_i; ++nl; }
                         else { over |= kOverflowLight; WF_INC(n_over) }
                     }
                 }
@@ -840,7 +879,7 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
 }
 
 // ---- host loop -----------------------------------------------------------------------------------
-size_t wf_bytes_per_slot() { return sizeof(WfSlot) + sizeof(WfAux) + 4 * sizeof(uint32_t); }      // + ring * 24 per PIXEL for the side planes
+size_t wf_bytes_per_slot() { return sizeof(uint4) + sizeof(WfRay) + sizeof(WfTL) + sizeof(WfPend) + sizeof(WfRes) + sizeof(WfCand) + 5 * sizeof(uint32_t); }      // + ring * 24 per PIXEL for the side planes
 int wf_trace_blocks(int device, bool smem_top) {
     int sms = 148, per_sm = 4;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -849,10 +888,20 @@ int wf_trace_blocks(int device, bool smem_top) {
     if (e != cudaSuccess || per_sm < 1) per_sm = 4;
     return sms * per_sm;
 }
-cudaError_t wf_runtime_init(WfRuntime &rt) {
+cudaError_t wf_runtime_init(WfRuntime &rt, int device) {
     cudaError_t e;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    // Both list kernels run best with the whole list in flight (one block per 128 entries).  Measured on B200 (C3,
+    // Mseg/s) with bounded grids of shade x regen blocks per SM, which keep the two kernels resident side by
+    // side: 3x2 1370, 3x3 1359, 4x3 1401, 5x3 1427, 6x8 1444, unbounded 1451 — each kernel needs all the
+    // warps it can get to hide its own memory latency; sharing the SMs costs more than the overlap returns.
+    (void)sms;
+    if (!rt.shade_blocks) rt.shade_blocks = 0xFFFFFFFFu;
+    if (!rt.regen_blocks) rt.regen_blocks = 0x7FFFFFFFu;
     if ((e = cudaStreamCreateWithFlags(&rt.side, cudaStreamNonBlocking)) != cudaSuccess) return e;
-    cudaEvent_t *evs[4] = {&rt.ev_fork, &rt.ev_shade, &rt.ev_join, &rt.ev_poll};
+    if ((e = cudaStreamCreateWithFlags(&rt.side2, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    cudaEvent_t *evs[5] = {&rt.ev_fork, &rt.ev_shade, &rt.ev_join, &rt.ev_poll, &rt.ev_regen};
     for (cudaEvent_t *ev : evs)
         if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return e;
     uint32_t *host = nullptr;
@@ -868,14 +917,15 @@ static void wf_drop_graph(WfRuntime &rt) {
 void wf_runtime_destroy(WfRuntime &rt) {
     wf_drop_graph(rt);
     if (rt.side) { cudaStreamSynchronize(rt.side); cudaStreamDestroy(rt.side); }
-    cudaEvent_t evs[4] = {rt.ev_fork, rt.ev_shade, rt.ev_join, rt.ev_poll};
+    if (rt.side2) { cudaStreamSynchronize(rt.side2); cudaStreamDestroy(rt.side2); }
+    cudaEvent_t evs[5] = {rt.ev_fork, rt.ev_shade, rt.ev_join, rt.ev_poll, rt.ev_regen};
     for (cudaEvent_t ev : evs) if (ev) cudaEventDestroy(ev);
     if (rt.host_live) cudaFreeHost((void *)rt.host_live);
     rt = WfRuntime{};
 }
 
 constexpr int kGraphIters = 4;              // iterations per graph launch
-constexpr int kLaunchesPerIter = 7;         // confirm, exact, shade_hit, regen, plan, sum, trace
+constexpr int kLaunchesPerIter = 8;         // confirm, exact, shade_hit, regen x 2, plan, sum, trace
 
 cudaError_t launch_render_wavefront(cudaStream_t st, WfRuntime &rt, const DScene &sc, uint32_t sample_begin, uint32_t sample_count,
                                     uint64_t seed, double *accum, DCounters *ctr, const WfBuf &b, int trace_blocks,
@@ -909,9 +959,9 @@ cudaError_t launch_render_wavefront(cudaStream_t st, WfRuntime &rt, const DScene
     // scenes without planes / boxes / ellipsoids (every glTF scene) run the kernels compiled without them
     const bool shapes = sc.n_planes || sc.boxes.n_prims || sc.ellipsoids.n_prims || sc.lboxes.n_prims || sc.lellipsoids.n_prims;
     const unsigned sum_blocks = (unsigned)std::min<uint64_t>(((uint64_t)b.n_px_cap + 255) / 256, 148 * 8);
-    // One iteration: confirm -> shade_hit -> regen -> trace on the main stream; on the forked stream
-    // k_wf_exact (after confirm) and the one-thread k_wf_plan + k_wf_sum (after regen, next to the
-    // trace kernel), joined before the next iteration.  Four iterations are captured ONCE per (scene,
+    // One iteration: confirm -> shade_hit -> regen (pass 1) -> trace on the main stream; forked after
+    // confirm: k_wf_exact, and the first regen pass next to shade_hit; forked after the second regen pass:
+    // the one-thread k_wf_plan + k_wf_sum, next to the trace kernel; all joined before the next iteration.  Four iterations are captured ONCE per (scene,
     // buffers) into a CUDA graph and replayed by every call: the inner loop is launch-bound on small
     // images and at the end of every render.
     auto issue_iteration = [&]() {
@@ -919,14 +969,19 @@ cudaError_t launch_render_wavefront(cudaStream_t st, WfRuntime &rt, const DScene
         k_wf_confirm<<<blocks, 128, 0, st>>>(sc, b, ctr);
         cudaEventRecord(rt.ev_fork, st);
         cudaStreamWaitEvent(rt.side, rt.ev_fork, 0);
+        cudaStreamWaitEvent(rt.side2, rt.ev_fork, 0);
         k_wf_exact<<<64, 128, 0, rt.side>>>(sc, b);
         if (shapes) {
-            k_wf_shade_hit<true><<<blocks, 128, 0, st>>>(sc, b, ctr);
-            k_wf_regen<true><<<blocks, 128, 0, st>>>(sc, b, ctr);
+            k_wf_regen<true><<<std::min(blocks, rt.regen_blocks), 128, 0, rt.side2>>>(sc, b, ctr, 0);
+            k_wf_shade_hit<true><<<std::min(blocks, rt.shade_blocks), 128, 0, st>>>(sc, b, ctr);
         } else {
-            k_wf_shade_hit<false><<<blocks, 128, 0, st>>>(sc, b, ctr);
-            k_wf_regen<false><<<blocks, 128, 0, st>>>(sc, b, ctr);
+            k_wf_regen<false><<<std::min(blocks, rt.regen_blocks), 128, 0, rt.side2>>>(sc, b, ctr, 0);
+            k_wf_shade_hit<false><<<std::min(blocks, rt.shade_blocks), 128, 0, st>>>(sc, b, ctr);
         }
+        cudaEventRecord(rt.ev_regen, rt.side2);
+        cudaStreamWaitEvent(st, rt.ev_regen, 0);
+        if (shapes) k_wf_regen<true><<<blocks, 128, 0, st>>>(sc, b, ctr, 1);
+        else k_wf_regen<false><<<blocks, 128, 0, st>>>(sc, b, ctr, 1);
         cudaEventRecord(rt.ev_shade, st);
         cudaStreamWaitEvent(rt.side, rt.ev_shade, 0);
         k_wf_plan<<<1, 1, 0, rt.side>>>(b);
@@ -936,13 +991,14 @@ cudaError_t launch_render_wavefront(cudaStream_t st, WfRuntime &rt, const DScene
         else k_wf_trace<false><<<trace_blocks, 128, 0, st>>>(sc, b, ctr);
         cudaStreamWaitEvent(st, rt.ev_join, 0);
     };
-    const bool same_key = rt.tried_graph && std::memcmp(&rt.key_sc, &sc, sizeof sc) == 0 && std::memcmp(&rt.key_b, &b, sizeof b) == 0 &&
+    const bool same_key = rt.tried_graph && rt.key_grid[0] == rt.shade_blocks && rt.key_grid[1] == rt.regen_blocks && std::memcmp(&rt.key_sc, &sc, sizeof sc) == 0 && std::memcmp(&rt.key_b, &b, sizeof b) == 0 &&
                           rt.key_accum == accum && rt.key_ctr == ctr && rt.key_blocks == trace_blocks;
     if (!same_key) {
         wf_drop_graph(rt);
         std::memcpy(&rt.key_sc, &sc, sizeof sc);
         std::memcpy(&rt.key_b, &b, sizeof b);
         rt.key_accum = accum; rt.key_ctr = ctr; rt.key_blocks = trace_blocks;
+        rt.key_grid[0] = rt.shade_blocks; rt.key_grid[1] = rt.regen_blocks;
         rt.tried_graph = true;
         if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
             for (int k = 0; k < kGraphIters; ++k) issue_iteration();
