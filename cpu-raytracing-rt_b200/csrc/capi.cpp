@@ -56,14 +56,14 @@ cudaError_t ensure_wavefront(rt_ctx *ctx) {
     free_wavefront(ctx);
     const size_t per = wf_bytes_per_slot();
     const uint32_t ring = ctx->knob_ring, batch = ctx->knob_batch;
-    const size_t total = per * n + (size_t)n_img * 24 * ring + 65536 + 64 * 256;
+    const size_t total = per * n + (size_t)n_img * 32 * ring + 65536 + 64 * 256;
     cudaError_t e = cudaMalloc(&ctx->wf_arena, total);
     if (e != cudaSuccess) return e;
     char *p = ctx->wf_arena;
     auto take = [&](size_t bytes) { char *r = p; p += (bytes + 255) & ~(size_t)255; return r; };
     WfBuf &b = ctx->wf;
     b.n = n;
-    b.head = (uint4 *)take((size_t)n * sizeof(uint4));
+    b.head = (WfHead *)take((size_t)n * sizeof(WfHead));
     b.ray = (WfRay *)take((size_t)n * sizeof(WfRay));
     b.tl = (WfTL *)take((size_t)n * sizeof(WfTL));
     b.pend = (WfPend *)take((size_t)n * sizeof(WfPend));
@@ -77,7 +77,7 @@ cudaError_t ensure_wavefront(rt_ctx *ctx) {
     b.counts = (uint32_t *)take(32);
     b.ring = ring;
     b.batch = batch;
-    b.side = (double *)take((size_t)n_img * 24 * ring);
+    b.side = (double4 *)take((size_t)n_img * 32 * ring);
     b.n_px_cap = n_img;
     b.item = (unsigned long long *)take(32);
     b.plane = (uint32_t *)take(16);

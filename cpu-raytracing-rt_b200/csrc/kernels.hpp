@@ -28,39 +28,41 @@ struct WfCall {
     DRegion rg;
 };
 // Path state, grouped by WHO touches it.  The confirm kernel walks the slots in index order, the other
-// kernels walk compacted lists (a gather): every group is a record of whole 32-byte sectors that its
-// readers need in full, so a gather never moves a sector for eight useful bytes, and the one group every
-// kernel reads (`head`, 16 bytes) is a plain array that the index-order walk reads coalesced.
-//   head[slot]  uint4: flags, sh_id, ncand, hit_prim
-//                 flags: alive / ended / pending Light::pdf / deferred to k_wf_exact | depth left << 8
-//                 sh_id: nearest analytic shape (kind << 28 | index) or 0xFFFFFFFF
-//                 ncand: trace -> confirm: #scene | #light << 8 | overflow bits; confirm -> shade: 0 / 1
-//                 hit_prim: nearest confirmed triangle
+// kernels walk compacted lists (a gather): every group is a record of whole 32-byte sectors, and every
+// writer writes whole sectors (a partial sector costs a read-modify-write in HBM: the kernels that walk
+// lists run at half the HBM bandwidth and more, so those bytes are time).
+struct __align__(16) WfHead {           // 32 B = one sector: every kernel reads it; shade_hit / regen rewrite it in full
+    uint32_t flags;                     // alive / ended / pending Light::pdf / deferred to k_wf_exact | depth left << 8
+    uint32_t sh_id;                     // nearest analytic shape (kind << 28 | index) or 0xFFFFFFFF
+    uint32_t ncand;                     // trace -> confirm: #scene | #light << 8 | overflow bits; confirm -> shade: 0 / 1
+    uint32_t hit_prim;                  // nearest confirmed triangle
+    uint32_t sample, pix, ord, rng_pos; // the item in flight (sample of the call, pixel, ordinal in the region), RNG draws consumed
+};
 struct __align__(16) WfRay {            // 64 B: trace (gather), confirm, shade_hit, regen
     double o[3], d[3];                  // the ray to trace / just traced
-    uint32_t sample, pix, ord, rng_pos; // the item in flight (sample of the call, pixel, ordinal in the region), RNG draws consumed
+    double _spare[2];
 };
 struct __align__(16) WfTL {             // 64 B: shade_hit, regen
     double T[3], L[3];                  // throughput, radiance so far
     double _spare[2];
 };
-struct __align__(16) WfPend {           // 64 B: only slots with a pending diffuse bounce
-    double pv[3], pcos;                 // dot * color / PI, Cosine::pdf
-    double pimp, lres;                  // Light::pdf impact: the analytic lights' part, the complete sum
-    double _spare[2];
+struct __align__(16) WfPend {           // 64 B: slots with a pending diffuse bounce (and, text scenes, a shape hit)
+    double pv[3], pcos;                 // sector 0: dot * color / PI, Cosine::pdf
+    double pimp, lres;                  // sector 1: Light::pdf impact: the analytic lights' part, the complete sum
+    double sh_t, _spare;                //           distance of sh_id
 };
 struct __align__(16) WfRes {            // 32 B: confirm / exact -> shade_hit
-    double t, u, v;                     // exact (t, u, v) of hit_prim
-    double sh_t;                        // distance of sh_id
+    double t, u, v, _spare;             // exact (t, u, v) of hit_prim
 };
 struct __align__(16) WfCand {           // 64 B: trace -> confirm
     uint32_t cand[kWfCand], lcand[kWfCand];     // triangles that survived the fp32 pre-test (scene / light hierarchy)
     uint32_t _spare[4];
 };
-static_assert(sizeof(WfRay) == 64 && sizeof(WfTL) == 64 && sizeof(WfPend) == 64 && sizeof(WfRes) == 32 && sizeof(WfCand) == 64, "slot records are whole sectors");
+static_assert(sizeof(WfHead) == 32 && sizeof(WfRay) == 64 && sizeof(WfTL) == 64 && sizeof(WfPend) == 64 && sizeof(WfRes) == 32 && sizeof(WfCand) == 64,
+              "slot records are whole sectors");
 struct WfBuf {
     uint32_t n;                         // slots allocated
-    uint4 *head;
+    WfHead *head;
     WfRay *ray;
     WfTL *tl;
     WfPend *pend;
@@ -77,7 +79,7 @@ struct WfBuf {
     uint32_t ring;                      // planes in the ring of finished samples
     uint32_t n_px_cap;                  // pixels the side planes were allocated for (width * height)
     WfCall *call;                       // device: the parameters of the render call in flight (written by k_wf_init)
-    double *side;                       // ring * 3 * n_px: radiance of finished samples: plane (sample % ring), component, ordinal
+    double4 *side;                      // ring * n_px: radiance of finished samples (x, y, z, -): plane (sample % ring), ordinal — one sector each
     unsigned long long *item;           // [0] next unclaimed item, [1] claim limit, [2] items of this call, [3] items taken in this iteration
     uint32_t *plane;                    // [0] planes added to accum, [1] oldest sample in flight, [2] ring, [3] planes complete
 };

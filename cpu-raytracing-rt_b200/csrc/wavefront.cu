@@ -56,8 +56,15 @@ constexpr uint32_t kOverflowClosest = 0x10000u, kOverflowLight = 0x20000u;
 constexpr uint32_t kNoShape = 0xFFFFFFFFu;
 enum { kCntFront = 0, kCntBack = 1, kCntCursor = 2, kCntExact = 3, kCntHit = 4, kCntRegen = 5 /* and 6: the two regen lists */, kCntWords = 8 };
 
-// ---- slot records: 16-byte vector access ---------------------------------------------------------
-// WfRay as double2[3] + uint4: (o.x o.y) (o.z d.x) (d.y d.z) | sample, pix, ord, rng_pos
+// ---- slot records: 16-byte vector access; stores always cover whole 32-byte sectors ----------------
+// WfHead as uint4[2]: (flags, sh_id, ncand, hit_prim) (sample, pix, ord, rng_pos)
+RT_D uint4 ld_head(const WfHead *h) { return reinterpret_cast<const uint4 *>(h)[0]; }
+RT_D uint4 ld_item(const WfHead *h) { return reinterpret_cast<const uint4 *>(h)[1]; }
+RT_D void st_head_item(WfHead *h, uint4 head, uint4 item) {
+    reinterpret_cast<uint4 *>(h)[0] = head;
+    reinterpret_cast<uint4 *>(h)[1] = item;
+}
+// WfRay as double2[4]: (o.x o.y) (o.z d.x) (d.y d.z) (spare)
 RT_D void ld_ray(const WfRay *s, d3 &o, d3 &d) {
     const double2 *p = reinterpret_cast<const double2 *>(s);
     const double2 q0 = p[0], q1 = p[1], q2 = p[2];
@@ -66,11 +73,9 @@ RT_D void ld_ray(const WfRay *s, d3 &o, d3 &d) {
 }
 RT_D void st_ray(WfRay *s, d3 o, d3 d) {
     double2 *p = reinterpret_cast<double2 *>(s);
-    p[0] = make_double2(o.x, o.y); p[1] = make_double2(o.z, d.x); p[2] = make_double2(d.y, d.z);
+    p[0] = make_double2(o.x, o.y); p[1] = make_double2(o.z, d.x); p[2] = make_double2(d.y, d.z); p[3] = make_double2(0.0, 0.0);
 }
-RT_D uint4 ld_item(const WfRay *s) { return reinterpret_cast<const uint4 *>(s)[3]; }       // sample, pix, ord, rng_pos
-RT_D void st_item(WfRay *s, uint4 v) { reinterpret_cast<uint4 *>(s)[3] = v; }
-// WfTL as double2[3]: (T.x T.y) (T.z L.x) (L.y L.z)
+// WfTL as double2[4]: (T.x T.y) (T.z L.x) (L.y L.z) (spare)
 RT_D void ld_TL(const WfTL *s, d3 &T, d3 &L) {
     const double2 *p = reinterpret_cast<const double2 *>(s);
     const double2 q0 = p[0], q1 = p[1], q2 = p[2];
@@ -79,9 +84,9 @@ RT_D void ld_TL(const WfTL *s, d3 &T, d3 &L) {
 }
 RT_D void st_TL(WfTL *s, d3 T, d3 L) {
     double2 *p = reinterpret_cast<double2 *>(s);
-    p[0] = make_double2(T.x, T.y); p[1] = make_double2(T.z, L.x); p[2] = make_double2(L.y, L.z);
+    p[0] = make_double2(T.x, T.y); p[1] = make_double2(T.z, L.x); p[2] = make_double2(L.y, L.z); p[3] = make_double2(0.0, 0.0);
 }
-// WfPend as double2[3]: (pv.x pv.y) (pv.z pcos) (pimp lres)
+// WfPend as double2[4]: (pv.x pv.y) (pv.z pcos) | (pimp lres) (sh_t spare)
 RT_D void ld_pending(const WfPend *a, Pending &pd, double &lres) {
     const double2 *p = reinterpret_cast<const double2 *>(a);
     const double2 q0 = p[0], q1 = p[1];
@@ -89,15 +94,18 @@ RT_D void ld_pending(const WfPend *a, Pending &pd, double &lres) {
     pd.cos_pdf = q1.y;
     lres = a->lres;
 }
-RT_D void st_pending(WfPend *a, const Pending &pd, double pimp) {
+RT_D void st_pending(WfPend *a, const Pending &pd) {
     double2 *p = reinterpret_cast<double2 *>(a);
     p[0] = make_double2(pd.v.x, pd.v.y); p[1] = make_double2(pd.v.z, pd.cos_pdf);
-    a->pimp = pimp;
 }
-// fields of head[slot]
-RT_D uint32_t *head_flags(uint4 *h) { return &h->x; }
-RT_D uint32_t *head_ncand(uint4 *h) { return &h->z; }
-RT_D uint32_t *head_hit_prim(uint4 *h) { return &h->w; }
+RT_D void st_pend_tail(WfPend *a, double pimp, double lres, double sh_t) {
+    double2 *p = reinterpret_cast<double2 *>(a);
+    p[2] = make_double2(pimp, lres); p[3] = make_double2(sh_t, 0.0);
+}
+RT_D void st_res(WfRes *r, double t, double u, double v) {
+    double2 *p = reinterpret_cast<double2 *>(r);
+    p[0] = make_double2(t, u); p[1] = make_double2(v, 0.0);
+}
 
 // Per-block event counters and list appends: one global atomic per BLOCK and per counter.  (Per warp,
 // the 65 000 warps of a kernel that does little else queue up on a handful of addresses.)
@@ -182,7 +190,7 @@ RT_D uint32_t region_tile_pixel(const DRegion &rg, uint32_t width, uint32_t i) {
 __global__ void k_wf_init(WfBuf b, WfCall cl, uint32_t sample_count) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_px = cl.n_px;
-    if (i < cl.n_slots) b.head[i] = make_uint4(0u, kNoShape, 0u, 0u);      // an empty slot: the first confirm pass sends it to k_wf_regen
+    if (i < cl.n_slots) st_head_item(b.head + i, make_uint4(0u, kNoShape, 0u, 0u), make_uint4(0u, 0u, 0u, 0u));      // an empty slot: the first confirm pass sends it to k_wf_regen
     if (i == 0) {
         *b.call = cl;                                   // what the kernels of this call read instead of arguments
         for (int k = 0; k < kCntWords; ++k) b.counts[k] = 0;
@@ -220,16 +228,18 @@ __global__ void __launch_bounds__(128, WF_CONFIRM_MINB) k_wf_confirm(DScene sc, 
     const uint32_t n_slots = b.call->n_slots;
     if (slot0 >= n_slots) return;                       // the grid covers the buffer's capacity
     uint32_t nc = 0, nl = 0, flags = 0, nc_all = 0, sh_id = kNoShape;
+    uint4 item = make_uint4(0u, 0u, 0u, 0u);
     bool mine = false;                                  // this thread's slot has results to fold
     int cls = 0;                                        // 1: hit list, 2: regen list
     if (i < n_slots) {
-        const uint4 h = b.head[i];
+        const uint4 h = ld_head(b.head + i);
+        item = ld_item(b.head + i);                     // same sector: lets phase 2 write the record back whole
         flags = h.x; sh_id = h.y; nc_all = h.z;
         if (flags & kFlagExactPending) {
             // k_wf_exact answered this slot during the last iteration (the graph joined since):
             // its results are final, the shade kernel takes them in this iteration
             flags &= ~kFlagExactPending;
-            *head_flags(b.head + i) = flags;
+            b.head[i].flags = flags;
             cls = ((nc_all & 0xFFu) || sh_id != kNoShape) ? 1 : 2;
         } else if (flags & kFlagAlive) {
             mine = true;
@@ -297,13 +307,15 @@ __global__ void __launch_bounds__(128, WF_CONFIRM_MINB) k_wf_confirm(DScene sc, 
         // is not worth a second fp32 search: the exact traversal answers the ray
         bool need_exact = (nc_all & (kOverflowClosest | kOverflowLight)) != 0 || base + nl + nc > kConfirmPairs;
         if ((flags & kFlagPendLight) && !need_exact) {
-            double impact = b.pend[i].pimp;
+            const double2 *pt = reinterpret_cast<const double2 *>(b.pend + i);
+            const double2 t0 = pt[2], t1 = pt[3];       // (pimp, lres) (sh_t, -): the sector is written back whole
+            double impact = t0.x;
             for (uint32_t k = 0; k < nl; ++k) {
                 const double term = s_t[base + k];
                 if (term == -2.0) need_exact = true;
                 else if (term != -1.0) impact += term;
             }
-            b.pend[i].lres = impact;
+            st_pend_tail(b.pend + i, t0.x, impact, t1.x);
         }
         bool tri_hit = false;
         if (!need_exact) {
@@ -317,21 +329,21 @@ __global__ void __launch_bounds__(128, WF_CONFIRM_MINB) k_wf_confirm(DScene sc, 
             if (fb.has) {
                 const d3 o = mk3(s_ray[0][tid], s_ray[1][tid], s_ray[2][tid]), d = mk3(s_ray[3][tid], s_ray[4][tid], s_ray[5][tid]);
                 need_exact = fbest_needs_exact(fb, o, d, (double)sc.ftris.bound);
-                b.res[i].t = fb.t; b.res[i].u = fb.u; b.res[i].v = fb.v;
+                st_res(b.res + i, fb.t, fb.u, fb.v);
             }
             if (!need_exact) {
-                // ncand and hit_prim are neighbours: one 8-byte store
-                *reinterpret_cast<uint2 *>(head_ncand(b.head + i)) = make_uint2(fb.has ? 1u : 0u, fb.prim);
+                // a ray without candidates already says ncand = 0; otherwise the whole sector goes back (no partial write)
+                if (nc_all != 0u) st_head_item(b.head + i, make_uint4(flags, sh_id, fb.has ? 1u : 0u, fb.prim), item);
                 tri_hit = fb.has;
             }
         }
         if (need_exact) {
             // Nothing is shaded or traced for the slot in this iteration: k_wf_exact answers both searches
             // with the reference's own traversal meanwhile, the next confirm pass picks the slot up.
-            *head_flags(b.head + i) = flags | kFlagExactPending;
+            b.head[i].flags = flags | kFlagExactPending;
             b.xlist[atomicAdd(&b.counts[kCntExact], 1u)] = i;
             atomicAdd(&ctr->exact_fallbacks, 1ull);     // rare
-            atomicMin(&b.plane[1], b.ray[i].sample);    // still in flight
+            atomicMin(&b.plane[1], item.x);             // its sample is still in flight
         } else {
             cls = (tri_hit || sh_id != kNoShape) ? 1 : 2;
         }
@@ -345,7 +357,7 @@ __global__ void __launch_bounds__(128, WF_CONFIRM_MINB) k_wf_confirm(DScene sc, 
 
 // ---- shade: the slots whose ray hit something ----------------------------------------------------
 #ifndef WF_SHADE_MINB
-#define WF_SHADE_MINB 6
+#define WF_SHADE_MINB 5        // 96 registers; measured 4 / 5 / 6 blocks per SM -> 1504 / 1510 / 1495 Mseg/s
 #endif
 template <bool SHAPES>
 __global__ void __launch_bounds__(128, SHAPES ? 4 : WF_SHADE_MINB) k_wf_shade_hit(DScene sc, WfBuf b, DCounters *ctr) {
@@ -372,7 +384,7 @@ __global__ void __launch_bounds__(128, SHAPES ? 4 : WF_SHADE_MINB) k_wf_shade_hi
         d3 o, d, T, L;
         ld_ray(rp, o, d);
         ld_TL(tp, T, L);
-        const uint4 h = b.head[slot], it = ld_item(rp);
+        const uint4 h = ld_head(b.head + slot), it = ld_item(b.head + slot);
         const uint32_t flags = h.x;
         smp = it.x;
         uint32_t left = (flags >> 8) & 0xFFu;
@@ -392,7 +404,7 @@ __global__ void __launch_bounds__(128, SHAPES ? 4 : WF_SHADE_MINB) k_wf_shade_hi
         if (!ended) {
             ShapeBest sb;
             sb.has = SHAPES && h.y != kNoShape; sb.kind = sb.has ? (int)(h.y >> 28) : -1; sb.prim = h.y & 0x0FFFFFFFu;
-            sb.t = sb.has ? b.res[slot].sh_t : 0.0;
+            sb.t = sb.has ? b.pend[slot].sh_t : 0.0;
             FBest fb;
             fbest_clear(fb);
             bool skip;
@@ -421,22 +433,24 @@ __global__ void __launch_bounds__(128, SHAPES ? 4 : WF_SHADE_MINB) k_wf_shade_hi
         if (ended) {
             // the second k_wf_regen pass parks the radiance in the plane of the sample and gives the slot its next item
             st_TL(tp, T, L);
-            *head_flags(b.head + slot) = kFlagEnded;
+            st_head_item(b.head + slot, make_uint4(kFlagEnded, kNoShape, 0u, 0u), it);
         } else {                                        // hand the ray to the trace kernel
             uint32_t sh_id = kNoShape;
+            double sh_t = 0.0;
             if (SHAPES) {
                 const ShapeBest nb = shapes_closest(sc, o, d, c);
                 sh_id = nb.has ? (((uint32_t)nb.kind << 28) | nb.prim) : kNoShape;
-                if (nb.has) b.res[slot].sh_t = nb.t;
+                sh_t = nb.t;
             }
             if (pend_light) {
                 ++c.lray;
-                st_pending(b.pend + slot, pd, SHAPES ? light_shapes_impact(sc, o, d, c) : 0.0);
+                st_pending(b.pend + slot, pd);
             }
+            if (pend_light || sh_id != kNoShape) st_pend_tail(b.pend + slot, (SHAPES && pend_light) ? light_shapes_impact(sc, o, d, c) : 0.0, 0.0, sh_t);
             st_ray(rp, o, d);
-            rp->rng_pos = rng.pos;
             st_TL(tp, T, L);
-            b.head[slot] = make_uint4(kFlagAlive | (pend_light ? kFlagPendLight : 0u) | (left << 8), sh_id, 0u, 0u);
+            st_head_item(b.head + slot, make_uint4(kFlagAlive | (pend_light ? kFlagPendLight : 0u) | (left << 8), sh_id, 0u, 0u),
+                         make_uint4(it.x, it.y, it.z, rng.pos));
             go_on = true;
         }
     }
@@ -505,9 +519,9 @@ __global__ void __launch_bounds__(128, SHAPES ? 4 : 8) k_wf_regen(DScene sc, WfB
         const uint32_t slot = b.regen_list[pass][i];
         WfRay *const rp = b.ray + slot;
         WfTL *const tp = b.tl + slot;
-        const uint32_t old_flags = b.head[slot].x;
+        const uint32_t old_flags = b.head[slot].flags;
         if (old_flags & (kFlagAlive | kFlagEnded)) {
-            const uint4 it = ld_item(rp);
+            const uint4 it = ld_item(b.head + slot);
             d3 T, L;
             ld_TL(tp, T, L);
             if (old_flags & kFlagAlive) {               // the ray escaped: raytrace_impl returns bg_color (raytrace.rs:14)
@@ -526,8 +540,8 @@ __global__ void __launch_bounds__(128, SHAPES ? 4 : 8) k_wf_regen(DScene sc, WfB
             // The finished sample's radiance goes to the plane of its sample index; k_wf_sum adds the
             // planes to the accumulation buffer in sample order (main.rs:102), whatever slot computed
             // them and whenever.
-            double *side = b.side + (size_t)(it.x % b.ring) * 3u * n_px + it.z;
-            side[0] = L.x; side[n_px] = L.y; side[2u * (size_t)n_px] = L.z;
+            double2 *side = reinterpret_cast<double2 *>(b.side + (size_t)(it.x % b.ring) * n_px + it.z);
+            side[0] = make_double2(L.x, L.y); side[1] = make_double2(L.z, 0.0);
         }
         if (i < plan.grant) {
             // item j = sample (j / n_px) of the pixel with ordinal (j % n_px) in the region's tile order;
@@ -548,15 +562,14 @@ __global__ void __launch_bounds__(128, SHAPES ? 4 : 8) k_wf_regen(DScene sc, WfB
             if (SHAPES) {
                 const ShapeBest nb = shapes_closest(sc, o, d, c);
                 sh_id = nb.has ? (((uint32_t)nb.kind << 28) | nb.prim) : kNoShape;
-                if (nb.has) b.res[slot].sh_t = nb.t;
+                if (nb.has) st_pend_tail(b.pend + slot, 0.0, 0.0, nb.t);
             }
             st_ray(rp, o, d);
-            st_item(rp, make_uint4(smp, pix, ord, rng.pos));
             st_TL(tp, mk3(1.0, 1.0, 1.0), mk3(0.0, 0.0, 0.0));
-            b.head[slot] = make_uint4(kFlagAlive | ((uint32_t)sc.ray_depth << 8), sh_id, 0u, 0u);
+            st_head_item(b.head + slot, make_uint4(kFlagAlive | ((uint32_t)sc.ray_depth << 8), sh_id, 0u, 0u), make_uint4(smp, pix, ord, rng.pos));
             b.live[plan.front + i] = slot;              // fresh camera rays: the FRONT of the trace list, in item order
         } else if (old_flags != 0u) {
-            *head_flags(b.head + slot) = 0u;            // nothing to take right now: an empty slot, asks again in the next iteration
+            b.head[slot].flags = 0u;                    // nothing to take right now: an empty slot, asks again in the next iteration
         }
     }
     }
@@ -596,8 +609,9 @@ __global__ void __launch_bounds__(256) k_wf_sum(WfBuf b, uint32_t width, double 
         const size_t p = (size_t)region_tile_pixel(rg, width, od) * 3;
         double ax = accum[p], ay = accum[p + 1], az = accum[p + 2];
         for (uint32_t smp = from; smp < upto; ++smp) {
-            const double *sp = b.side + (size_t)(smp % b.ring) * 3u * n_px + od;
-            ax += sp[0]; ay += sp[n_px]; az += sp[2u * (size_t)n_px];
+            const double2 *sp = reinterpret_cast<const double2 *>(b.side + (size_t)(smp % b.ring) * n_px + od);
+            const double2 xy = sp[0];
+            ax += xy.x; ay += xy.y; az += sp[1].x;
         }
         accum[p] = ax; accum[p + 1] = ay; accum[p + 2] = az;
     }
@@ -618,7 +632,7 @@ __global__ void __launch_bounds__(128) k_wf_exact(DScene sc, WfBuf b) {
         d3 o, d;
         ld_ray(b.ray + slot, o, d);
         Cnt scratch;
-        if (b.head[slot].x & kFlagPendLight) {
+        if (b.head[slot].flags & kFlagPendLight) {
             double impact = b.pend[slot].pimp;          // the analytic lights' part (shade kernel), then the triangles
             light_hits_exact<3>(sc.ltris, sc.ltri_i, sc.ltri_s, o, d, impact, scratch);
             b.pend[slot].lres = impact;
@@ -627,10 +641,10 @@ __global__ void __launch_bounds__(128) k_wf_exact(DScene sc, WfBuf b) {
         if (bt.has) {
             double t, u, v;
             tri_exact(sc.tri_i + bt.prim, o, d, t, u, v);
-            *head_hit_prim(b.head + slot) = bt.prim;
-            b.res[slot].t = t; b.res[slot].u = u; b.res[slot].v = v;
+            b.head[slot].hit_prim = bt.prim;
+            st_res(b.res + slot, t, u, v);
         }
-        *head_ncand(b.head + slot) = bt.has ? 1u : 0u;  // no overflow: nothing left to search
+        b.head[slot].ncand = bt.has ? 1u : 0u;          // no overflow: nothing left to search
     }
 }
 
@@ -734,7 +748,7 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
                     cur = sc.fltris.root; cur_t = 0.0f;
                     WF_ENTER_LEAF()
                 } else {                                                            // publish, go idle
-                    *head_ncand(b.head + my_slot) = nc | (nl << 8) | over;
+                    b.head[my_slot].ncand = nc | (nl << 8) | over;
                     has = false;
                 }
             }
@@ -754,12 +768,12 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
                         my_slot = slot_new;
                         d3 o, dd;
                         ld_ray(b.ray + slot_new, o, dd);
-                        const uint4 h = b.head[slot_new];
+                        const uint4 h = ld_head(b.head + slot_new);
                         my_ray[0] = o.x; my_ray[128] = o.y; my_ray[256] = o.z;
                         my_ray[384] = dd.x; my_ray[512] = dd.y; my_ray[640] = dd.z;
                         r = make_fray(o, dd);
                         const uint32_t sid = h.y;
-                        const double st = sid != kNoShape ? b.res[slot_new].sh_t : 0.0;
+                        const double st = sid != kNoShape ? b.pend[slot_new].sh_t : 0.0;
                         bool skip = (sid != kNoShape && st != st) || ray_is_nan(o, dd);
                         tmax = (sid != kNoShape && !skip) ? up_f32(st) : inf;
                         want_light = (h.x & kFlagPendLight) != 0;
@@ -879,7 +893,7 @@ __global__ void __launch_bounds__(128, WF_TRACE_BLOCKS) k_wf_trace(DScene sc, Wf
 }
 
 // ---- host loop -----------------------------------------------------------------------------------
-size_t wf_bytes_per_slot() { return sizeof(uint4) + sizeof(WfRay) + sizeof(WfTL) + sizeof(WfPend) + sizeof(WfRes) + sizeof(WfCand) + 5 * sizeof(uint32_t); }      // + ring * 24 per PIXEL for the side planes
+size_t wf_bytes_per_slot() { return sizeof(WfHead) + sizeof(WfRay) + sizeof(WfTL) + sizeof(WfPend) + sizeof(WfRes) + sizeof(WfCand) + 5 * sizeof(uint32_t); }      // + ring * 32 per PIXEL for the side planes
 int wf_trace_blocks(int device, bool smem_top) {
     int sms = 148, per_sm = 4;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
