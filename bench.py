@@ -112,7 +112,8 @@ def workload_name(args, n_tris):
 def config_block(args, n_tris, world):
     """The part of `config` both arms share (the driver compares them)."""
     return {"workload": workload_name(args, n_tris), "name": args.config, "baseline_config": CONFIGS[args.config]["what"],
-            "spp": args.spp, "width": args.width, "height": args.height, "triangles": n_tris}
+            "spp": args.spp, "width": args.width, "height": args.height, "triangles": n_tris,
+            "l2": "inputs larger than L2: scene records (>= 313 MB) + path state (>= 0.6 GB) per GPU against 126 MB of L2, no flush"}
 
 
 class ClockSampler:
@@ -403,7 +404,7 @@ def main():
         traffic = None
         if args.sched == "wavefront" and args.config in ("c3", "c4") and "dram_bytes_per_spp_at_1080p" in prof:
             traffic = prof["dram_bytes_per_spp_at_1080p"] * spp_per_launch * (args.width * args.height / 2073600.0)
-        kernel_name = ("k_wf_confirm + k_wf_shade + k_wf_trace per iteration (one wavefront render call)" if args.sched == "wavefront" else "k_render_mega<FastPolicy>") if args.mode == "fast" else "k_render_mega<ExactPolicy>"
+        kernel_name = ("k_wf_confirm + k_wf_shade_hit + k_wf_regen + k_wf_trace per iteration (one wavefront render call)" if args.sched == "wavefront" else "k_render_mega<FastPolicy>") if args.mode == "fast" else "k_render_mega<ExactPolicy>"
         hbm = {"achieved": achieved, "peak": peak, "unit": "GB/s", "algorithmic_hbm_frac": achieved / peak, "traffic": traffic,
                "measured_dram_frac": (traffic / (kernel_ms * 1e-3) / 1e9 / peak) if traffic else None,
                "traffic_source": prof.get("source"), "peak_source": peak_src, "algorithmic_bytes_per_segment": bytes_per_segment,
@@ -417,18 +418,17 @@ def main():
         else:       # no tracked instruction counts for this path: the contract's HBM form
             roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                         "kernel": kernel_name, "kernel_ms_per_launch": kernel_ms, "hbm": hbm, "algorithmic_hbm_frac": hbm["algorithmic_hbm_frac"]}
-        cfg = config_block(args, n_tris, world)
-        cfg.update({"spp_per_step_per_gpu": S if weak else [rtb200.shard_sample_range(r, world, S)[1] for r in range(world)],
-                    "mode": args.mode, "scheduler": args.sched, "shard": args.shard if world > 1 else "none",
-                    "reduce": f"rt_reduce_accum (in-library ncclReduce, f64, NCCL {comm['nccl_version']}, {comm['world']} ranks)" if world > 1 else "none (1 GPU)",
-                    "l2": f"inputs larger than L2: {scene_bytes / 1e6:.0f} MB of scene records per GPU, no flush",
-                    "scene_load_s": load_s, "scene_cache_hit": bool(scene.cache_hit),
-                    "segments_per_path": segments / max(1.0, main_leg["paths"]), "light_pdf_rays_per_segment": main_leg["lrays"] / max(1.0, segments),
-                    "exact_fallbacks_per_million_segments": 1e6 * main_leg["xf"] / max(1.0, segments)})
+        cfg = config_block(args, n_tris, world)       # the same object in both arms (the driver compares them)
+        details = {"spp_per_step_per_gpu": S if weak else [rtb200.shard_sample_range(r, world, S)[1] for r in range(world)],
+                   "mode": args.mode, "scheduler": args.sched, "shard": args.shard if world > 1 else "none",
+                   "reduce": f"rt_reduce_accum (in-library ncclReduce, f64, NCCL {comm['nccl_version']}, {comm['world']} ranks)" if world > 1 else "none (1 GPU)",
+                   "scene_device_bytes": int(scene_bytes), "scene_load_s": load_s, "scene_cache_hit": bool(scene.cache_hit),
+                   "segments_per_path": segments / max(1.0, main_leg["paths"]), "light_pdf_rays_per_segment": main_leg["lrays"] / max(1.0, segments),
+                   "exact_fallbacks_per_million_segments": 1e6 * main_leg["xf"] / max(1.0, segments)}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / max(1, args.steps), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": cfg,
+            "dtype": "f64", "data": "synthetic", "config": cfg, "details": details,
             "time_to_1024spp_s": strong["time_to_1024spp_s"] if strong else (ms * 1e-3) / max(1, args.steps) / (S * world if weak else S) * 1024,
             "strong": strong,
             "gpu_launches": main_leg["launches_rank0"],

@@ -7,6 +7,7 @@ import pytest
 import rtb200
 import rtb200.ctypes_types as T
 from rtb200.scene_desc import RawScene
+from tests import helpers
 
 pytestmark = pytest.mark.gpu
 
@@ -234,3 +235,26 @@ def test_tiny_images_and_regions(ctx, tmp_path, w, h):
     assert one[h - 1, w - 1].tobytes() == want[h - 1, w - 1].tobytes()
     one[h - 1, w - 1] = 0
     assert not one.any()
+
+
+def test_shared_memory_staging_of_the_top_levels_is_bitwise_the_same(tmp_path, monkeypatch):
+    """north_star's "shared-memory staging of the top BVH levels": the trace kernel instantiation that
+    copies the first levels of the fp32 hierarchy (breadth-first, 85 nodes) to shared memory is selected
+    with RT_WF_SMEM_TOP=1, read at rt_create.  It is off by default (measured slower on B200, DESIGN.md
+    §4) — and must give the same image bit for bit, with the same number of segments."""
+    path, _ = helpers.heightfield(tmp_path, 60, 90)
+    scene = rtb200.Scene.load_gltf(path, 160, 96, 6)
+    plain = rtb200.Context(0).upload(scene)
+    plain.reset_counters()
+    plain.render_accum(0, 6, 0x5EED, T.MODE_FAST, T.SCHED_WAVEFRONT, clear=True)
+    want, wc = plain.accum(), plain.counters()
+    plain.close()
+    monkeypatch.setenv("RT_WF_SMEM_TOP", "1")
+    staged = rtb200.Context(0).upload(scene)
+    monkeypatch.delenv("RT_WF_SMEM_TOP")
+    staged.reset_counters()
+    staged.render_accum(0, 6, 0x5EED, T.MODE_FAST, T.SCHED_WAVEFRONT, clear=True)
+    got, gc = staged.accum(), staged.counters()
+    staged.close()
+    assert want.sum() > 0 and got.tobytes() == want.tobytes()
+    assert gc["segments"] == wc["segments"] and gc["light_pdf_rays"] == wc["light_pdf_rays"]

@@ -1,7 +1,9 @@
 """Launch list (ncu --metrics ... --csv of the short bench command) -> profiles/<tag>_issue.json and
 profiles/<tag>_launch_summary.md: per-kernel time share, DRAM bytes, lanes per instruction, issue activity,
 and the per-SEGMENT instruction counts bench.py's issue roofline is computed from.
-usage: issue_summary.py <tag> <spp_per_render> [segments_per_path]"""
+usage: issue_summary.py <tag> <spp_per_render> [segments_per_path] [csv] [command]
+The launch list is gpurun_out/<tag>_launches.csv (the short bench command) or, with [csv], the list of one
+render written by tools/launch_list.sh."""
 import collections
 import csv
 import json
@@ -10,7 +12,8 @@ import sys
 tag, spp = sys.argv[1], int(sys.argv[2])
 seg_per_path = float(sys.argv[3]) if len(sys.argv) > 3 else 1.8330860533537687
 W, H = 1920, 1080
-rows = [r for r in csv.reader(open(f"gpurun_out/{tag}_launches.csv")) if len(r) > 10 and r[0].isdigit()]
+src = sys.argv[4] if len(sys.argv) > 4 else f"gpurun_out/{tag}_launches.csv"
+rows = [r for r in csv.reader(open(src)) if len(r) > 10 and r[0].isdigit()]
 launch = collections.OrderedDict()
 for r in rows:
     e = launch.setdefault(int(r[0]), {"k": r[4].split("(")[0].replace("void ", "")})
@@ -41,10 +44,10 @@ for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["ns"]):
         per_kernel[k] = {"time_share_of_wavefront": a["ns"] / sum(x["ns"] for x in wf.values()), "lanes_per_instruction": lanes,
                          "issue_active_pct": a["issue_x_t"] / max(1.0, a["ns"]), "warp_inst_per_segment": a["warp_inst"] / segments,
                          "thread_inst_per_segment": a["thread_inst"] / segments, "dram_bytes_per_segment": a["dram"] / segments}
-cmd = f"python bench.py --steps 2 --warmup 3 --spp-per-step {spp} --no-cpu-baseline --no-strong"
+cmd = sys.argv[5] if len(sys.argv) > 5 else f"python bench.py --steps 2 --warmup 3 --spp-per-step {spp} --no-cpu-baseline --no-strong"
 open(f"profiles/{tag}_launch_summary.md", "w").write(
     f"# {tag} launch list summary (ncu --metrics gpu__time_duration.sum,dram__bytes_*.sum,smsp__inst_executed.sum,... --clock-control none)\n\n"
-    f"command: `{cmd}` ({renders} wavefront renders of {spp} spp + the EXACT counter pass)\n\n"
+    f"command: `{cmd}` ({renders} wavefront render(s) of {spp} spp)\n\n"
     "kernel | launches | total ms | share | DRAM GB (read+write) | lanes/inst | issue active % (time-weighted)\n---|---|---|---|---|---|---\n" + "\n".join(lines) +
     "\n\nper-launch times are cold-cache and serialised by the profiler: compare SHARES, not absolutes.\n")
 out = {"source": f"profiles/{tag}_launches.csv ({cmd}): sums over every k_wf_* launch of {renders} render calls / {segments:.0f} path segments",
