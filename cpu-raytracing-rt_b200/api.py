@@ -44,9 +44,30 @@ def build(force=False):
     return _LIB_PATH
 
 
+def _pick_nccl():
+    """The library dlopen()s NCCL by its soname, which finds the SYSTEM copy.  In a Python process that also
+    imports PyTorch that is the wrong one: torch links against its own bundled (newer) libnccl.so.2, the
+    loader reuses whatever object of that soname is already in the process, and `import torch` then fails
+    with an undefined NCCL symbol.  So in Python the library is pointed at the copy torch would load
+    (RT_NCCL_LIB, read once at the first multi-GPU call); a C or Rust host keeps the system copy."""
+    if os.environ.get("RT_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for root in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(root, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["RT_NCCL_LIB"] = cand
+                return
+    except (ImportError, ValueError, AttributeError):
+        pass
+
+
 def lib():
     global _LIB
     if _LIB is None:
+        _pick_nccl()
         if not os.path.exists(_LIB_PATH):
             raise ImportError(f"{_LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                               "(there is no fallback implementation)")

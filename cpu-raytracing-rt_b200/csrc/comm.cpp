@@ -9,8 +9,10 @@
 //     broadcasts the 128 bytes, every rank calls rt_comm_init on its context, then rt_reduce_accum;
 //   * one process, all GPUs (the CLI): rt_group_* — ncclCommInitAll, one host thread per device
 //     while rendering, the same reduce.
-// NCCL is resolved at run time (dlopen "libnccl.so.2"): a single-GPU user needs no NCCL at all,
-// and inside a process that already carries NCCL (PyTorch) the same copy is used.
+// NCCL is resolved at run time (dlopen "libnccl.so.2", or the path in RT_NCCL_LIB): a single-GPU
+// user needs no NCCL at all.  A process that will ALSO load PyTorch must point RT_NCCL_LIB at torch's
+// bundled copy (the Python binding does): two libraries of one soname cannot coexist, and the first
+// one loaded wins.
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -51,7 +53,7 @@ const Nccl &nccl() {
         const char *names[3] = {std::getenv("RT_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
         for (const char *name : names) {
             if (!name || !*name) continue;
-            n.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            n.handle = dlopen(name, RTLD_NOW | RTLD_LOCAL);
             if (n.handle) break;
             n.why = dlerror();
         }
