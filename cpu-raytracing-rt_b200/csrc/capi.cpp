@@ -80,7 +80,7 @@ cudaError_t ensure_wavefront(rt_ctx *ctx) {
     b.side = (double4 *)take((size_t)n_img * 32 * ring);
     b.n_px_cap = n_img;
     b.item = (unsigned long long *)take(32);
-    b.plane = (uint32_t *)take(16);
+    b.plane = (uint32_t *)take(32);
     b.call = (WfCall *)take(sizeof(WfCall));
     if ((size_t)(p - ctx->wf_arena) > total) return cudaErrorMemoryAllocation;
     if (!ctx->wf_rt.side && (e = wf_runtime_init(ctx->wf_rt, ctx->device)) != cudaSuccess) return e;
@@ -558,6 +558,9 @@ void rt_destroy(rt_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     comm_release(ctx);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
+    if (ctx->h_rgb) cudaFreeHost(ctx->h_rgb);
     free_scene(ctx, false);
     if (ctx->d_ctr) cudaFree(ctx->d_ctr);
     wf_runtime_destroy(ctx->wf_rt);
@@ -767,14 +770,76 @@ int rt_render(rt_ctx *ctx, uint64_t seed, int mode, int sched, double *rgb_out) 
     if (int r = rt_render_accum(ctx, &p)) return r;
     return rt_postprocess(ctx, ctx->samples, rgb_out);
 }
+// what rt_render_accum would pick for this scene
+static void resolve_mode(const rt_ctx *ctx, int &mode, int &sched) {
+    const bool has_tris = ctx->dsc.tris.n_prims != 0;
+    if (mode == RT_MODE_AUTO) mode = has_tris ? RT_MODE_FAST : RT_MODE_EXACT;
+    if (mode == RT_MODE_FAST && !fast_usable(ctx)) { mode = RT_MODE_EXACT; sched = RT_SCHED_MEGAKERNEL; }
+    if (sched == RT_SCHED_AUTO) sched = (mode == RT_MODE_FAST && has_tris) ? RT_SCHED_WAVEFRONT : RT_SCHED_MEGAKERNEL;
+}
+struct ProgressiveShow {                // WfProgress::show: tonemap the samples in the buffer, hand the image to the caller
+    rt_ctx *ctx;
+    rt_progress_fn progress;
+    void *user;
+    double *rgb_out;
+    uint32_t total;
+    uint32_t *samples_done;
+    // tonemap on the render stream (behind the launches already queued), copy on a stream of its own: the
+    // host later waits for the copy only, the render stream goes on with the next chunk
+    static int prepare(void *self, uint32_t samples) {
+        ProgressiveShow *p = (ProgressiveShow *)self;
+        rt_ctx *ctx = p->ctx;
+        if (!ctx->copy_stream) {
+            if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return -1;
+            if (cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming) != cudaSuccess) return -1;
+        }
+        if (rt_postprocess(ctx, samples, nullptr) != RT_OK) return -1;
+        if (cudaEventRecord(ctx->ev_copy, ctx->stream) != cudaSuccess || cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy, 0) != cudaSuccess) return -1;
+        if (ctx->h_rgb_px != ctx->n_px) {
+            if (ctx->h_rgb) cudaFreeHost(ctx->h_rgb);
+            ctx->h_rgb = nullptr; ctx->h_rgb_px = 0;
+            if (cudaHostAlloc((void **)&ctx->h_rgb, ctx->n_px * 24, cudaHostAllocDefault) != cudaSuccess) return -1;
+            ctx->h_rgb_px = ctx->n_px;
+        }
+        if (cudaMemcpyAsync(ctx->h_rgb, ctx->d_rgb, ctx->n_px * 24, cudaMemcpyDeviceToHost, ctx->copy_stream) != cudaSuccess) return -1;
+        return 0;
+    }
+    static int show(void *self, uint32_t samples) {
+        ProgressiveShow *p = (ProgressiveShow *)self;
+        if (cudaStreamSynchronize(p->ctx->copy_stream) != cudaSuccess) return -1;
+        std::memcpy(p->rgb_out, p->ctx->h_rgb, p->ctx->n_px * 24);
+        if (p->samples_done) *p->samples_done = samples;
+        return (p->progress && p->progress(p->user, samples, p->total, p->rgb_out) != 0) ? 1 : 0;
+    }
+};
 int rt_render_progressive(rt_ctx *ctx, uint64_t seed, int mode, int sched, uint32_t chunk_samples, rt_progress_fn progress,
                           void *user, double *rgb_out, uint32_t *samples_done) {
     if (int r = need_scene(ctx)) return r;
     if (!rgb_out) return set_err(ctx, RT_ERR_INVALID_ARG, "null argument");
     if (chunk_samples == 0) return set_err(ctx, RT_ERR_INVALID_ARG, "chunk_samples must be positive");
     const uint32_t total = ctx->samples;
-    uint32_t done = 0;
     if (samples_done) *samples_done = 0;
+    int rmode = mode, rsched = sched;
+    resolve_mode(ctx, rmode, rsched);
+    if (rsched == RT_SCHED_WAVEFRONT && rmode == RT_MODE_FAST && ctx->dsc.ray_depth > 0 && total > 0) {
+        // ONE render call: the wavefront scheduler holds its ordered sums at each chunk boundary while the next
+        // chunk's paths are already in flight (WfProgress), so a chunk costs no pipeline drain and refill
+        if (int r = check_mode(ctx, rmode)) return r;
+        CK(ctx, cudaMemsetAsync(ctx->d_accum, 0, ctx->n_px * 3 * sizeof(double), ctx->stream));
+        CK(ctx, ensure_wavefront(ctx));
+        ProgressiveShow ps{ctx, progress, user, rgb_out, total, samples_done};
+        WfProgress wp;
+        wp.chunk = chunk_samples; wp.prepare = &ProgressiveShow::prepare; wp.show = &ProgressiveShow::show; wp.user = &ps;
+        const DRegion rg{0u, 0u, ctx->dsc.width, ctx->dsc.height};
+        CK(ctx, launch_render_wavefront(ctx->stream, ctx->wf_rt, ctx->dsc, 0u, total, seed, ctx->d_accum, ctx->d_ctr, ctx->wf,
+                                        ctx->wf_blocks, &ctx->launches, rg, &wp));
+        if (wp.samples_done < total) { CK(ctx, cudaStreamSynchronize(ctx->stream)); return RT_OK; }      // the callback stopped the render: rgb_out holds that image
+        if (int r = rt_postprocess(ctx, total, rgb_out)) return r;
+        if (samples_done) *samples_done = total;
+        if (progress) progress(user, total, total, rgb_out);
+        return RT_OK;
+    }
+    uint32_t done = 0;
     do {                                            // samples == 0 still clears and tonemaps once, like rt_render
         rt_render_params p{};
         p.sample_begin = done;

@@ -33,6 +33,10 @@ struct rt_ctx {
     // experiment knobs, read ONCE at rt_create (never on the render path)
     uint64_t knob_cap = 0;
     uint32_t knob_ring = rt::kWfRing, knob_batch = 4;
+    cudaStream_t copy_stream = nullptr; // progressive output: the image of a chunk goes to the host while the next chunk renders
+    cudaEvent_t ev_copy = nullptr;
+    double *h_rgb = nullptr;            // page-locked staging image of that copy (a copy into pageable memory would not overlap anything)
+    size_t h_rgb_px = 0;
     rt_comm *comm = nullptr;            // set by rt_comm_init / rt_group_create, torn down in rt_destroy
 };
 

@@ -81,7 +81,7 @@ struct WfBuf {
     WfCall *call;                       // device: the parameters of the render call in flight (written by k_wf_init)
     double4 *side;                      // ring * n_px: radiance of finished samples (x, y, z, -): plane (sample % ring), ordinal — one sector each
     unsigned long long *item;           // [0] next unclaimed item, [1] claim limit, [2] items of this call, [3] items taken in this iteration
-    uint32_t *plane;                    // [0] planes added to accum, [1] oldest sample in flight, [2] ring, [3] planes complete
+    uint32_t *plane;                    // [0] planes added to accum, [1] oldest sample in flight, [2] ring, [3] planes complete, [4] stop line of a progressive render
 };
 size_t wf_bytes_per_slot();
 // Slots a render of n_px pixels uses: twice the pixels for small images (fewer, fuller iterations: the
@@ -116,9 +116,22 @@ struct WfRuntime {
 };
 cudaError_t wf_runtime_init(WfRuntime &rt, int device);
 void wf_runtime_destroy(WfRuntime &rt);
+// Progressive output without draining the pipeline between chunks: the ordered plane sums are held at
+// the end of the chunk about to be shown while the paths of the next chunk are already in flight; `show`
+// is called (on the host, between graph launches) when the accumulation buffer holds exactly `samples`
+// samples of every pixel.  It returns 0 to go on, > 0 to stop the render there, < 0 on error.
+// `prepare` runs first and only ENQUEUES (tonemap, copy to the host); the launcher then queues the next
+// group of iterations before `show` waits for the image, so the device never runs dry.
+struct WfProgress {
+    uint32_t chunk = 0;                 // samples per chunk (0: no progressive output)
+    int (*prepare)(void *user, uint32_t samples) = nullptr;
+    int (*show)(void *user, uint32_t samples) = nullptr;
+    void *user = nullptr;
+    mutable uint32_t samples_done = 0;  // out: samples in the buffer when the call returned
+};
 cudaError_t launch_render_wavefront(cudaStream_t st, WfRuntime &rt, const DScene &sc, uint32_t sample_begin, uint32_t sample_count,
                                     uint64_t seed, double *accum, DCounters *ctr, const WfBuf &b, int trace_blocks,
-                                    uint64_t *launches, DRegion rg);
+                                    uint64_t *launches, DRegion rg, const WfProgress *progress = nullptr);
 
 cudaError_t launch_postprocess(cudaStream_t st, uint64_t n, const double *accum, uint32_t samples, double *rgb);
 cudaError_t launch_rng_probe(cudaStream_t st, uint64_t seed, uint32_t pixel, uint32_t sample, uint64_t n,

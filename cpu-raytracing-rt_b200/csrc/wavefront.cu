@@ -187,7 +187,7 @@ RT_D uint32_t region_tile_pixel(const DRegion &rg, uint32_t width, uint32_t i) {
     const uint32_t tx = r / (8u * ht), l = r - tx * 8u * ht, wt = min(8u, rg.w - 8u * tx);
     return (rg.y0 + 4u * ty + l / wt) * width + rg.x0 + 8u * tx + l % wt;
 }
-__global__ void k_wf_init(WfBuf b, WfCall cl, uint32_t sample_count) {
+__global__ void k_wf_init(WfBuf b, WfCall cl, uint32_t sample_count, uint32_t first_stop) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_px = cl.n_px;
     if (i < cl.n_slots) st_head_item(b.head + i, make_uint4(0u, kNoShape, 0u, 0u), make_uint4(0u, 0u, 0u, 0u));      // an empty slot: the first confirm pass sends it to k_wf_regen
@@ -196,7 +196,7 @@ __global__ void k_wf_init(WfBuf b, WfCall cl, uint32_t sample_count) {
         for (int k = 0; k < kCntWords; ++k) b.counts[k] = 0;
         const unsigned long long total = (unsigned long long)n_px * sample_count, first = (unsigned long long)(b.ring - cl.reserve) * n_px;
         b.item[0] = 0; b.item[1] = first < total ? first : total; b.item[2] = total; b.item[3] = 0;
-        b.plane[0] = 0; b.plane[1] = 0xFFFFFFFFu; b.plane[2] = b.ring; b.plane[3] = 0;
+        b.plane[0] = 0; b.plane[1] = 0xFFFFFFFFu; b.plane[2] = b.ring; b.plane[3] = 0; b.plane[4] = first_stop;
     }
 }
 
@@ -590,9 +590,14 @@ __global__ void k_wf_plan(WfBuf b) {
     const unsigned long long claimed = next / n_px;     // planes whose items have all been handed out
     const uint32_t oldest = b.plane[1];
     uint32_t upto = (uint32_t)min(claimed, (unsigned long long)oldest);
+    // a progressive render holds the sums at the end of the chunk the host is about to show (plane[4]) while
+    // the paths of the next chunk are already in flight: the buffer then holds exactly that many samples
+    const uint32_t stop = b.plane[4];
+    const bool held = upto >= stop;
+    if (held) upto = stop;
     // batches of four planes amortise the read-modify-write of the accumulation buffer; at the end
     // of the call (nothing left to claim) everything that is complete goes
-    if (upto < summed + b.batch && next < total) upto = summed;
+    if (upto < summed + b.batch && next < total && !held) upto = summed;
     if (upto < summed) upto = summed;
     b.plane[3] = upto;
     // b.reserve planes of the ring stay free (headroom; the regen passes never take an item past the limit)
@@ -919,7 +924,7 @@ cudaError_t wf_runtime_init(WfRuntime &rt, int device) {
     for (cudaEvent_t *ev : evs)
         if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return e;
     uint32_t *host = nullptr;
-    if ((e = cudaHostAlloc((void **)&host, 8 * sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess) return e;
+    if ((e = cudaHostAlloc((void **)&host, 16 * sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess) return e;
     rt.host_live = host;
     return cudaSuccess;
 }
@@ -943,7 +948,7 @@ constexpr int kLaunchesPerIter = 8;         // confirm, exact, shade_hit, regen 
 
 cudaError_t launch_render_wavefront(cudaStream_t st, WfRuntime &rt, const DScene &sc, uint32_t sample_begin, uint32_t sample_count,
                                     uint64_t seed, double *accum, DCounters *ctr, const WfBuf &b, int trace_blocks,
-                                    uint64_t *launches, DRegion rg) {
+                                    uint64_t *launches, DRegion rg, const WfProgress *progress) {
     const uint32_t n_px = rg.w * rg.h;
     const unsigned long long total_items = (unsigned long long)n_px * sample_count;
     // Slots are independent of pixels: all of the buffer's capacity is used, but never more than
@@ -965,7 +970,10 @@ cudaError_t launch_render_wavefront(cudaStream_t st, WfRuntime &rt, const DScene
     // The grids cover the buffer's CAPACITY (blocks past the slots in use, or past the end of a
     // list, leave at once), so the launch configuration does not depend on the call either.
     const unsigned blocks = (b.n + 127) / 128;
-    k_wf_init<<<(cl.n_slots + 127) / 128, 128, 0, st>>>(b, cl, sample_count);
+    // progressive: the sums stop at `stop` samples until the host has shown that image (WfProgress)
+    const uint32_t chunk = progress && progress->chunk ? progress->chunk : 0u;
+    uint32_t stop = chunk && chunk < sample_count ? chunk : 0xFFFFFFFFu;
+    k_wf_init<<<(cl.n_slots + 127) / 128, 128, 0, st>>>(b, cl, sample_count, stop);
     ++*launches;
     // a segment takes one iteration, two when it is deferred to k_wf_exact; an item can wait for
     // a free plane of the ring: generous bound, reaching it is reported as an error
@@ -1024,8 +1032,11 @@ cudaError_t launch_render_wavefront(cudaStream_t st, WfRuntime &rt, const DScene
     }
     const bool use_graph = rt.exec != nullptr;
     volatile uint32_t *host_live = rt.host_live;
+    volatile uint32_t *host_stop = rt.host_live + 7;       // pinned staging word for the stop line
+    uint32_t stopped_at = 0;                                // the callback asked to stop after this many samples
     bool poll_pending = false, finished = false;
     cudaError_t result = cudaSuccess;
+    uint32_t showing = 0;                                   // a chunk image is on its way to the host (prepare done, show pending)
     for (uint64_t it = 0; it < max_iters; it += kGraphIters) {
         if (use_graph) {
             result = cudaGraphLaunch(rt.exec, st);
@@ -1034,20 +1045,39 @@ cudaError_t launch_render_wavefront(cudaStream_t st, WfRuntime &rt, const DScene
             for (int k = 0; k < kGraphIters; ++k) issue_iteration();
         }
         *launches += kGraphIters * kLaunchesPerIter;
+        if (showing) {
+            // the image was enqueued before the group just launched: wait for it and hand it over while that group runs
+            const int rc = progress->show(progress->user, showing);
+            if (rc < 0) { result = cudaErrorUnknown; break; }
+            if (rc > 0) { stopped_at = showing; finished = true; break; }
+            showing = 0;
+            stop = stop + chunk < sample_count ? stop + chunk : 0xFFFFFFFFu;
+            *host_stop = stop;
+            cudaMemcpyAsync(&b.plane[4], (const void *)host_stop, sizeof(uint32_t), cudaMemcpyHostToDevice, st);
+        }
         // poll the state after the PREVIOUS group of four without stalling the stream: nothing
         // traced, nothing deferred and nothing left to claim means the call is done
         if (poll_pending) {
             result = cudaEventSynchronize(rt.ev_poll);
             if (result != cudaSuccess) break;
             const unsigned long long next = (unsigned long long)host_live[4] | ((unsigned long long)host_live[5] << 32);
-            if (host_live[kCntFront] + host_live[kCntBack] + host_live[kCntExact] == 0 && next >= total_items) { finished = true; break; }
+            if (stop == 0xFFFFFFFFu && host_live[kCntFront] + host_live[kCntBack] + host_live[kCntExact] == 0 && next >= total_items) { finished = true; break; }
+            if (stop != 0xFFFFFFFFu && !showing && host_live[6] >= stop) {
+                // The accumulation buffer holds exactly `stop` samples of every pixel and will not change until
+                // the stop line moves: tonemap + copy are enqueued now, the next group of iterations behind
+                // them (the paths of the next chunk are in flight), and the image is handed over while it runs.
+                if (progress->prepare(progress->user, stop) < 0) { result = cudaErrorUnknown; break; }
+                showing = stop;
+            }
         }
         cudaMemcpyAsync((void *)host_live, b.counts, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
         cudaMemcpyAsync((void *)(host_live + 4), b.item, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync((void *)(host_live + 6), &b.plane[3], sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
         cudaEventRecord(rt.ev_poll, st);
         poll_pending = true;
     }
-    if (result == cudaSuccess) {
+    if (progress) progress->samples_done = stopped_at ? stopped_at : sample_count;
+    if (result == cudaSuccess && !stopped_at) {
         // the planes completed by the last iterations (k_wf_plan sees no path in flight and nothing
         // left to claim, so everything that remains goes)
         for (int k = 0; k < 2; ++k) {
