@@ -546,8 +546,6 @@ int rt_create(int device_id, rt_ctx **out) {
     // k_wf_plan only moves on when `batch` planes are complete, and at most ring - reserve (reserve <= 4)
     // planes are ever open: a larger batch would never be reached
     if (ctx->knob_batch > ctx->knob_ring - 4u) ctx->knob_batch = ctx->knob_ring - 4u;
-    if (const char *e = std::getenv("RT_WF_SHADE_BLOCKS")) { const int v = std::atoi(e); if (v >= 1 && v <= 32) ctx->wf_rt.shade_blocks = 148u * (unsigned)v; }
-    if (const char *e = std::getenv("RT_WF_REGEN_BLOCKS")) { const int v = std::atoi(e); if (v >= 1 && v <= 32) ctx->wf_rt.regen_blocks = 148u * (unsigned)v; }
     if (const char *e = std::getenv("RT_WF_SMEM_TOP")) ctx->wf_rt.smem_top = std::atoi(e) != 0;
     if (const char *e = std::getenv("RT_WF_SLOTS")) { const long long v = std::atoll(e); if (v >= 1024) ctx->wf_rt.slots_override = (uint64_t)v; }
     *out = ctx.release();

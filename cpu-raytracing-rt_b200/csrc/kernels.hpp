@@ -107,8 +107,6 @@ struct WfRuntime {
     double *key_accum = nullptr;
     DCounters *key_ctr = nullptr;
     int key_blocks = 0;
-    unsigned key_grid[2] = {0, 0};
-    unsigned shade_blocks = 0, regen_blocks = 0;       // grids of k_wf_shade_hit / k_wf_regen (RT_WF_SHADE_BLOCKS / RT_WF_REGEN_BLOCKS per SM override, experiments)
     volatile uint32_t *host_live = nullptr;     // pinned, 6 words: what the host polls (counts[0..3], next item)
     uint64_t slots_override = 0;        // RT_WF_SLOTS (experiments), read once at rt_create
     bool smem_top = false;              // RT_WF_SMEM_TOP=1: the trace kernel stages the top levels of the hierarchy in shared memory

@@ -361,14 +361,12 @@ __global__ void __launch_bounds__(128, WF_CONFIRM_MINB) k_wf_confirm(DScene sc, 
 #endif
 template <bool SHAPES>
 __global__ void __launch_bounds__(128, SHAPES ? 4 : WF_SHADE_MINB) k_wf_shade_hit(DScene sc, WfBuf b, DCounters *ctr) {
-    // the list in chunks of 128 entries (one chunk per block unless RT_WF_SHADE_BLOCKS bounds the grid)
     const uint32_t n = b.counts[kCntHit];
-    if (blockIdx.x * 128u >= n) return;
+    if (blockIdx.x * 128u >= n) return;                 // the grid covers the buffer's capacity
     __shared__ BlockShared s_blk;
     block_shared_init(s_blk);
     Cnt c;
-    for (uint32_t chunk = blockIdx.x * 128u; chunk < n; chunk += gridDim.x * 128u) {
-    const uint32_t i = chunk + threadIdx.x;
+    const uint32_t i = blockIdx.x * 128u + threadIdx.x;
     const bool on = i < n;
     // The lanes of a warp part ways twice — a pending weight or none, light sampling or cosine sampling —
     // and left to itself the compiler keeps the four groups apart until the end of the kernel (ncu: 12.5 of
@@ -460,8 +458,6 @@ __global__ void __launch_bounds__(128, SHAPES ? 4 : WF_SHADE_MINB) k_wf_shade_hi
     if (go_on) b.live[b.n - 1u - pos_back] = slot;
     if (ended) b.regen_list[1][pos_regen] = slot;
     block_note_oldest(s_blk, go_on, smp);
-    __syncthreads();                                    // block_append2's shared words are reused by the next chunk
-    }
     block_count(s_blk, c);
     block_shared_flush(s_blk, ctr, &b.plane[1]);
 }
@@ -512,8 +508,7 @@ __global__ void __launch_bounds__(128, SHAPES ? 4 : 8) k_wf_regen(DScene sc, WfB
     const WfCall cl = *b.call;                          // uniform: one broadcast load
     const uint32_t n_px = cl.n_px;
     Cnt c;
-    for (uint32_t chunk = blockIdx.x * 128u; chunk < n; chunk += gridDim.x * 128u) {
-    const uint32_t i = chunk + threadIdx.x;
+    const uint32_t i = blockIdx.x * 128u + threadIdx.x;
     const bool on = i < n;
     if (on) {
         const uint32_t slot = b.regen_list[pass][i];
@@ -571,7 +566,6 @@ __global__ void __launch_bounds__(128, SHAPES ? 4 : 8) k_wf_regen(DScene sc, WfB
         } else if (old_flags != 0u) {
             b.head[slot].flags = 0u;                    // nothing to take right now: an empty slot, asks again in the next iteration
         }
-    }
     }
     block_count(s_blk, c);
     block_shared_flush(s_blk, ctr, &b.plane[1]);
@@ -909,15 +903,7 @@ int wf_trace_blocks(int device, bool smem_top) {
 }
 cudaError_t wf_runtime_init(WfRuntime &rt, int device) {
     cudaError_t e;
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    // Both list kernels run best with the whole list in flight (one block per 128 entries).  Measured on B200 (C3,
-    // Mseg/s) with bounded grids of shade x regen blocks per SM, which keep the two kernels resident side by
-    // side: 3x2 1370, 3x3 1359, 4x3 1401, 5x3 1427, 6x8 1444, unbounded 1451 — each kernel needs all the
-    // warps it can get to hide its own memory latency; sharing the SMs costs more than the overlap returns.
-    (void)sms;
-    if (!rt.shade_blocks) rt.shade_blocks = 0xFFFFFFFFu;
-    if (!rt.regen_blocks) rt.regen_blocks = 0x7FFFFFFFu;
+    (void)device;
     if ((e = cudaStreamCreateWithFlags(&rt.side, cudaStreamNonBlocking)) != cudaSuccess) return e;
     if ((e = cudaStreamCreateWithFlags(&rt.side2, cudaStreamNonBlocking)) != cudaSuccess) return e;
     cudaEvent_t *evs[5] = {&rt.ev_fork, &rt.ev_shade, &rt.ev_join, &rt.ev_poll, &rt.ev_regen};
@@ -994,11 +980,11 @@ cudaError_t launch_render_wavefront(cudaStream_t st, WfRuntime &rt, const DScene
         cudaStreamWaitEvent(rt.side2, rt.ev_fork, 0);
         k_wf_exact<<<64, 128, 0, rt.side>>>(sc, b);
         if (shapes) {
-            k_wf_regen<true><<<std::min(blocks, rt.regen_blocks), 128, 0, rt.side2>>>(sc, b, ctr, 0);
-            k_wf_shade_hit<true><<<std::min(blocks, rt.shade_blocks), 128, 0, st>>>(sc, b, ctr);
+            k_wf_regen<true><<<blocks, 128, 0, rt.side2>>>(sc, b, ctr, 0);
+            k_wf_shade_hit<true><<<blocks, 128, 0, st>>>(sc, b, ctr);
         } else {
-            k_wf_regen<false><<<std::min(blocks, rt.regen_blocks), 128, 0, rt.side2>>>(sc, b, ctr, 0);
-            k_wf_shade_hit<false><<<std::min(blocks, rt.shade_blocks), 128, 0, st>>>(sc, b, ctr);
+            k_wf_regen<false><<<blocks, 128, 0, rt.side2>>>(sc, b, ctr, 0);
+            k_wf_shade_hit<false><<<blocks, 128, 0, st>>>(sc, b, ctr);
         }
         cudaEventRecord(rt.ev_regen, rt.side2);
         cudaStreamWaitEvent(st, rt.ev_regen, 0);
@@ -1013,14 +999,13 @@ cudaError_t launch_render_wavefront(cudaStream_t st, WfRuntime &rt, const DScene
         else k_wf_trace<false><<<trace_blocks, 128, 0, st>>>(sc, b, ctr);
         cudaStreamWaitEvent(st, rt.ev_join, 0);
     };
-    const bool same_key = rt.tried_graph && rt.key_grid[0] == rt.shade_blocks && rt.key_grid[1] == rt.regen_blocks && std::memcmp(&rt.key_sc, &sc, sizeof sc) == 0 && std::memcmp(&rt.key_b, &b, sizeof b) == 0 &&
+    const bool same_key = rt.tried_graph && std::memcmp(&rt.key_sc, &sc, sizeof sc) == 0 && std::memcmp(&rt.key_b, &b, sizeof b) == 0 &&
                           rt.key_accum == accum && rt.key_ctr == ctr && rt.key_blocks == trace_blocks;
     if (!same_key) {
         wf_drop_graph(rt);
         std::memcpy(&rt.key_sc, &sc, sizeof sc);
         std::memcpy(&rt.key_b, &b, sizeof b);
         rt.key_accum = accum; rt.key_ctr = ctr; rt.key_blocks = trace_blocks;
-        rt.key_grid[0] = rt.shade_blocks; rt.key_grid[1] = rt.regen_blocks;
         rt.tried_graph = true;
         if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
             for (int k = 0; k < kGraphIters; ++k) issue_iteration();
