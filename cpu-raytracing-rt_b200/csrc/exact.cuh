@@ -300,14 +300,11 @@ RT_D Best closest_exact_walk(const DBvh bvh, const void *prims, d3 o, d3 d, Cnt 
         }
     }
 }
-template <int KIND>
-static __device__ __noinline__ Best closest_exact_deep(const DBvh bvh, const void *prims, d3 o, d3 d, Cnt &c) {
-    return closest_exact_walk<KIND, true>(bvh, prims, o, d, c);
-}
-template <int KIND>
+// DEEP is a COMPILE-TIME choice of the kernel (kernels.cu launches the ...Deep instantiations when some
+// hierarchy of the scene is deeper than the stack): the ordinary kernels carry no trace of the stackless walk.
+template <int KIND, bool DEEP = false>
 RT_D Best closest_exact(const DBvh bvh, const void *prims, d3 o, d3 d, Cnt &c) {
-    if (bvh.parent) return closest_exact_deep<KIND>(bvh, prims, o, d, c);      // uniform, cold: trees deeper than the stack
-    return closest_exact_walk<KIND, false>(bvh, prims, o, d, c);
+    return closest_exact_walk<KIND, DEEP>(bvh, prims, o, d, c);
 }
 
 // ---- intersections::intersect, reference src/intersections.rs:42-85 --------------------------
@@ -325,6 +322,7 @@ RT_D void finish_shape_hit(const DShape *sp, d3 o, d3 d, SceneHit &h) {
     const d3 w = unit3(qrot(s.rot, n));                   // with_rotated_normal, :31-40
     h.ng = w; h.ns = w; h.inside = in; h.material = s.material;
 }
+template <bool DEEP = false>
 RT_D SceneHit intersect_exact(const DScene &sc, d3 o, d3 d, Cnt &c) {
     SceneHit h;
     h.kind = -1; h.prim = 0; h.material = 0; h.t = 0.0; h.inside = false;
@@ -336,11 +334,11 @@ RT_D SceneHit intersect_exact(const DScene &sc, d3 o, d3 d, Cnt &c) {
         if (!shape_closest(load_shape(sc.planes + i), o, d, t, n, in)) continue;
         if (!has || t < h.t) { has = true; h.t = t; h.kind = 0; h.prim = i; }
     }
-    const Best b = closest_exact<1>(sc.boxes, sc.box_prims, o, d, c);       // :51
+    const Best b = closest_exact<1, DEEP>(sc.boxes, sc.box_prims, o, d, c); // :51
     if (b.has && (!has || b.t < h.t)) { has = true; h.t = b.t; h.kind = 1; h.prim = b.prim; }
-    const Best e = closest_exact<2>(sc.ellipsoids, sc.ell_prims, o, d, c);  // :52
+    const Best e = closest_exact<2, DEEP>(sc.ellipsoids, sc.ell_prims, o, d, c);  // :52
     if (e.has && (!has || e.t < h.t)) { has = true; h.t = e.t; h.kind = 2; h.prim = e.prim; }
-    const Best t3 = closest_exact<3>(sc.tris, sc.tri_i, o, d, c);           // :53
+    const Best t3 = closest_exact<3, DEEP>(sc.tris, sc.tri_i, o, d, c);     // :53
     if (t3.has && (!has || t3.t < h.t)) { has = true; h.t = t3.t; h.kind = 3; h.prim = t3.prim; }
     if (!has) return h;
     if (!(h.t * len3(d) <= dinf())) { h.kind = -1; return h; }             // :56 (false only for NaN)
@@ -449,22 +447,18 @@ RT_D void light_hits_exact_walk(const DBvh bvh, const void *prims, const DTriS *
         }
     }
 }
-template <int KIND>
-static __device__ __noinline__ void light_hits_exact_deep(const DBvh bvh, const void *prims, const DTriS *tri_s, d3 o, d3 d, double &impact, Cnt &c) {
-    light_hits_exact_walk<KIND, true>(bvh, prims, tri_s, o, d, impact, c);
-}
-template <int KIND>
+template <int KIND, bool DEEP = false>
 RT_D void light_hits_exact(const DBvh bvh, const void *prims, const DTriS *tri_s, d3 o, d3 d, double &impact, Cnt &c) {
-    if (bvh.parent) { light_hits_exact_deep<KIND>(bvh, prims, tri_s, o, d, impact, c); return; }
-    light_hits_exact_walk<KIND, false>(bvh, prims, tri_s, o, d, impact, c);
+    light_hits_exact_walk<KIND, DEEP>(bvh, prims, tri_s, o, d, impact, c);
 }
 // o = pos + EPSILON * dir (ray_sampler.rs:133) is formed by the caller
+template <bool DEEP = false>
 RT_D double light_pdf_exact(const DScene &sc, d3 o, d3 dir, Cnt &c) {
     double impact = 0.0;
     ++c.lray;
-    light_hits_exact<1>(sc.lboxes, sc.lbox_prims, nullptr, o, dir, impact, c);
-    light_hits_exact<2>(sc.lellipsoids, sc.lell_prims, nullptr, o, dir, impact, c);
-    light_hits_exact<3>(sc.ltris, sc.ltri_i, sc.ltri_s, o, dir, impact, c);
+    light_hits_exact<1, DEEP>(sc.lboxes, sc.lbox_prims, nullptr, o, dir, impact, c);
+    light_hits_exact<2, DEEP>(sc.lellipsoids, sc.lell_prims, nullptr, o, dir, impact, c);
+    light_hits_exact<3, DEEP>(sc.ltris, sc.ltri_i, sc.ltri_s, o, dir, impact, c);
     return impact / (double)sc.n_lights;
 }
 

@@ -172,11 +172,17 @@ __global__ void k_rng_probe(unsigned long long seed, uint32_t pixel, uint32_t sa
 
 // ---- launchers ----------------------------------------------------------------------------------
 static inline unsigned blocks_for(unsigned long long n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
+// a hierarchy deeper than the traversal stack was uploaded with parent links: the stackless instantiations serve (EXACT only:
+// FAST requests on such a scene are turned into EXACT ones by the C ABI)
+static inline bool deep(const DScene &sc) {
+    return sc.boxes.parent || sc.ellipsoids.parent || sc.tris.parent || sc.lboxes.parent || sc.lellipsoids.parent || sc.ltris.parent;
+}
 
 cudaError_t launch_trace_rays(cudaStream_t st, const DScene &sc, int mode, uint64_t n, const double *o, const double *d,
                               void *hits, DCounters *ctr) {
     if (n == 0) return cudaSuccess;
     if (mode == RT_MODE_FAST) k_trace_rays<FastPolicy><<<blocks_for(n, 128), 128, 0, st>>>(sc, n, o, d, (rt_hit *)hits, ctr);
+    else if (deep(sc)) k_trace_rays<ExactDeepPolicy><<<blocks_for(n, 128), 128, 0, st>>>(sc, n, o, d, (rt_hit *)hits, ctr);
     else k_trace_rays<ExactPolicy><<<blocks_for(n, 128), 128, 0, st>>>(sc, n, o, d, (rt_hit *)hits, ctr);
     return cudaGetLastError();
 }
@@ -184,6 +190,7 @@ cudaError_t launch_trace_primary(cudaStream_t st, const DScene &sc, int mode, do
                                  double *rays, DCounters *ctr) {
     const unsigned n = tile_grid_threads(sc.width, sc.height);
     if (mode == RT_MODE_FAST) k_trace_primary<FastPolicy><<<blocks_for(n, 128), 128, 0, st>>>(sc, jx, jy, (rt_hit *)hits, rays, ctr);
+    else if (deep(sc)) k_trace_primary<ExactDeepPolicy><<<blocks_for(n, 128), 128, 0, st>>>(sc, jx, jy, (rt_hit *)hits, rays, ctr);
     else k_trace_primary<ExactPolicy><<<blocks_for(n, 128), 128, 0, st>>>(sc, jx, jy, (rt_hit *)hits, rays, ctr);
     return cudaGetLastError();
 }
@@ -191,6 +198,7 @@ cudaError_t launch_light_pdf(cudaStream_t st, const DScene &sc, int mode, uint64
                              double *pdf, DCounters *ctr) {
     if (n == 0) return cudaSuccess;
     if (mode == RT_MODE_FAST) k_light_pdf<FastPolicy><<<blocks_for(n, 128), 128, 0, st>>>(sc, n, pos, dir, pdf, ctr);
+    else if (deep(sc)) k_light_pdf<ExactDeepPolicy><<<blocks_for(n, 128), 128, 0, st>>>(sc, n, pos, dir, pdf, ctr);
     else k_light_pdf<ExactPolicy><<<blocks_for(n, 128), 128, 0, st>>>(sc, n, pos, dir, pdf, ctr);
     return cudaGetLastError();
 }
@@ -198,6 +206,7 @@ cudaError_t launch_render_mega(cudaStream_t st, const DScene &sc, int mode, uint
                                uint64_t seed, double *accum, DCounters *ctr, DRegion rg) {
     const unsigned n = tile_grid_threads(rg.w, rg.h);
     if (mode == RT_MODE_FAST) k_render_mega<FastPolicy><<<blocks_for(n, 128), 128, 0, st>>>(sc, sample_begin, sample_count, seed, accum, ctr, rg);
+    else if (deep(sc)) k_render_mega<ExactDeepPolicy><<<blocks_for(n, 128), 128, 0, st>>>(sc, sample_begin, sample_count, seed, accum, ctr, rg);
     else k_render_mega<ExactPolicy><<<blocks_for(n, 128), 128, 0, st>>>(sc, sample_begin, sample_count, seed, accum, ctr, rg);
     return cudaGetLastError();
 }

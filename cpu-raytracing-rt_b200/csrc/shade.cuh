@@ -288,9 +288,12 @@ RT_D bool bounce(const DScene &sc, d3 &o, d3 &d, d3 &T, d3 &L, Rng &rng, Cnt &c)
     return apply_pending(pd, POLICY::light_pdf_ray(sc, o, d, c), T);
 }
 
-struct ExactPolicy {
-    RT_D static SceneHit intersect(const DScene &sc, d3 o, d3 d, Cnt &c) { return intersect_exact(sc, o, d, c); }
-    RT_D static double light_pdf_ray(const DScene &sc, d3 o, d3 dir, Cnt &c) { return light_pdf_exact(sc, o, dir, c); }
+template <bool DEEP>
+struct ExactPolicyT {                   // DEEP: some hierarchy of the scene is deeper than the traversal stack (exact.cuh)
+    RT_D static SceneHit intersect(const DScene &sc, d3 o, d3 d, Cnt &c) { return intersect_exact<DEEP>(sc, o, d, c); }
+    RT_D static double light_pdf_ray(const DScene &sc, d3 o, d3 dir, Cnt &c) { return light_pdf_exact<DEEP>(sc, o, dir, c); }
 };
+using ExactPolicy = ExactPolicyT<false>;
+using ExactDeepPolicy = ExactPolicyT<true>;
 
 }  // namespace rt
