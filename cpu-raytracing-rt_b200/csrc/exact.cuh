@@ -352,7 +352,7 @@ RT_D SceneHit intersect_exact(const DScene &sc, d3 o, d3 d, Cnt &c) {
         const quat ident = mkq_xyzw(0.0, 0.0, 0.0, 1.0);
         h.ng = unit3(qrot(ident, ng));
         h.ns = unit3(qrot(ident, ns));
-        h.material = __ldg(&sc.tri_i[h.prim].material);
+        h.material = __ldg(&sc.tri_s[h.prim].material);         // same value as in the intersect record, on the line tri_finish just read
     } else {
         const DShape *sp = h.kind == 0 ? sc.planes + h.prim : (h.kind == 1 ? sc.box_prims + h.prim : sc.ell_prims + h.prim);
         finish_shape_hit(sp, o, d, h);
